@@ -1,0 +1,193 @@
+"""Synthetic problem generators.
+
+The reference ships no data sets and no Stiefel / Rayleigh problems; these
+generators define the synthetic inputs every test and benchmark uses.  All
+randomness comes from a counter-based splitmix64 stream (index -> value), so
+any slice of any array can be regenerated independently and identically on
+every rank of a sharded run.  Pure numpy: the SAME arrays are handed to the CPU
+oracle and to the CUDA path.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(seed: int, idx: np.ndarray) -> np.ndarray:
+    """Counter-based generator: value = mix(seed * golden + idx)."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + idx.astype(np.uint64)
+             + np.uint64(0x632BE59BD9B4E019))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def uniform01(seed: int, start: int, count: int) -> np.ndarray:
+    """count doubles in [0,1), stream positions start .. start+count-1."""
+    idx = np.arange(start, start + count, dtype=np.uint64)
+    return (splitmix64(seed, idx) >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+
+
+def gaussish(seed: int, start: int, count: int) -> np.ndarray:
+    """Zero-mean unit-variance bell-shaped samples (sum of 4 uniforms; no libm)."""
+    acc = np.zeros(count)
+    for k in range(4):
+        acc += uniform01(seed * 4 + k + 1000003, start, count)
+    return (acc - 2.0) * np.sqrt(3.0)
+
+
+def to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float -> bf16 bit pattern; asserts the values are exactly representable."""
+    f = np.ascontiguousarray(x, dtype=np.float32)
+    bits = f.view(np.uint32)
+    assert np.all((bits & np.uint32(0xFFFF)) == 0), "value not on the bf16 grid"
+    return (bits >> np.uint32(16)).astype(np.uint16)
+
+
+def from_bf16_bits(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint32) << np.uint32(16)).view(np.float32).astype(np.float64)
+
+
+@dataclasses.dataclass
+class StiefelProblem:
+    """Trace minimisation f(Y) = 1/2 tr(Y^T A Y) on St(n, p), A block-diagonal.
+
+    A: nblk blocks of nb x nb, symmetric, every entry exactly bf16-representable
+    (so bf16 storage is lossless and the CPU oracle holds the same matrix in
+    double).  Rows of the last block beyond n are zero.
+    """
+    n: int
+    p: int
+    nb: int
+    A_bf16: np.ndarray      # (nblk, nb, nb) uint16
+    Y0: np.ndarray          # (n, p) float64, orthonormal columns
+    g: np.ndarray           # (n, p) float64, tangent at Y0 (stand-alone tCG rhs)
+
+    @property
+    def nblk(self) -> int:
+        return (self.n + self.nb - 1) // self.nb
+
+    def A_dense_blocks(self) -> np.ndarray:
+        return from_bf16_bits(self.A_bf16)
+
+
+def stiefel_rows(n: int, nb: int, row0: int, row1: int, seed: int = 21,
+                 diag_width: float = 28.0, low: np.ndarray | None = None) -> np.ndarray:
+    """A blocks covering rows [row0,row1) (block aligned) as float64 (nblk_local, nb, nb).
+
+    Block = diag(c) + R, c in [3, 3+diag_width) on a 1/4 grid, R symmetric with
+    entries m * 2^-11, |m| <= 31 (all exactly bf16).  Rows/columns listed in
+    `low` get diagonal 1 and zero off-diagonals, so span{e_i : i in low} is the
+    exact minimising subspace of tr(Y^T A Y)."""
+    assert row0 % nb == 0
+    b0, b1 = row0 // nb, (row1 + nb - 1) // nb
+    out = np.zeros((b1 - b0, nb, nb))
+    iu = np.triu_indices(nb, 1)
+    for b in range(b0, b1):
+        base = b * nb * nb
+        u = uniform01(seed, base, nb * nb).reshape(nb, nb)
+        m = np.floor(u * 63.0) - 31.0            # integers in [-31, 31]
+        R = np.zeros((nb, nb))
+        R[iu] = (m * 2.0 ** -11)[iu]
+        R = R + R.T
+        assert 0.0 < diag_width <= 28.0
+        dg = 3.0 + np.floor(u.diagonal() * diag_width * 4.0) / 4.0   # [3, 3+width) step 1/4
+        blk = R + np.diag(dg)
+        rows = min(nb, n - b * nb)
+        if low is not None:
+            for i in low[(low >= b * nb) & (low < (b + 1) * nb)] - b * nb:
+                blk[i, :] = 0.0
+                blk[:, i] = 0.0
+                blk[i, i] = 1.0
+        blk[rows:, :] = 0.0
+        blk[:, rows:] = 0.0
+        out[b - b0] = blk
+    return out
+
+
+def low_rows(n: int, p: int) -> np.ndarray:
+    """The p row indices whose diagonal entry is lowered to 1 (the minimising subspace)."""
+    return (np.arange(p) * (n // p) + min(5, n // p - 1)).astype(np.int64)
+
+
+def make_stiefel(n: int, p: int = 32, nb: int = 128, seed: int = 21,
+                 y_noise: float = 0.3, diag_width: float = 28.0) -> StiefelProblem:
+    """Y0 = qf(E_L + (y_noise / sqrt(n)) * N): a point at relative distance
+    ~y_noise from the minimising subspace; g = grad f(Y0) (computed by callers
+    that need it) or the random tangent below."""
+    L = low_rows(n, p)
+    A = stiefel_rows(n, nb, 0, n, seed, diag_width, L)
+    E = np.zeros((n, p))
+    E[L, np.arange(p)] = 1.0
+    Z = E + (y_noise / np.sqrt(n)) * gaussish(seed + 1, 0, n * p).reshape(n, p)
+    Y0, Rq = np.linalg.qr(Z)
+    Y0 = Y0 * np.sign(np.diag(Rq))[None, :]
+    Y0 = np.ascontiguousarray(Y0)
+    N = gaussish(seed + 2, 0, n * p).reshape(n, p)
+    G = Y0.T @ N
+    g = N - Y0 @ (0.5 * (G + G.T))
+    return StiefelProblem(n, p, nb, to_bf16_bits(A), Y0, np.ascontiguousarray(g))
+
+
+def stiefel_hess_numpy(prob: StiefelProblem, Y: np.ndarray, V: np.ndarray) -> np.ndarray:
+    """Dense numpy Hess f(Y)[V] = P_Y(A V - V sym(Y^T A Y)); small n only."""
+    A = prob.A_dense_blocks()
+    n, p, nb = prob.n, prob.p, prob.nb
+
+    def applyA(X):
+        out = np.zeros_like(X)
+        for b in range(prob.nblk):
+            r0, r1 = b * nb, min(n, (b + 1) * nb)
+            out[r0:r1] = A[b, : r1 - r0, : r1 - r0] @ X[r0:r1]
+        return out
+    AY = applyA(Y)
+    S = Y.T @ AY
+    S = 0.5 * (S + S.T)
+    W = applyA(V) - V @ S
+    G = Y.T @ W
+    return W - Y @ (0.5 * (G + G.T))
+
+
+@dataclasses.dataclass
+class SphereProblem:
+    """Rayleigh quotient f(x) = x^T A x on S^{n-1}, A = diag(d) + U diag(sigma) U^T."""
+    n: int
+    k: int
+    d: np.ndarray
+    U: np.ndarray
+    sigma: np.ndarray
+    x0: np.ndarray
+    g: np.ndarray
+
+
+def make_sphere(n: int, k: int = 16, seed: int = 11) -> SphereProblem:
+    d = 1.0 + uniform01(seed, 0, n)
+    U = gaussish(seed + 1, 0, n * k).reshape(n, k) / np.sqrt(n) if k else np.zeros((n, 0))
+    sigma = 2.0 * uniform01(seed + 2, 0, k) - 1.0
+    x0 = gaussish(seed + 3, 0, n)
+    x0 /= np.linalg.norm(x0)
+    z = gaussish(seed + 4, 0, n)
+    g = z - x0 * float(x0 @ z)
+    return SphereProblem(n, k, d, np.ascontiguousarray(U), sigma, x0, g)
+
+
+@dataclasses.dataclass
+class DiagProblem:
+    """Diagonal SPD Hessian with optional Jacobi preconditioner (the shape of the
+    reference's own STPCG tests, tests/IterativeSolvers_unit_test.cpp:82-131)."""
+    n: int
+    g: np.ndarray
+    h: np.ndarray
+    minv: np.ndarray
+
+
+def make_diag(n: int, seed: int = 5, lo: float = 1000.0, hi: float = 3000.0) -> DiagProblem:
+    g = 2.0 * uniform01(seed, 0, n) - 1.0
+    h = lo + (hi - lo) * uniform01(seed + 1, 0, n)
+    m = lo + (hi - lo) * uniform01(seed + 2, 0, n)
+    return DiagProblem(n, g, h, 1.0 / m)
