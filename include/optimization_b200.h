@@ -1,0 +1,191 @@
+/* optimization_b200.h -- C ABI of liboptimization_b200.so
+ *
+ * Drop-in boundary for the ONE hot path of david-m-rosen/Optimization that this
+ * library accelerates: the Steihaug-Toint truncated preconditioned CG inner
+ * loop (reference include/Optimization/LinearAlgebra/IterativeSolvers.h:166-426)
+ * as driven by the Riemannian truncated-Newton trust-region method (reference
+ * include/Optimization/Riemannian/TNT.h:242-689).
+ *
+ * The reference is a header-only template library with no ABI of its own: its
+ * "plugin" surface is the std::function functor set of
+ * include/Optimization/Riemannian/Concepts.h:44-112 and
+ * include/Optimization/LinearAlgebra/Concepts.h:16-26.  The C++ host templates
+ * shipped in include/Optimization/ (same include paths and signatures as the
+ * reference) call the entry points below whenever the tangent type is the
+ * device matrix handle `Optimization::b200::DeviceMatrix`; each entry point
+ * cites the reference statement(s) it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int
+ * status (OB200_OK == 0) and never throws; `*_dev` pointers are device memory on
+ * the context's GPU, everything else is host memory; all work is issued on the
+ * context's stream and functions that return scalars synchronise that stream.
+ * Matrices are row-major n x p doubles (leading dimension p).
+ */
+#ifndef OPTIMIZATION_B200_H
+#define OPTIMIZATION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------- */
+#define OB200_OK 0
+#define OB200_INVALID_ARGUMENT 1 /* host templates map this to std::invalid_argument
+                                    (reference IterativeSolvers.h:183-205, TNT.h:260-318) */
+#define OB200_CUDA_ERROR 2
+#define OB200_UNSUPPORTED 3
+#define OB200_NUMERIC_RANGE 4 /* fixed-point Gram bound exceeded / non-finite data */
+#define OB200_ABORTED 5       /* device watchdog fired (grid barrier timeout) */
+
+/* ---- tCG exit reasons (control-flow exits of IterativeSolvers.h:285-426) -- */
+#define OB200_EXIT_RESIDUAL 0       /* l.290: ||r||_P <= target                      */
+#define OB200_EXIT_MAX_ITERATIONS 1 /* l.285: loop bound reached                     */
+#define OB200_EXIT_KERNEL 2         /* l.305-337: p in ker(H), stepped to the boundary */
+#define OB200_EXIT_BOUNDARY 3       /* l.347-361: kappa <= 0 or step leaves the region */
+
+typedef struct ob200_context ob200_context;
+
+/* Create a context on `device` (CUDA ordinal).  `stream` is a cudaStream_t to
+ * issue work on, or NULL to let the context create its own non-blocking
+ * stream.  Fails loudly (OB200_CUDA_ERROR) if there is no usable GPU: there is
+ * no CPU fallback anywhere in this library. */
+int ob200_create(int device, void *stream, ob200_context **ctx);
+int ob200_destroy(ob200_context *ctx);
+const char *ob200_last_error(const ob200_context *ctx);
+int ob200_version(void);
+int ob200_sm_count(const ob200_context *ctx);
+int ob200_synchronize(ob200_context *ctx);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+uint64_t ob200_kernel_launches(const ob200_context *ctx);
+
+/* ---- Hessian operator descriptors -----------------------------------------
+ * Replaces the user's `Riemannian::LinearOperator` Hessian functor
+ * (reference Riemannian/Concepts.h:49-51, bound to x at TNT.h:400-403 and
+ * called at IterativeSolvers.h:294 and TNT.h:512) for the recognised operator
+ * families, so the Hessian-vector product can be fused into the CG step. */
+#define OB200_OP_DIAG 1             /* H v = d .* v                                   */
+#define OB200_OP_STIEFEL_BLOCKDIAG 2 /* H V = P_Y(A V - V S), P_Y(Z) = Z - Y sym(Y^T Z),
+                                        A block-diagonal dense (bf16 storage), p == 32  */
+#define OB200_OP_SPHERE_LOWRANK 3   /* H v = 2 P_x(A v) - 2 (x^T A x) v,
+                                        A = diag(d) + U diag(sigma) U^T               */
+
+typedef struct {
+  int kind;
+  uint64_t n; /* rows */
+  uint64_t p; /* columns (1 for plain vectors) */
+  /* OB200_OP_DIAG: d (n*p, device).  OB200_OP_SPHERE_LOWRANK: d (n, device). */
+  const double *diag_dev;
+  /* OB200_OP_STIEFEL_BLOCKDIAG */
+  const uint16_t *A_bf16_dev; /* ceil(n/128) blocks of 128x128 bf16, row-major, zero padded */
+  const double *Y_dev;        /* n x p base point, orthonormal columns */
+  const double *S_host;       /* p x p, sym(Y^T A Y) (host memory; see ob200_stiefel_model) */
+  double op_norm_bound;       /* >= ||A||_2 + ||S||_2 (ob200_stiefel_model returns one) */
+  /* OB200_OP_SPHERE_LOWRANK */
+  const double *x_dev;     /* n, unit vector */
+  const double *U_dev;     /* n x k row-major */
+  const double *sigma_host; /* k */
+  uint64_t k;
+  double xAx;
+} ob200_operator;
+
+/* Replaces the optional preconditioner functor (reference
+ * IterativeSolvers.h:83-85, adapter TNT.h:413-426). */
+#define OB200_PRECON_NONE 0
+#define OB200_PRECON_JACOBI 1 /* v = minv .* r */
+typedef struct {
+  int kind;
+  const double *minv_dev; /* n*p */
+} ob200_precon;
+
+typedef struct {
+  double Delta;            /* trust-region radius, > 0          (IterativeSolvers.h:171,183) */
+  uint64_t max_iterations; /* default 1000                      (l.172) */
+  double kappa_fgr;        /* in [0,1), default .1              (l.172,191) */
+  double theta;            /* in [0,1], default .5              (l.172,196) */
+  double epsilon;          /* in (0,1), default 1e-8            (l.179,201) */
+} ob200_stpcg_params;
+
+typedef struct {
+  double update_step_M_norm; /* IterativeSolvers.h:334,359,424 */
+  uint64_t num_iterations;   /* IterativeSolvers.h:285 */
+  int exit_reason;           /* OB200_EXIT_* */
+  double r0_norm;            /* l.275 */
+  double final_rv;           /* last <r, v> */
+  uint64_t kernel_launches;  /* kernels launched by this call */
+} ob200_stpcg_result;
+
+/* Steihaug-Toint truncated preconditioned CG, whole solve on the device.
+ * Mirrors  Vector STPCG(g, H, inner_product, update_step_M_norm, num_iterations,
+ * Delta, max_iterations, kappa_fgr, theta, P, At, user_function, epsilon)
+ * (reference IterativeSolvers.h:166-179) with the Frobenius inner product
+ * (every in-tree metric: Riemannian/Concepts.h:181-185), no constraint operator
+ * `At` and no per-iteration host hook -- exactly how TNT calls it (TNT.h:489-492).
+ * g_dev, s_dev: n*p doubles on the device.  s_dev receives the step. */
+int ob200_stpcg(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P,
+                const double *g_dev, const ob200_stpcg_params *params, double *s_dev,
+                ob200_stpcg_result *result);
+
+/* Same call with HOST buffers for g and s (pinned or pageable): the copies are
+ * part of the call.  This is the end-to-end entry bench.py times as `e2e`. */
+int ob200_stpcg_host(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P,
+                     const double *g_host, const ob200_stpcg_params *params, double *s_host,
+                     ob200_stpcg_result *result);
+
+/* Stand-alone Hessian-vector product out = H(v) (reference call sites
+ * IterativeSolvers.h:294, TNT.h:512). */
+int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v_dev, double *out_dev);
+
+/* ---- level-1 primitives with the exact, order-independent reduction --------
+ * Replace `metric(x, a, b)` (TNT.h:382,387,493,511-512,575,579) and the
+ * generic vector expressions of the Krylov loops when the user's Hessian is an
+ * arbitrary functor over device matrices. */
+int ob200_dot(ob200_context *ctx, uint64_t n, const double *a_dev, const double *b_dev,
+              double *result);
+/* up to 4 inner products <a_i, b_i> in one pass */
+int ob200_dots(ob200_context *ctx, uint64_t n, int count, const double *const *a_dev,
+               const double *const *b_dev, double *results);
+/* out = alpha * x + beta * y   (out may alias x or y) */
+int ob200_axpby(ob200_context *ctx, uint64_t n, double alpha, const double *x_dev, double beta,
+                const double *y_dev, double *out_dev);
+/* out = d .* x */
+int ob200_hadamard(ob200_context *ctx, uint64_t n, const double *d_dev, const double *x_dev,
+                   double *out_dev);
+
+/* ---- Stiefel trace-minimisation model on the device -------------------------
+ * f(Y) = 1/2 tr(Y^T A Y).  These replace the user's Objective / QuadraticModel /
+ * Retraction functors (reference Base/Concepts.h:37-38, Riemannian/Concepts.h:
+ * 63-67,110-112; call sites TNT.h:377,380,505,508,573) for this model so the
+ * outer loop never copies n x p matrices to the host. */
+/* S = sym(Y^T A Y) (host, p*p), f = 1/2 tr(S), optional grad = A Y - Y S (device),
+ * op_norm_bound = ||A||_inf + ||S||_F. */
+int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16_t *A_bf16_dev,
+                        const double *Y_dev, double *S_host, double *f, double *grad_dev,
+                        double *op_norm_bound);
+/* Cholesky-QR retraction  out = qf(Y + V) */
+int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y_dev,
+                          const double *V_dev, double *out_dev);
+
+/* ---- device memory helpers (so non-CUDA hosts can stage data) -------------- */
+int ob200_malloc(ob200_context *ctx, size_t bytes, void **ptr_dev);
+int ob200_free(ob200_context *ctx, void *ptr_dev);
+int ob200_memcpy_h2d(ob200_context *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int ob200_memcpy_d2h(ob200_context *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int ob200_malloc_host(ob200_context *ctx, size_t bytes, void **ptr_host); /* pinned */
+int ob200_free_host(ob200_context *ctx, void *ptr_host);
+
+/* ---- multi-GPU (row-block sharding, one process per GPU) --------------------
+ * Each rank holds a contiguous row block (multiple of 128 rows) of every n x p
+ * matrix.  Reductions are exchanged as exact integer accumulators, so results
+ * are bit-identical for any world size.  The host (torch.distributed or MPI)
+ * supplies the all-reduce as a callback over int64 buffers in DEVICE memory. */
+typedef int (*ob200_allreduce_i64_fn)(void *user, void *buf_dev, uint64_t count);
+int ob200_set_allreduce(ob200_context *ctx, ob200_allreduce_i64_fn fn, void *user, int rank,
+                        int world_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTIMIZATION_B200_H */

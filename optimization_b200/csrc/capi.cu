@@ -1,0 +1,539 @@
+// C ABI of liboptimization_b200.so (see include/optimization_b200.h).
+// Host-side dispatch only: every arithmetic statement of the hot path runs in
+// the CUDA kernels of tcg_elementwise.cu / tcg_stiefel.cu / level1.cu.  There is
+// no CPU fallback: without a usable GPU ob200_create fails.
+#include "../../include/optimization_b200.h"
+#include "tcg.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace ob200 {
+cudaError_t launch_tcg_init(const TcgCommon &a, int grid, cudaStream_t st);
+cudaError_t launch_tcg_finalize(const u64 *acc, int slot, double *out, cudaStream_t st);
+cudaError_t launch_tcg_diag(const TcgCommon &a, const double *hdiag, int grid, cudaStream_t st);
+cudaError_t launch_tcg_stiefel(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
+                               const double *Y, const double *S_dev, double op_norm_bound, int grid,
+                               cudaStream_t stm);
+cudaError_t launch_stiefel_apply(unsigned long long n_rows, const unsigned short *A, const double *V,
+                                 const double *S_dev, const double *Y, double *Wout, u64 *set, double inv_q,
+                                 int grid, cudaStream_t stm);
+cudaError_t launch_stiefel_gram(unsigned long long n_rows, const double *X, const double *Z, u64 *set,
+                                double inv_q, int grid, cudaStream_t stm);
+cudaError_t launch_stiefel_rowgemm(unsigned long long n_rows, const double *W, double cW, const double *X,
+                                   const double *M_dev, double *out, int grid, cudaStream_t stm);
+cudaError_t launch_stiefel_absrowsum(const unsigned short *A, unsigned long long nrows_padded,
+                                     unsigned long long *out_bits, cudaStream_t stm);
+int gram_exponent_host(double bound);
+cudaError_t launch_dots(unsigned long long N, int count, const double *const *a, const double *const *b,
+                        u64 *set, int sm_count, cudaStream_t st);
+cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st);
+cudaError_t launch_axpby(unsigned long long N, double alpha, const double *x, double beta, const double *y,
+                         double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_hadamard(unsigned long long N, const double *d, const double *x, double *out,
+                            int sm_count, cudaStream_t st);
+}  // namespace ob200
+
+using namespace ob200;
+
+struct ob200_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+  // workspace
+  size_t vec_capacity = 0;        // doubles per work vector
+  double *r = nullptr, *p0 = nullptr, *p1 = nullptr, *Hp = nullptr, *gs = nullptr; // gs: staging for g/s (host entry)
+  size_t gs_capacity = 0;
+  u64 *acc = nullptr;             // ACC_SETS * ACC_WORDS
+  unsigned *barrier = nullptr;    // [0] counter, [1] abort flag (int)
+  TcgDeviceResult *dres = nullptr;
+  double *dscal = nullptr;        // 8 doubles
+  double *dmat = nullptr;         // 2 * 32*32 doubles (S, M)
+  unsigned long long *dbits = nullptr;
+  // pinned host mirrors
+  TcgDeviceResult *hres = nullptr;
+  double *hscal = nullptr;
+  u64 *hacc = nullptr;            // ACC_WORDS
+  double *hmat = nullptr;         // 32*32
+  // multi-GPU
+  ob200_allreduce_i64_fn allreduce = nullptr;
+  void *allreduce_user = nullptr;
+  int rank = 0, world = 1;
+};
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+      return OB200_CUDA_ERROR;                                                          \
+    }                                                                                   \
+  } while (0)
+
+static int fail(ob200_context *ctx, int code, const char *msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+extern "C" {
+
+int ob200_version(void) { return 100; }
+
+int ob200_create(int device, void *stream, ob200_context **out) {
+  if (!out) return OB200_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    fprintf(stderr, "optimization_b200: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    return OB200_CUDA_ERROR;
+  }
+  ob200_context *ctx = new ob200_context;
+  ctx->device = device;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) { delete ctx; return OB200_UNSUPPORTED; }
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  CK(cudaMalloc(&ctx->acc, sizeof(u64) * ACC_SETS * ACC_WORDS));
+  CK(cudaMalloc(&ctx->barrier, 64));
+  CK(cudaMalloc(&ctx->dres, sizeof(TcgDeviceResult)));
+  CK(cudaMalloc(&ctx->dscal, sizeof(double) * 8));
+  CK(cudaMalloc(&ctx->dmat, sizeof(double) * 2 * 32 * 32));
+  CK(cudaMalloc(&ctx->dbits, 64));
+  CK(cudaMallocHost(&ctx->hres, sizeof(TcgDeviceResult)));
+  CK(cudaMallocHost(&ctx->hscal, sizeof(double) * 8));
+  CK(cudaMallocHost(&ctx->hacc, sizeof(u64) * ACC_WORDS));
+  CK(cudaMallocHost(&ctx->hmat, sizeof(double) * 32 * 32));
+  *out = ctx;
+  return OB200_OK;
+}
+
+int ob200_destroy(ob200_context *ctx) {
+  if (!ctx) return OB200_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->r); cudaFree(ctx->p0); cudaFree(ctx->p1); cudaFree(ctx->Hp); cudaFree(ctx->gs);
+  cudaFree(ctx->acc); cudaFree(ctx->barrier); cudaFree(ctx->dres); cudaFree(ctx->dscal);
+  cudaFree(ctx->dmat); cudaFree(ctx->dbits);
+  cudaFreeHost(ctx->hres); cudaFreeHost(ctx->hscal); cudaFreeHost(ctx->hacc); cudaFreeHost(ctx->hmat);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return OB200_OK;
+}
+
+const char *ob200_last_error(const ob200_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int ob200_sm_count(const ob200_context *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t ob200_kernel_launches(const ob200_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int ob200_synchronize(ob200_context *ctx) {
+  if (!ctx) return OB200_INVALID_ARGUMENT;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OB200_OK;
+}
+
+int ob200_set_allreduce(ob200_context *ctx, ob200_allreduce_i64_fn fn, void *user, int rank, int world) {
+  if (!ctx || world < 1 || rank < 0 || rank >= world) return OB200_INVALID_ARGUMENT;
+  ctx->allreduce = fn;
+  ctx->allreduce_user = user;
+  ctx->rank = rank;
+  ctx->world = world;
+  return OB200_OK;
+}
+
+// ---- memory helpers ---------------------------------------------------------
+int ob200_malloc(ob200_context *ctx, size_t bytes, void **p) {
+  if (!ctx || !p) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  return OB200_OK;
+}
+int ob200_free(ob200_context *ctx, void *p) {
+  if (!ctx) return OB200_INVALID_ARGUMENT;
+  CK(cudaFree(p));
+  return OB200_OK;
+}
+int ob200_memcpy_h2d(ob200_context *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return OB200_INVALID_ARGUMENT;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OB200_OK;
+}
+int ob200_memcpy_d2h(ob200_context *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return OB200_INVALID_ARGUMENT;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OB200_OK;
+}
+int ob200_malloc_host(ob200_context *ctx, size_t bytes, void **p) {
+  if (!ctx || !p) return OB200_INVALID_ARGUMENT;
+  CK(cudaMallocHost(p, bytes ? bytes : 16));
+  return OB200_OK;
+}
+int ob200_free_host(ob200_context *ctx, void *p) {
+  if (!ctx) return OB200_INVALID_ARGUMENT;
+  CK(cudaFreeHost(p));
+  return OB200_OK;
+}
+
+}  // extern "C"
+
+// ---- internals ----------------------------------------------------------------
+static int ensure_vectors(ob200_context *ctx, size_t N) {
+  if (N <= ctx->vec_capacity) return OB200_OK;
+  cudaFree(ctx->r); cudaFree(ctx->p0); cudaFree(ctx->p1); cudaFree(ctx->Hp);
+  ctx->r = ctx->p0 = ctx->p1 = ctx->Hp = nullptr;
+  ctx->vec_capacity = 0;
+  const size_t bytes = sizeof(double) * (N + 64);
+  CK(cudaMalloc(&ctx->r, bytes));
+  CK(cudaMalloc(&ctx->p0, bytes));
+  CK(cudaMalloc(&ctx->p1, bytes));
+  CK(cudaMalloc(&ctx->Hp, bytes));
+  ctx->vec_capacity = N;
+  return OB200_OK;
+}
+static int ensure_staging(ob200_context *ctx, size_t N) {
+  if (N <= ctx->gs_capacity) return OB200_OK;
+  cudaFree(ctx->gs);
+  ctx->gs = nullptr;
+  ctx->gs_capacity = 0;
+  CK(cudaMalloc(&ctx->gs, sizeof(double) * (2 * N + 64)));
+  ctx->gs_capacity = N;
+  return OB200_OK;
+}
+
+// exact dot products (<= 4) -> host doubles; synchronises the stream
+static int dots_sync(ob200_context *ctx, uint64_t N, int count, const double *const *a, const double *const *b,
+                     double *out) {
+  u64 *set = ctx->acc;  // set 0
+  CK(cudaMemsetAsync(set, 0, sizeof(u64) * ACC_SCAL_WORDS, ctx->stream));
+  CK(launch_dots(N, count, a, b, set, ctx->sm_count, ctx->stream));
+  CK(launch_finalize_many(set, count, ctx->dscal, ctx->stream));
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) out[i] = ctx->hscal[i];
+  return OB200_OK;
+}
+
+// read the fixed-point Gram of set 0 back to the host as doubles (p x p = 32 x 32)
+static int read_gram(ob200_context *ctx, int e, double *G /* 1024 */, double *scal2 /* nullable: 2 scalars */) {
+  if (scal2) {
+    CK(launch_finalize_many(ctx->acc, 2, ctx->dscal, ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ctx->hacc, ctx->acc, sizeof(u64) * ACC_WORDS, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->hacc[ACC_FLAG_OFF] != 0) return fail(ctx, OB200_NUMERIC_RANGE, "fixed-point Gram bound exceeded");
+  const double q = std::ldexp(1.0, e - 90);
+  for (int i = 0; i < 1024; ++i)
+    G[i] = fix2_to_double((i64)ctx->hacc[ACC_GRAM_OFF + 2 * i], (i64)ctx->hacc[ACC_GRAM_OFF + 2 * i + 1], q);
+  if (scal2) { scal2[0] = ctx->hscal[0]; scal2[1] = ctx->hscal[1]; }
+  return OB200_OK;
+}
+
+static int check_params(ob200_context *ctx, const ob200_stpcg_params *p) {
+  // reference IterativeSolvers.h:183-205 (max_iterations < 0 is dead code for size_t, l.187)
+  if (!(p->Delta > 0)) return fail(ctx, OB200_INVALID_ARGUMENT, "Trust-region radius (Delta) must be a positive real value");
+  if ((p->kappa_fgr < 0) || (p->kappa_fgr >= 1) || std::isnan(p->kappa_fgr))
+    return fail(ctx, OB200_INVALID_ARGUMENT, "Target fractional reduction of the gradient norm (kappa_fgr) must be a real value in the range [0,1)");
+  if ((p->theta < 0) || (p->theta > 1) || std::isnan(p->theta))
+    return fail(ctx, OB200_INVALID_ARGUMENT, "Target superlinear convergence rate (theta) must be a real value in the range [0,1]");
+  if ((p->epsilon <= 0) || (p->epsilon >= 1) || std::isnan(p->epsilon))
+    return fail(ctx, OB200_INVALID_ARGUMENT, "Relative norm tolerance for declaring a vector to lie in the kernel of H (epsilon) should be a small positive number in the range (0,1)");
+  return OB200_OK;
+}
+
+static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
+                        const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
+  int rc = check_params(ctx, prm);
+  if (rc) return rc;
+  if (!H || !g_dev || !s_dev || !res) return fail(ctx, OB200_INVALID_ARGUMENT, "null argument");
+  if (H->n == 0 || H->p == 0) return fail(ctx, OB200_INVALID_ARGUMENT, "empty operator");
+  const uint64_t N = H->n * H->p;
+  const double *minv = nullptr;
+  if (P && P->kind == OB200_PRECON_JACOBI) {
+    if (!P->minv_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "Jacobi preconditioner without minv");
+    minv = P->minv_dev;
+  } else if (P && P->kind != OB200_PRECON_NONE) {
+    return fail(ctx, OB200_UNSUPPORTED, "unknown preconditioner kind");
+  }
+  if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG) {
+    if (H->p != 32) return fail(ctx, OB200_UNSUPPORTED, "Stiefel block-diagonal operator requires p == 32");
+    if (minv) return fail(ctx, OB200_UNSUPPORTED, "elementwise Jacobi does not preserve the Stiefel tangent space");
+    if (!H->A_bf16_dev || !H->Y_dev || !H->S_host) return fail(ctx, OB200_INVALID_ARGUMENT, "incomplete Stiefel operator");
+    if (!(H->op_norm_bound > 0)) return fail(ctx, OB200_INVALID_ARGUMENT, "op_norm_bound must be positive");
+  } else if (H->kind == OB200_OP_DIAG) {
+    if (!H->diag_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "diag operator without diagonal");
+  } else {
+    return fail(ctx, OB200_UNSUPPORTED, "operator kind not supported by the fused tCG path");
+  }
+  CK(cudaSetDevice(ctx->device));
+  if ((rc = ensure_vectors(ctx, N))) return rc;
+  const uint64_t launches0 = ctx->launches;
+  cudaStream_t st = ctx->stream;
+
+  TcgCommon a;
+  a.N = N;
+  a.g = g_dev;
+  a.s = s_dev;
+  a.r = ctx->r;
+  a.p0 = ctx->p0;
+  a.p1 = ctx->p1;
+  a.Hp = ctx->Hp;
+  a.minv = minv;
+  a.rv0 = 0; a.target = 0;
+  a.Delta = prm->Delta;
+  a.epsilon = prm->epsilon;
+  a.max_iterations = prm->max_iterations;
+  a.acc = ctx->acc;
+  a.barrier = ctx->barrier;
+  a.abort_flag = reinterpret_cast<int *>(ctx->barrier + 1);
+  a.result = ctx->dres;
+
+  // s = 0, r = g, <r, v>  (IterativeSolvers.h:211-266)
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SETS * ACC_WORDS, st));
+  CK(cudaMemsetAsync(ctx->barrier, 0, 64, st));
+  CK(launch_tcg_init(a, ctx->sm_count * 2, st));
+  CK(launch_tcg_finalize(ctx->acc, SC_RV, ctx->dscal, st));
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));  // set 0 is reused by the loop
+  if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG)
+    CK(cudaMemcpyAsync(ctx->dmat, H->S_host, sizeof(double) * 32 * 32, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  const double rv0 = ctx->hscal[0];
+  const double r0_norm = std::sqrt(rv0);                                            // l.275
+  const double target = r0_norm * std::min(prm->kappa_fgr, std::pow(r0_norm, prm->theta));  // l.278-279
+  a.rv0 = rv0;
+  a.target = target;
+
+  if (H->kind == OB200_OP_DIAG) {
+    CK(launch_tcg_diag(a, H->diag_dev, ctx->sm_count, st));
+  } else {
+    const unsigned long long nblk = (H->n + 127) / 128;
+    int grid = ctx->sm_count;
+    if ((unsigned long long)grid > nblk) grid = (int)nblk;
+    CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
+  }
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(ctx->hres, ctx->dres, sizeof(TcgDeviceResult), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  res->update_step_M_norm = ctx->hres->update_step_M_norm;
+  res->num_iterations = ctx->hres->num_iterations;
+  res->exit_reason = ctx->hres->exit_reason;
+  res->r0_norm = r0_norm;
+  res->final_rv = ctx->hres->final_rv;
+  res->kernel_launches = ctx->launches - launches0;
+  if (ctx->hres->status == OB200_NUMERIC_RANGE) return fail(ctx, OB200_NUMERIC_RANGE, "fixed-point Gram bound exceeded or non-finite data");
+  if (ctx->hres->status == OB200_ABORTED) return fail(ctx, OB200_ABORTED, "device grid barrier watchdog fired");
+  return OB200_OK;
+}
+
+extern "C" {
+
+int ob200_stpcg(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
+                const ob200_stpcg_params *params, double *s_dev, ob200_stpcg_result *result) {
+  if (!ctx || !params) return OB200_INVALID_ARGUMENT;
+  return stpcg_device(ctx, H, P, g_dev, params, s_dev, result);
+}
+
+int ob200_stpcg_host(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_host,
+                     const ob200_stpcg_params *params, double *s_host, ob200_stpcg_result *result) {
+  if (!ctx || !params || !H || !g_host || !s_host) return OB200_INVALID_ARGUMENT;
+  const uint64_t N = H->n * H->p;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_staging(ctx, N);
+  if (rc) return rc;
+  double *g_dev = ctx->gs, *s_dev = ctx->gs + N + (N & 1);
+  CK(cudaMemcpyAsync(g_dev, g_host, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  rc = stpcg_device(ctx, H, P, g_dev, params, s_dev, result);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(s_host, s_dev, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OB200_OK;
+}
+
+int ob200_dot(ob200_context *ctx, uint64_t n, const double *a, const double *b, double *result) {
+  if (!ctx || !a || !b || !result) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const double *aa[1] = {a}, *bb[1] = {b};
+  return dots_sync(ctx, n, 1, aa, bb, result);
+}
+int ob200_dots(ob200_context *ctx, uint64_t n, int count, const double *const *a, const double *const *b,
+               double *results) {
+  if (!ctx || count < 1 || count > 4 || !a || !b || !results) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  return dots_sync(ctx, n, count, a, b, results);
+}
+int ob200_axpby(ob200_context *ctx, uint64_t n, double alpha, const double *x, double beta, const double *y,
+                double *out) {
+  if (!ctx || !x || !out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_axpby(n, alpha, x, beta, y, out, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  return OB200_OK;
+}
+int ob200_hadamard(ob200_context *ctx, uint64_t n, const double *d, const double *x, double *out) {
+  if (!ctx || !d || !x || !out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_hadamard(n, d, x, out, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  return OB200_OK;
+}
+
+int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16_t *A, const double *Y,
+                        double *S_host, double *f, double *grad_dev, double *op_norm_bound) {
+  if (!ctx || !A || !Y || !S_host) return OB200_INVALID_ARGUMENT;
+  if (p != 32) return fail(ctx, OB200_UNSUPPORTED, "Stiefel model requires p == 32");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_vectors(ctx, n * p);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const unsigned long long nblk = (n + 127) / 128;
+  int grid = ctx->sm_count;
+  if ((unsigned long long)grid > nblk) grid = (int)nblk;
+  // ||A||_inf
+  CK(cudaMemsetAsync(ctx->dbits, 0, 8, st));
+  CK(launch_stiefel_absrowsum(A, nblk * 128, ctx->dbits, st));
+  ctx->launches += 1;
+  unsigned long long bits = 0;
+  CK(cudaMemcpyAsync(&bits, ctx->dbits, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  double Ainf;
+  memcpy(&Ainf, &bits, 8);
+  if (!(Ainf > 0)) Ainf = 1.0;
+  // W = A Y (into Hp workspace), Gram Y^T W, <Y, W>
+  const int e = gram_exponent_host(Ainf * 4.0);
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));
+  CK(launch_stiefel_apply(n, A, Y, nullptr, Y, ctx->Hp, ctx->acc, std::ldexp(1.0, 90 - e), grid, st));
+  ctx->launches += 1;
+  std::vector<double> G(1024);
+  double sc[2];
+  if ((rc = read_gram(ctx, e, G.data(), sc))) return rc;
+  double fro = 0.0;
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j) {
+      const double sij = 0.5 * (G[i * 32 + j] + G[j * 32 + i]);
+      S_host[i * 32 + j] = sij;
+      fro += sij * sij;
+    }
+  if (f) *f = 0.5 * sc[0];
+  if (op_norm_bound) *op_norm_bound = Ainf + std::sqrt(fro);
+  if (grad_dev) {
+    for (int i = 0; i < 1024; ++i) ctx->hmat[i] = -S_host[i];
+    CK(cudaMemcpyAsync(ctx->dmat + 1024, ctx->hmat, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
+    CK(launch_stiefel_rowgemm(n, ctx->Hp, 1.0, Y, ctx->dmat + 1024, grad_dev, grid, st));   // A Y - Y S
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(st));  // hmat is reused
+  }
+  return OB200_OK;
+}
+
+int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, double *out) {
+  if (!ctx || !H || !v || !out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t N = H->n * H->p;
+  cudaStream_t st = ctx->stream;
+  if (H->kind == OB200_OP_DIAG) {
+    CK(launch_hadamard(N, H->diag_dev, v, out, ctx->sm_count, st));
+    ctx->launches += 1;
+    return OB200_OK;
+  }
+  if (H->kind != OB200_OP_STIEFEL_BLOCKDIAG || H->p != 32) return fail(ctx, OB200_UNSUPPORTED, "operator kind");
+  int rc = ensure_vectors(ctx, N);
+  if (rc) return rc;
+  const unsigned long long nblk = (H->n + 127) / 128;
+  int grid = ctx->sm_count;
+  if ((unsigned long long)grid > nblk) grid = (int)nblk;
+  double vv = 0.0;
+  const double *aa[1] = {v}, *bb[1] = {v};
+  if ((rc = dots_sync(ctx, N, 1, aa, bb, &vv))) return rc;
+  const int e = gram_exponent_host(H->op_norm_bound * std::sqrt(vv) * 4.0);
+  CK(cudaMemcpyAsync(ctx->dmat, H->S_host, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));
+  CK(launch_stiefel_apply(H->n, H->A_bf16_dev, v, ctx->dmat, H->Y_dev, ctx->Hp, ctx->acc,
+                          std::ldexp(1.0, 90 - e), grid, st));
+  ctx->launches += 1;
+  std::vector<double> G(1024);
+  if ((rc = read_gram(ctx, e, G.data(), nullptr))) return rc;
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j) ctx->hmat[i * 32 + j] = -0.5 * (G[i * 32 + j] + G[j * 32 + i]);
+  CK(cudaMemcpyAsync(ctx->dmat + 1024, ctx->hmat, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
+  CK(launch_stiefel_rowgemm(H->n, ctx->Hp, 1.0, H->Y_dev, ctx->dmat + 1024, out, grid, st));
+  ctx->launches += 1;
+  CK(cudaStreamSynchronize(st));
+  return OB200_OK;
+}
+
+int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y, const double *V,
+                          double *out) {
+  if (!ctx || !Y || !V || !out) return OB200_INVALID_ARGUMENT;
+  if (p != 32) return fail(ctx, OB200_UNSUPPORTED, "Stiefel retraction requires p == 32");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t N = n * p;
+  int rc = ensure_vectors(ctx, N);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const unsigned long long nblk = (n + 127) / 128;
+  int grid = ctx->sm_count;
+  if ((unsigned long long)grid > nblk) grid = (int)nblk;
+  double *Z = ctx->Hp;
+  CK(launch_axpby(N, 1.0, Y, 1.0, V, Z, ctx->sm_count, st));   // Z = Y + V
+  ctx->launches += 1;
+  double zz = 0.0;
+  const double *aa[1] = {Z}, *bb[1] = {Z};
+  if ((rc = dots_sync(ctx, N, 1, aa, bb, &zz))) return rc;
+  const int e = gram_exponent_host(zz * 2.0);                  // |(Z^T Z)_ij| <= ||Z||_F^2
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));
+  CK(launch_stiefel_gram(n, Z, Z, ctx->acc, std::ldexp(1.0, 90 - e), grid, st));
+  ctx->launches += 1;
+  std::vector<double> M(1024), R(1024, 0.0), Ri(1024, 0.0);
+  if ((rc = read_gram(ctx, e, M.data(), nullptr))) return rc;
+  const int P = 32;
+  for (int i = 0; i < P; ++i)
+    for (int j = i; j < P; ++j) { const double s = 0.5 * (M[i * P + j] + M[j * P + i]); M[i * P + j] = s; M[j * P + i] = s; }
+  // upper Cholesky M = R^T R
+  for (int j = 0; j < P; ++j) {
+    double s = M[j * P + j];
+    for (int k = 0; k < j; ++k) s -= R[k * P + j] * R[k * P + j];
+    if (!(s > 0)) return fail(ctx, OB200_NUMERIC_RANGE, "retraction: Y + V is rank deficient");
+    const double rjj = std::sqrt(s);
+    R[j * P + j] = rjj;
+    for (int i = j + 1; i < P; ++i) {
+      double t = M[j * P + i];
+      for (int k = 0; k < j; ++k) t -= R[k * P + j] * R[k * P + i];
+      R[j * P + i] = t / rjj;
+    }
+  }
+  // Ri = R^{-1} (upper triangular), column by column: R * Ri = I
+  for (int c = 0; c < P; ++c) {
+    for (int i = c; i >= 0; --i) {
+      double t = (i == c) ? 1.0 : 0.0;
+      for (int k = i + 1; k <= c; ++k) t -= R[i * P + k] * Ri[k * P + c];
+      Ri[i * P + c] = t / R[i * P + i];
+    }
+  }
+  for (int i = 0; i < 1024; ++i) ctx->hmat[i] = Ri[i];
+  CK(cudaMemcpyAsync(ctx->dmat + 1024, ctx->hmat, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
+  CK(launch_stiefel_rowgemm(n, nullptr, 0.0, Z, ctx->dmat + 1024, out, grid, st));   // Q = Z R^{-1}
+  ctx->launches += 1;
+  CK(cudaStreamSynchronize(st));
+  return OB200_OK;
+}
+
+}  // extern "C"

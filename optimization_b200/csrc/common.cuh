@@ -1,0 +1,239 @@
+// Shared device/host helpers for the fused tCG kernels (sm_100a).
+//
+// Determinism model: every inner product that feeds a
+// decision of the Steihaug-Toint loop (reference IterativeSolvers.h:290,305-307,
+// 320,341,347,408) is reduced as
+//   fixed unit (8-row strip / 256-element run) -> double partial in a fixed
+//   lane order -> EXACT integer accumulation (Kulisch long accumulator).
+// Integer addition is associative, so the result does not depend on which
+// warp / CTA / GPU processed which unit, on the grid size, or on atomics
+// ordering: runs are bit-reproducible and independent of the GPU count.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+
+namespace ob200 {
+
+// ---------------------------------------------------------------------------
+// Kulisch-style long accumulator: 32-bit digits held in int64 limbs.
+// value = sum_j limb[j] * 2^(32 j - KUL_BIAS)
+// ---------------------------------------------------------------------------
+constexpr int KUL_BIAS = 1088;      // > 1074 (smallest subnormal exponent), multiple of 32
+constexpr int KUL_LIMBS = 68;       // covers up to 2^(68*32-1088) = 2^1088
+constexpr int KUL_STRIDE = 72;      // limbs + [68] non-finite counter, padded
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+// Split x into (at most) three signed 32-bit digits at limb j, j+1, j+2.
+// Returns false for inf / nan.
+__host__ __device__ __forceinline__ bool kul_decompose(double x, int &j, i64 &d0, i64 &d1, i64 &d2) {
+  u64 bits;
+#ifdef __CUDA_ARCH__
+  bits = (u64)__double_as_longlong(x);
+#else
+  memcpy(&bits, &x, 8);
+#endif
+  const int e = (int)((bits >> 52) & 0x7ff);
+  u64 mant = bits & 0xFFFFFFFFFFFFFull;
+  if (e == 0x7ff) return false;
+  int shift;
+  if (e == 0) {
+    shift = -1074 + KUL_BIAS;
+  } else {
+    mant |= (1ull << 52);
+    shift = e - 1075 + KUL_BIAS;
+  }
+  j = shift >> 5;
+  const int off = shift & 31;
+  const u64 lo = mant << off;                          // low 64 bits of mant * 2^off
+  const u64 hi = off ? (mant >> (64 - off)) : 0ull;    // bits above 64 (mant < 2^53, off < 32)
+  d0 = (i64)(lo & 0xFFFFFFFFull);
+  d1 = (i64)(lo >> 32);
+  d2 = (i64)hi;
+  if (bits >> 63) { d0 = -d0; d1 = -d1; d2 = -d2; }
+  return true;
+}
+
+#ifdef __CUDACC__
+// Add x into a (shared- or global-memory) accumulator with 64-bit atomics.
+__device__ __forceinline__ void kul_add_atomic(u64 *acc, double x) {
+  if (x == 0.0) return;
+  int j;
+  i64 d0, d1, d2;
+  if (!kul_decompose(x, j, d0, d1, d2)) {  // inf / nan poisons the sum
+    atomicAdd(acc + KUL_LIMBS, 1ull);
+    return;
+  }
+  if (d0) atomicAdd(acc + j, (u64)d0);
+  if (d1) atomicAdd(acc + j + 1, (u64)d1);
+  if (d2) atomicAdd(acc + j + 2, (u64)d2);
+}
+#endif
+
+// host twin (tests): plain adds
+inline void kul_add_host(u64 *acc, double x) {
+  if (x == 0.0) return;
+  int j;
+  i64 d0, d1, d2;
+  if (!kul_decompose(x, j, d0, d1, d2)) { acc[KUL_LIMBS] += 1; return; }
+  acc[j] += (u64)d0;
+  acc[j + 1] += (u64)d1;
+  acc[j + 2] += (u64)d2;
+}
+
+// Correctly rounded (round-to-nearest-even) double value of an accumulator.
+// `ld(j)` returns limb j.  Executed redundantly and identically per CTA.
+template <class Load>
+__host__ __device__ inline double kul_finalize(Load ld) {
+  if (ld(KUL_LIMBS) != 0) {
+    const u64 nanbits = 0x7ff8000000000000ull;
+    double nanv;
+    memcpy(&nanv, &nanbits, 8);
+    return nanv;
+  }
+  i64 raw[KUL_LIMBS];
+  i64 carry = 0;
+#pragma unroll 1
+  for (int j = 0; j < KUL_LIMBS; ++j) {
+    raw[j] = (i64)ld(j);
+    carry = (raw[j] + carry) >> 32;   // arithmetic shift: floor division
+  }
+  const bool neg = carry < 0;
+  uint32_t dig[KUL_LIMBS];
+  carry = 0;
+  int top = -1;
+#pragma unroll 1
+  for (int j = 0; j < KUL_LIMBS; ++j) {
+    const i64 t = (neg ? -raw[j] : raw[j]) + carry;
+    dig[j] = (uint32_t)(t & 0xFFFFFFFFll);
+    carry = t >> 32;
+    if (dig[j]) top = j;
+  }
+  if (top < 0) return 0.0;
+  const uint32_t d_top = dig[top];
+  const uint32_t d_mid = top >= 1 ? dig[top - 1] : 0u;
+  const uint32_t d_low = top >= 2 ? dig[top - 2] : 0u;
+  bool sticky = false;
+#pragma unroll 1
+  for (int j = 0; j < top - 2; ++j) sticky = sticky || (dig[j] != 0);
+  // 96-bit integer I = d_top*2^64 + d_mid*2^32 + d_low, value = I * 2^(32*(top-2) - BIAS)
+  const u64 hi64 = ((u64)d_top << 32) | (u64)d_mid;
+#ifdef __CUDA_ARCH__
+  const int lz = __clzll((i64)hi64);
+#else
+  const int lz = __builtin_clzll(hi64);
+#endif
+  u64 m64 = hi64;
+  uint32_t rem = d_low;
+  if (lz) {  // d_top != 0 -> lz <= 31
+    m64 = (hi64 << lz) | ((u64)d_low >> (32 - lz));
+    rem = d_low << lz;
+  }
+  if (rem != 0 || sticky) m64 |= 1ull;  // sticky bit, far below the rounding position
+#ifdef __CUDA_ARCH__
+  const double m = __ull2double_rn(m64);
+#else
+  const double m = (double)m64;
+#endif
+  const int ex = 32 * (top - 1) - KUL_BIAS - lz;
+  const double v = scalbn(m, ex);
+  return neg ? -v : v;
+}
+
+// ---------------------------------------------------------------------------
+// Bounded two-limb fixed point for the p x p Gram of the tangent projection.
+// x is quantised to q = 2^(e-90) with |x| < 2^e guaranteed by the caller's
+// bound; integer = hi * 2^45 + lo, both accumulated exactly in int64.
+// ---------------------------------------------------------------------------
+struct Fix2 { i64 hi, lo; };
+
+__host__ __device__ __forceinline__ Fix2 fix2_from_double(double x, double inv_q /* 2^(90-e) */,
+                                                 unsigned *overflow) {
+  const double t = x * inv_q;                       // exact power-of-two scaling
+  if (!(fabs(t) < 0x1p90)) { *overflow = 1u; Fix2 z = {0, 0}; return z; }
+  const double h = floor(t * 0x1p-45);              // exact
+  const double r = t - h * 0x1p45;                  // exact, in [0, 2^45)
+  Fix2 f;
+  f.hi = (i64)h;
+  f.lo = (i64)rint(r);
+  return f;
+}
+__host__ __device__ __forceinline__ double fix2_to_double(i64 hi, i64 lo, double q /* 2^(e-90) */) {
+  // hi*2^45 exact (|hi| < 2^53); lo < 2^63 rounds once; the sum rounds once.
+  return ((double)hi * 0x1p45 + (double)lo) * q;
+}
+
+// ---------------------------------------------------------------------------
+// Grid-wide barrier for the persistent kernels (cooperative launch guarantees
+// co-residency).  Monotonic counter; `gen` is the caller's private generation.
+// Returns false if the watchdog expired (never on a healthy run): callers then
+// abandon the solve instead of hanging the device.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ bool grid_barrier(unsigned *counter, unsigned &gen, int *abort_flag) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    gen += 1;
+    const unsigned target = gen * gridDim.x;
+    __threadfence();
+    red_release_add_u32(counter, 1u);
+    int ok = 1;
+    unsigned spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+      if (++spins > (1u << 24)) {  // ~ seconds: a peer CTA is gone; bail out
+        if (*((volatile int *)abort_flag) || spins > (1u << 25)) { ok = 0; break; }
+      }
+      if (spins > 64) __nanosleep(64);
+    }
+    if (!ok) atomicExch(abort_flag, 1);
+    __threadfence();
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// ---------------------------------------------------------------------------
+// fp64 tensor-core MMA (DMMA): D(8x8) += A(8x4) * B(4x8)
+//   a : A[row = lane/4][k = lane%4]
+//   b : B[k = lane%4][col = lane/4]
+//   c0,c1 : C[row = lane/4][col = 2*(lane%4) + {0,1}]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double bf16_bits_to_double(unsigned short b) {
+  return (double)__uint_as_float(((unsigned)b) << 16);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming (L2-only) vector accesses: no L1 allocation, no stale-L1 hazard for
+// data produced by other CTAs earlier in the same persistent kernel
+__device__ __forceinline__ double2 ldcg2(const double *p) {
+  return __ldcg(reinterpret_cast<const double2 *>(p));
+}
+__device__ __forceinline__ void stcg2(double *p, double2 v) {
+  __stcg(reinterpret_cast<double2 *>(p), v);
+}
+
+}  // namespace ob200
