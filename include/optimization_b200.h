@@ -138,6 +138,12 @@ int ob200_stpcg_host(ob200_context *ctx, const ob200_operator *H, const ob200_pr
  * IterativeSolvers.h:294, TNT.h:512). */
 int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v_dev, double *out_dev);
 
+/* Algorithmic HBM bytes of ONE fused tCG step / one stand-alone HVP for this
+ * operator (the roofline numerator; definition in DESIGN.md section 4):
+ *   step = 10 N e + B_op (+ 2 N e with Jacobi),  hvp = 2 N e + B_op,  e = 8. */
+uint64_t ob200_stpcg_step_bytes(const ob200_operator *H, const ob200_precon *P);
+uint64_t ob200_hvp_bytes(const ob200_operator *H);
+
 /* ---- level-1 primitives with the exact, order-independent reduction --------
  * Replace `metric(x, a, b)` (TNT.h:382,387,493,511-512,575,579) and the
  * generic vector expressions of the Krylov loops when the user's Hessian is an

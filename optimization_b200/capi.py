@@ -1,0 +1,138 @@
+"""ctypes binding of liboptimization_b200.so (include/optimization_b200.h).
+
+This is the Python face of the drop-in boundary: every call goes through the C
+ABI exactly as the reference-side C++ host templates do.  There is NO fallback:
+if the shared library (built in-tree by `make -C optimization_b200/csrc` /
+`__graft_entry__.build()`) is missing, importing this module raises, and if no
+GPU is usable `Context()` raises.  torch is used only to own device memory and
+the CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboptimization_b200.so")
+
+OK, INVALID_ARGUMENT, CUDA_ERROR, UNSUPPORTED, NUMERIC_RANGE, ABORTED = range(6)
+EXIT_RESIDUAL, EXIT_MAX_ITERATIONS, EXIT_KERNEL, EXIT_BOUNDARY = range(4)
+EXIT_NAMES = {0: "residual", 1: "max_iterations", 2: "kernel", 3: "boundary"}
+OP_DIAG, OP_STIEFEL_BLOCKDIAG, OP_SPHERE_LOWRANK = 1, 2, 3
+PRECON_NONE, PRECON_JACOBI = 0, 1
+
+# every symbol include/optimization_b200.h declares (checked by the CPU test-suite)
+EXPORTS = [
+    "ob200_create", "ob200_destroy", "ob200_last_error", "ob200_version", "ob200_sm_count",
+    "ob200_synchronize", "ob200_kernel_launches", "ob200_stpcg", "ob200_stpcg_host", "ob200_hvp",
+    "ob200_dot", "ob200_dots", "ob200_axpby", "ob200_hadamard", "ob200_stiefel_model",
+    "ob200_stiefel_retract", "ob200_malloc",
+    "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
+    "ob200_set_allreduce", "ob200_stpcg_step_bytes", "ob200_hvp_bytes",
+]
+
+
+class Operator(C.Structure):
+    _fields_ = [("kind", C.c_int), ("n", C.c_uint64), ("p", C.c_uint64),
+                ("diag_dev", C.c_void_p), ("A_bf16_dev", C.c_void_p), ("Y_dev", C.c_void_p),
+                ("S_host", C.c_void_p), ("op_norm_bound", C.c_double), ("x_dev", C.c_void_p),
+                ("U_dev", C.c_void_p), ("sigma_host", C.c_void_p), ("k", C.c_uint64),
+                ("xAx", C.c_double)]
+
+
+class Precon(C.Structure):
+    _fields_ = [("kind", C.c_int), ("minv_dev", C.c_void_p)]
+
+
+class StpcgParams(C.Structure):
+    _fields_ = [("Delta", C.c_double), ("max_iterations", C.c_uint64), ("kappa_fgr", C.c_double),
+                ("theta", C.c_double), ("epsilon", C.c_double)]
+
+
+class StpcgResult(C.Structure):
+    _fields_ = [("update_step_M_norm", C.c_double), ("num_iterations", C.c_uint64),
+                ("exit_reason", C.c_int), ("r0_norm", C.c_double), ("final_rv", C.c_double),
+                ("kernel_launches", C.c_uint64)]
+
+
+class TntParams(C.Structure):
+    """Field for field TNTParams (reference TNT.h:76-130 + Concepts.h:42-60,116-131)."""
+    _fields_ = [("max_iterations", C.c_uint64), ("max_computation_time", C.c_double),
+                ("gradient_tolerance", C.c_double), ("relative_decrease_tolerance", C.c_double),
+                ("stepsize_tolerance", C.c_double),
+                ("preconditioned_gradient_tolerance", C.c_double),
+                ("Delta_tolerance", C.c_double), ("Delta0", C.c_double), ("eta1", C.c_double),
+                ("eta2", C.c_double), ("alpha1", C.c_double), ("alpha2", C.c_double),
+                ("max_TPCG_iterations", C.c_uint64), ("kappa_fgr", C.c_double),
+                ("theta", C.c_double)]
+
+
+class TntResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("f", C.c_double), ("gradfx_norm", C.c_double),
+                ("preconditioned_grad_f_x_norm", C.c_double), ("elapsed_time", C.c_double),
+                ("n_outer", C.c_uint64), ("n_trace", C.c_uint64), ("cap", C.c_uint64),
+                ("inner_iterations", C.POINTER(C.c_uint64)), ("gain_ratios", C.POINTER(C.c_double)),
+                ("update_step_norms", C.POINTER(C.c_double)),
+                ("update_step_M_norms", C.POINTER(C.c_double)),
+                ("trust_region_radius", C.POINTER(C.c_double)),
+                ("objective_values", C.POINTER(C.c_double)),
+                ("gradient_norms", C.POINTER(C.c_double)), ("kernel_launches", C.c_uint64)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `make -C optimization_b200/csrc` "
+            "(or __graft_entry__.build()).  optimization_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, u64, dbl, i = C.c_void_p, C.c_uint64, C.c_double, C.c_int
+    lib.ob200_create.argtypes = [i, vp, C.POINTER(vp)]
+    lib.ob200_destroy.argtypes = [vp]
+    lib.ob200_last_error.argtypes = [vp]
+    lib.ob200_last_error.restype = C.c_char_p
+    lib.ob200_sm_count.argtypes = [vp]
+    lib.ob200_synchronize.argtypes = [vp]
+    lib.ob200_kernel_launches.argtypes = [vp]
+    lib.ob200_kernel_launches.restype = u64
+    lib.ob200_stpcg.argtypes = [vp, C.POINTER(Operator), C.POINTER(Precon), vp,
+                                C.POINTER(StpcgParams), vp, C.POINTER(StpcgResult)]
+    lib.ob200_stpcg_host.argtypes = lib.ob200_stpcg.argtypes
+    lib.ob200_hvp.argtypes = [vp, C.POINTER(Operator), vp, vp]
+    lib.ob200_dot.argtypes = [vp, u64, vp, vp, C.POINTER(dbl)]
+    lib.ob200_dots.argtypes = [vp, u64, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(dbl)]
+    lib.ob200_axpby.argtypes = [vp, u64, dbl, vp, dbl, vp, vp]
+    lib.ob200_hadamard.argtypes = [vp, u64, vp, vp, vp]
+    lib.ob200_stiefel_model.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(dbl), vp,
+                                        C.POINTER(dbl)]
+    lib.ob200_stiefel_retract.argtypes = [vp, u64, u64, vp, vp, vp]
+    lib.ob200_malloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.ob200_free.argtypes = [vp, vp]
+    lib.ob200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.ob200_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.ob200_malloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.ob200_free_host.argtypes = [vp, vp]
+    lib.ob200_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, i, i]
+    lib.ob200_stpcg_step_bytes.argtypes = [C.POINTER(Operator), C.POINTER(Precon)]
+    lib.ob200_stpcg_step_bytes.restype = u64
+    lib.ob200_hvp_bytes.argtypes = [C.POINTER(Operator)]
+    lib.ob200_hvp_bytes.restype = u64
+    return lib
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = load_library()
+    return _LIB
+
+
+class Ob200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ob200 status {code}: {msg}")
+        self.code = code

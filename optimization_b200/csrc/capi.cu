@@ -368,6 +368,26 @@ int ob200_stpcg_host(ob200_context *ctx, const ob200_operator *H, const ob200_pr
   return OB200_OK;
 }
 
+static uint64_t op_bytes(const ob200_operator *H) {
+  const uint64_t N = H->n * H->p;
+  switch (H->kind) {
+    case OB200_OP_DIAG: return 8 * N;                                   // d read once
+    case OB200_OP_STIEFEL_BLOCKDIAG:                                    // A (bf16) + Y read twice
+      return ((H->n + 127) / 128) * 128 * 128 * 2 + 2 * 8 * N;
+    case OB200_OP_SPHERE_LOWRANK: return 8 * H->n * (2 + H->k);         // d, x, U
+    default: return 0;
+  }
+}
+uint64_t ob200_stpcg_step_bytes(const ob200_operator *H, const ob200_precon *P) {
+  if (!H) return 0;
+  const uint64_t N = H->n * H->p;
+  return 10 * 8 * N + op_bytes(H) + ((P && P->kind == OB200_PRECON_JACOBI) ? 2 * 8 * N : 0);
+}
+uint64_t ob200_hvp_bytes(const ob200_operator *H) {
+  if (!H) return 0;
+  return 2 * 8 * H->n * H->p + op_bytes(H);
+}
+
 int ob200_dot(ob200_context *ctx, uint64_t n, const double *a, const double *b, double *result) {
   if (!ctx || !a || !b || !result) return OB200_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));

@@ -1,0 +1,206 @@
+"""Python host-side handle over the C ABI: contexts, operators, tCG solves.
+
+torch owns device memory and the stream (plumbing only); every arithmetic
+statement of the hot path executes inside liboptimization_b200.so.  Names and
+argument meaning follow the reference (`STPCG(g, H, inner_product, ...,
+Delta, max_iterations, kappa_fgr, theta, P, ..., epsilon)`,
+IterativeSolvers.h:166-179); bad parameters raise ValueError where the
+reference throws std::invalid_argument (IterativeSolvers.h:183-205).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous()
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        assert t.flags.c_contiguous
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(int(t))
+
+
+@dataclasses.dataclass
+class StpcgOutput:
+    s: object
+    update_step_M_norm: float
+    num_iterations: int
+    exit_reason: str
+    r0_norm: float
+    final_rv: float
+    kernel_launches: int
+
+
+class Context:
+    """One per GPU / process.  Work is issued on torch's current stream of `device`."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("optimization_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = capi.lib()
+        self.device = int(device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        rc = self.lib.ob200_create(self.device, C.c_void_p(self.stream.cuda_stream), C.byref(h))
+        if rc != capi.OK:
+            raise capi.Ob200Error(rc, "ob200_create failed (no usable GPU?)")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ob200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------
+    def _check(self, rc):
+        if rc == capi.OK:
+            return
+        msg = self.lib.ob200_last_error(self.h).decode()
+        if rc == capi.INVALID_ARGUMENT:
+            raise ValueError(msg)          # reference: std::invalid_argument
+        raise capi.Ob200Error(rc, msg)
+
+    def to_device(self, a: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a)).to(f"cuda:{self.device}")
+
+    @property
+    def sm_count(self):
+        return self.lib.ob200_sm_count(self.h)
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.ob200_kernel_launches(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.ob200_synchronize(self.h))
+
+    # -- operators ---------------------------------------------------------------
+    def diag_operator(self, d: torch.Tensor) -> "OperatorHandle":
+        op = capi.Operator()
+        op.kind = capi.OP_DIAG
+        op.n = d.numel()
+        op.p = 1
+        op.diag_dev = d.data_ptr()
+        return OperatorHandle(self, op, [d])
+
+    def stiefel_operator(self, A_bf16: torch.Tensor, Y: torch.Tensor) -> "OperatorHandle":
+        """Hess f(Y)[V] = P_Y(A V - V sym(Y^T A Y)); computes S on the device."""
+        n, p = Y.shape
+        S = np.zeros((p, p))
+        f = C.c_double(0)
+        bound = C.c_double(0)
+        self._check(self.lib.ob200_stiefel_model(self.h, n, p, _ptr(A_bf16), _ptr(Y), _ptr(S),
+                                                 C.byref(f), None, C.byref(bound)))
+        op = capi.Operator()
+        op.kind = capi.OP_STIEFEL_BLOCKDIAG
+        op.n, op.p = n, p
+        op.A_bf16_dev = A_bf16.data_ptr()
+        op.Y_dev = Y.data_ptr()
+        op.S_host = S.ctypes.data
+        op.op_norm_bound = bound.value
+        h = OperatorHandle(self, op, [A_bf16, Y, S])
+        h.S, h.f = S, f.value
+        return h
+
+    def jacobi(self, minv: torch.Tensor | None):
+        pc = capi.Precon()
+        if minv is None:
+            pc.kind = capi.PRECON_NONE
+            pc.minv_dev = None
+        else:
+            pc.kind = capi.PRECON_JACOBI
+            pc.minv_dev = minv.data_ptr()
+        return pc
+
+    # -- the hot path --------------------------------------------------------------
+    def stpcg(self, g, H: "OperatorHandle", Delta, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
+              minv=None, epsilon=1e-8, s_out=None, host=False) -> StpcgOutput:
+        """Steihaug-Toint truncated preconditioned CG (IterativeSolvers.h:166-426).
+
+        g: torch cuda tensor (device entry) or, with host=True, a numpy array /
+        pinned torch CPU tensor (copies are part of the call)."""
+        prm = capi.StpcgParams(float(Delta), int(max_iterations), float(kappa_fgr), float(theta),
+                               float(epsilon))
+        res = capi.StpcgResult()
+        pc = self.jacobi(minv)
+        if host:
+            if s_out is None:
+                s_out = np.empty_like(g) if isinstance(g, np.ndarray) else torch.empty_like(g)
+            rc = self.lib.ob200_stpcg_host(self.h, C.byref(H.op), C.byref(pc), _ptr(g),
+                                           C.byref(prm), _ptr(s_out), C.byref(res))
+        else:
+            if s_out is None:
+                s_out = torch.empty_like(g)
+            rc = self.lib.ob200_stpcg(self.h, C.byref(H.op), C.byref(pc), _ptr(g), C.byref(prm),
+                                      _ptr(s_out), C.byref(res))
+        self._check(rc)
+        return StpcgOutput(s_out, res.update_step_M_norm, int(res.num_iterations),
+                           capi.EXIT_NAMES.get(res.exit_reason, str(res.exit_reason)),
+                           res.r0_norm, res.final_rv, int(res.kernel_launches))
+
+    def hvp(self, H: "OperatorHandle", v: torch.Tensor, out=None):
+        if out is None:
+            out = torch.empty_like(v)
+        self._check(self.lib.ob200_hvp(self.h, C.byref(H.op), _ptr(v), _ptr(out)))
+        return out
+
+    # -- level 1 -------------------------------------------------------------------
+    def dot(self, a: torch.Tensor, b: torch.Tensor) -> float:
+        r = C.c_double(0)
+        self._check(self.lib.ob200_dot(self.h, a.numel(), _ptr(a), _ptr(b), C.byref(r)))
+        return r.value
+
+    def axpby(self, alpha, x, beta, y, out=None):
+        if out is None:
+            out = torch.empty_like(x)
+        self._check(self.lib.ob200_axpby(self.h, x.numel(), float(alpha), _ptr(x), float(beta),
+                                         _ptr(y), _ptr(out)))
+        return out
+
+    def stiefel_model(self, A_bf16, Y, want_grad=True):
+        n, p = Y.shape
+        S = np.zeros((p, p))
+        f = C.c_double(0)
+        bound = C.c_double(0)
+        grad = torch.empty_like(Y) if want_grad else None
+        self._check(self.lib.ob200_stiefel_model(self.h, n, p, _ptr(A_bf16), _ptr(Y), _ptr(S),
+                                                 C.byref(f), _ptr(grad), C.byref(bound)))
+        return S, f.value, grad, bound.value
+
+    def stiefel_retract(self, Y, V, out=None):
+        n, p = Y.shape
+        if out is None:
+            out = torch.empty_like(Y)
+        self._check(self.lib.ob200_stiefel_retract(self.h, n, p, _ptr(Y), _ptr(V), _ptr(out)))
+        return out
+
+
+class OperatorHandle:
+    def __init__(self, ctx, op, keep):
+        self.ctx, self.op, self._keep = ctx, op, keep
+
+    def step_bytes(self, precon=False):
+        pc = capi.Precon()
+        pc.kind = capi.PRECON_JACOBI if precon else capi.PRECON_NONE
+        return int(self.ctx.lib.ob200_stpcg_step_bytes(C.byref(self.op), C.byref(pc)))
+
+    def hvp_bytes(self):
+        return int(self.ctx.lib.ob200_hvp_bytes(C.byref(self.op)))

@@ -134,6 +134,28 @@ def make_stiefel(n: int, p: int = 32, nb: int = 128, seed: int = 21,
     return StiefelProblem(n, p, nb, to_bf16_bits(A), Y0, np.ascontiguousarray(g))
 
 
+def make_stiefel_critical(n: int, p: int = 32, nb: int = 128, seed: int = 21,
+                          diag_width: float = 28.0) -> StiefelProblem:
+    """Stand-alone tCG workload (config C3 throughput runs): Y0 = E_L Q is an exact
+    minimiser (E_L spans the eigenvalue-1 invariant subspace of A, Q a p x p
+    rotation), so Hess f(Y0) = P(A V - V) is positive definite on the horizontal
+    space (spectrum within [~1.7, ~31]) and CG runs a natural 50-80 iterations to
+    1e-12; g is a horizontal tangent (Y0^T g = 0), like a Riemannian gradient.
+    Away from critical points the trace-min Hessian on St(n,p) is indefinite (the
+    cost is invariant under Y -> Y Q), and tCG leaves through the trust-region
+    boundary after a handful of iterations: `make_stiefel` covers that regime."""
+    L = low_rows(n, p)
+    A = stiefel_rows(n, nb, 0, n, seed, diag_width, L)
+    Qm, Rq = np.linalg.qr(gaussish(seed + 5, 0, p * p).reshape(p, p))
+    Qm = Qm * np.sign(np.diag(Rq))[None, :]
+    Y0 = np.zeros((n, p))
+    Y0[L, :] = Qm
+    N = gaussish(seed + 2, 0, n * p).reshape(n, p)
+    g = N - Y0 @ (Y0.T @ N)
+    g = g - Y0 @ (Y0.T @ g)
+    return StiefelProblem(n, p, nb, to_bf16_bits(A), np.ascontiguousarray(Y0), np.ascontiguousarray(g))
+
+
 def stiefel_hess_numpy(prob: StiefelProblem, Y: np.ndarray, V: np.ndarray) -> np.ndarray:
     """Dense numpy Hess f(Y)[V] = P_Y(A V - V sym(Y^T A Y)); small n only."""
     A = prob.A_dense_blocks()

@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads and exports every symbol include/optimization_b200.h
+declares; header and ctypes mirror agree; no compute calls (no GPU here)."""
+import os
+import re
+
+from optimization_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "optimization_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ob200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(capi.EXPORTS) == syms
+    assert lib.ob200_version() >= 100
+
+
+def test_create_fails_loudly_without_gpu():
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        return
+    lib = capi.load_library()
+    h = C.c_void_p()
+    assert lib.ob200_create(0, None, C.byref(h)) == capi.CUDA_ERROR
+    assert not h.value
+
+
+def test_byte_model():
+    import ctypes as C
+    lib = capi.load_library()
+    op = capi.Operator()
+    op.kind, op.n, op.p = capi.OP_STIEFEL_BLOCKDIAG, 100000, 32
+    pc = capi.Precon()
+    N = 100000 * 32
+    A = 782 * 128 * 128 * 2
+    assert lib.ob200_stpcg_step_bytes(C.byref(op), C.byref(pc)) == 12 * 8 * N + A
+    assert lib.ob200_hvp_bytes(C.byref(op)) == 4 * 8 * N + A
+    op.kind, op.n, op.p = capi.OP_DIAG, 1000, 1
+    assert lib.ob200_stpcg_step_bytes(C.byref(op), C.byref(pc)) == 11 * 8 * 1000
+    pc.kind = capi.PRECON_JACOBI
+    assert lib.ob200_stpcg_step_bytes(C.byref(op), C.byref(pc)) == 13 * 8 * 1000
+
+
+def test_product_never_imports_oracle():
+    pk = os.path.join(ROOT, "optimization_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./](refapi|_ref|stpcg_port|liboracle)",
+                                     txt, flags=re.M), f

@@ -1,0 +1,230 @@
+"""GPU: parity of the fused CUDA tCG path (through the C ABI) against the CPU
+oracle (oracle/stpcg_port.c, pinned by tests/test_oracle.py) and the committed
+golden fixtures from the unmodified reference headers.
+
+Bar (BASELINE.json north_star): iteration counts and exit reasons bit-exact,
+iterates within 1e-10 relative.  RTOL below is that tolerance."""
+import math
+
+import numpy as np
+import pytest
+
+from optimization_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+DBL_MAX = 1.7976931348623157e308
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from optimization_b200.device import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def port(build_oracle):
+    from oracle import refapi
+    return refapi.PortOracle()
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def run_diag(ctx, g, h, minv=None, **kw):
+    H = ctx.diag_operator(ctx.to_device(h))
+    out = ctx.stpcg(ctx.to_device(g), H, minv=None if minv is None else ctx.to_device(minv), **kw)
+    return out.s.cpu().numpy(), out
+
+
+# ---- the reference's own known-answer tests -----------------------------------
+def test_kats_against_golden(ctx, golden):
+    rec, _ = golden
+    for name in ("ExactSTPCG", "ExactSTPCGwithNegativeCurvature", "ExactSTPCGwithPreconditioning",
+                 "ExactSTPCGwithNegativeCurvatureAndPreconditioning"):
+        a = rec[name]["args"]
+        minv = None if a["minv"] is None else np.array(a["minv"])
+        s, out = run_diag(ctx, np.array(a["g"]), np.array(a["h"]), minv, Delta=a["Delta"],
+                          max_iterations=a["max_iterations"], kappa_fgr=a["kappa_fgr"], theta=a["theta"])
+        assert out.num_iterations == rec[name]["num_iterations"], name
+        assert rel(s, rec[name]["s"]) < RTOL, name
+        assert abs(out.update_step_M_norm - rec[name]["update_step_M_norm"]) <= RTOL * rec[name]["update_step_M_norm"]
+
+
+def test_kat_closed_forms(ctx):
+    g3, H3 = np.array([21., -.4, 19.]), np.array([1000., 100., 1.])
+    s, out = run_diag(ctx, g3, H3, Delta=DBL_MAX, max_iterations=3, kappa_fgr=1e-8, theta=.999)
+    assert np.linalg.norm(s + g3 / H3) < 1e-6 and out.num_iterations == 3
+    s, out = run_diag(ctx, g3, -H3, Delta=1000., max_iterations=3, kappa_fgr=1e-8, theta=.999)
+    assert np.linalg.norm(s + 1000. * g3 / np.linalg.norm(g3)) < 1e-6
+    assert out.num_iterations == 0 and out.exit_reason == "boundary" and out.update_step_M_norm == 1000.
+
+
+# ---- diagonal operator, seeded data --------------------------------------------
+def test_diag_golden(ctx, golden):
+    rec, arr = golden
+    dp = P.make_diag(1000, seed=5)
+    for name, minv in (("diag1000_trunc", None), ("diag1000_precon_trunc", dp.minv),
+                       ("diag1000_tight", None), ("diag1000_boundary", None)):
+        s, out = run_diag(ctx, dp.g, dp.h, minv, **rec[name]["args"])
+        assert out.num_iterations == rec[name]["num_iterations"], name
+        assert rel(s, arr[name + "_s"]) < RTOL, name
+        assert abs(out.update_step_M_norm - rec[name]["update_step_M_norm"]) <= RTOL * rec[name]["update_step_M_norm"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 4099, 100003, 1 << 20])
+@pytest.mark.parametrize("precon", [False, True])
+def test_diag_vs_oracle_ragged(ctx, port, n, precon):
+    dp = P.make_diag(n, seed=7 + n % 13)
+    minv = dp.minv if precon else None
+    for kw in (dict(Delta=1e6, max_iterations=40, kappa_fgr=1e-10, theta=0.),
+               dict(Delta=1e-3, max_iterations=40, kappa_fgr=.1, theta=.5),
+               dict(Delta=1e6, max_iterations=3, kappa_fgr=1e-10, theta=0.)):
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_diag(dp.g, dp.h, minv, **kw)
+        s, out = run_diag(ctx, dp.g, dp.h, minv, **kw)
+        assert out.num_iterations == it_ref
+        assert out.exit_reason == why_ref
+        assert rel(s, s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+
+
+def test_diag_indefinite_and_kernel(ctx, port):
+    n = 5000
+    dp = P.make_diag(n, seed=3)
+    h = dp.h.copy()
+    h[::7] *= -1.0                     # indefinite: negative curvature exit
+    kw = dict(Delta=50., max_iterations=100, kappa_fgr=1e-8, theta=0.)
+    s_ref, mn_ref, it_ref, why_ref = port.stpcg_diag(dp.g, h, None, **kw)
+    s, out = run_diag(ctx, dp.g, h, None, **kw)
+    assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+    assert rel(s, s_ref) < RTOL and out.update_step_M_norm == mn_ref == 50.
+    # H = 0: p lies in ker(H) (IterativeSolvers.h:305-337)
+    z = np.zeros(n)
+    s_ref, mn_ref, it_ref, why_ref = port.stpcg_diag(dp.g, z, None, **kw)
+    s, out = run_diag(ctx, dp.g, z, None, **kw)
+    assert why_ref == "kernel" and (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+    assert rel(s, s_ref) < RTOL
+
+
+def test_invalid_arguments_raise(ctx):
+    g3, H3 = np.array([21., -.4, 19.]), np.array([1000., 100., 1.])
+    for kw in (dict(Delta=0.), dict(Delta=-1.), dict(kappa_fgr=1.), dict(kappa_fgr=-.1), dict(theta=1.5),
+               dict(theta=-.1), dict(epsilon=0.), dict(epsilon=1.)):
+        args = dict(Delta=1., max_iterations=3, kappa_fgr=.1, theta=.5, epsilon=1e-8)
+        args.update(kw)
+        with pytest.raises(ValueError):
+            run_diag(ctx, g3, H3, **args)
+
+
+# ---- exact reductions ---------------------------------------------------------------
+def test_dot_is_correctly_rounded(ctx):
+    rng = np.random.default_rng(0)
+    for n in (1, 31, 256, 1000, 65537, 3_200_000):
+        a = rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))
+        b = rng.standard_normal(n)
+        got = ctx.dot(ctx.to_device(a), ctx.to_device(b))
+        # unit partials are fma-chains of 256 elements: compare with fsum of exact products (tolerance 2 ulp of
+        # the partial-sum magnitude), and check bitwise run-to-run determinism
+        want = math.fsum((a * b).tolist())
+        scale = math.fsum(np.abs(a * b).tolist())
+        assert abs(got - want) <= 1e-13 * scale
+        assert got == ctx.dot(ctx.to_device(a), ctx.to_device(b))
+
+
+# ---- Stiefel block-diagonal Hessian ----------------------------------------------------
+def stiefel_setup(ctx, prob):
+    import torch
+    A = torch.from_numpy(prob.A_bf16.astype(np.int16)).to("cuda:0")   # bit pattern
+    Y = ctx.to_device(prob.Y0)
+    return A, Y, ctx.stiefel_operator(A, Y)
+
+
+@pytest.mark.parametrize("tag,maker", [("stiefel512_yn1", lambda: P.make_stiefel(512, 32, y_noise=.1)),
+                                       ("stiefel512_yn3", lambda: P.make_stiefel(512, 32, y_noise=.3)),
+                                       ("stiefel1000_yn1", lambda: P.make_stiefel(1000, 32, y_noise=.1)),
+                                       ("stiefelcrit512", lambda: P.make_stiefel_critical(512, 32)),
+                                       ("stiefelcrit1000", lambda: P.make_stiefel_critical(1000, 32))])
+def test_stiefel_stpcg_golden(ctx, golden, tag, maker):
+    rec, arr = golden
+    prob = maker()
+    A, Y, H = stiefel_setup(ctx, prob)
+    if tag + "_S" in arr:
+        assert rel(H.S, arr[tag + "_S"]) < RTOL
+        assert abs(H.f - rec[tag + "_f"]) <= RTOL * abs(rec[tag + "_f"])
+    for name in ("tight", "default", "boundary"):
+        r = rec[f"{tag}_{name}"]
+        out = ctx.stpcg(ctx.to_device(prob.g), H, **r["args"])
+        assert out.num_iterations == r["num_iterations"], name
+        s_ref = arr[f"{tag}_{name}_s"]
+        if np.all(np.isfinite(s_ref)):
+            assert rel(out.s.cpu().numpy(), s_ref) < RTOL, name
+        assert abs(out.update_step_M_norm - r["update_step_M_norm"]) <= RTOL * r["update_step_M_norm"], name
+
+
+@pytest.mark.parametrize("n", [128, 300, 4096, 20000])
+def test_stiefel_stpcg_vs_oracle(ctx, port, n):
+    for prob in (P.make_stiefel_critical(n, 32), P.make_stiefel(n, 32, y_noise=.2)):
+        A, Y, H = stiefel_setup(ctx, prob)
+        for kw in (dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.),
+                   dict(Delta=3.0, max_iterations=60, kappa_fgr=1e-3, theta=.5)):
+            s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
+            out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+            assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+            assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+            assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+
+
+def test_stiefel_hvp_model_retract_golden(ctx, golden):
+    rec, arr = golden
+    tag = "stiefel512_yn1"
+    prob = P.make_stiefel(512, 32, y_noise=.1)
+    A, Y, H = stiefel_setup(ctx, prob)
+    hv = ctx.hvp(H, ctx.to_device(prob.g)).cpu().numpy()
+    assert rel(hv, arr[tag + "_hess_g"]) < RTOL
+    S, f, grad, bound = ctx.stiefel_model(A, Y)
+    assert rel(S, arr[tag + "_S"]) < RTOL and rel(grad.cpu().numpy(), arr[tag + "_grad"]) < RTOL
+    # retraction: orthonormal columns, same column space as Y + V, first-order agreement
+    V = ctx.to_device(0.01 * prob.g)
+    Q = ctx.stiefel_retract(Y, V).cpu().numpy()
+    assert np.linalg.norm(Q.T @ Q - np.eye(32)) < 1e-12
+    Z = prob.Y0 + 0.01 * prob.g
+    Qn, Rn = np.linalg.qr(Z)
+    Qn = Qn * np.sign(np.diag(Rn))[None, :]
+    assert rel(Q, Qn) < 1e-10
+
+
+# ---- BASELINE size: size-independent properties ------------------------------------------
+def test_stiefel_full_size_properties(ctx):
+    import torch
+    prob = P.make_stiefel_critical(100000, 32)
+    A, Y, H = stiefel_setup(ctx, prob)
+    g = ctx.to_device(prob.g)
+    kw = dict(Delta=1e6, max_iterations=200, kappa_fgr=1e-9, theta=0.)
+    o1 = ctx.stpcg(g, H, **kw)
+    s1 = o1.s.clone()
+    o2 = ctx.stpcg(g, H, **kw)
+    assert o1.exit_reason == "residual" and 20 < o1.num_iterations < 200
+    # bitwise run-to-run determinism (exact reductions)
+    assert o1.num_iterations == o2.num_iterations and o1.update_step_M_norm == o2.update_step_M_norm
+    assert torch.equal(s1, o2.s)
+    # residual reduction ||g + H s|| <= kappa ||g||  (the property the reference tests, :254-275)
+    Hs = ctx.hvp(H, s1)
+    r = (g + Hs)
+    assert math.sqrt(ctx.dot(r, r)) <= 1.0001 * 1e-9 * math.sqrt(ctx.dot(g, g))
+    # reported M-norm equals the Frobenius norm of s (recurrence, IterativeSolvers.h:415-424)
+    assert abs(o1.update_step_M_norm - math.sqrt(ctx.dot(s1, s1))) <= 1e-9 * o1.update_step_M_norm
+    # s is tangent at Y: sym(Y^T s) = 0
+    G = (Y.T @ s1).cpu().numpy()
+    assert np.linalg.norm(G + G.T) <= 1e-9 * np.linalg.norm(s1.cpu().numpy())
+    # linearity of the HVP
+    v = ctx.to_device(P.make_stiefel(100000, 32, y_noise=.1).g)
+    lhs = ctx.hvp(H, ctx.axpby(2.0, g, -3.0, v)).cpu().numpy()
+    rhs = 2.0 * ctx.hvp(H, g).cpu().numpy() - 3.0 * ctx.hvp(H, v).cpu().numpy()
+    assert rel(lhs, rhs) < 1e-12
+    # host-buffer entry gives the same result as the device entry
+    oh = ctx.stpcg(prob.g, H, host=True, **kw)
+    assert oh.num_iterations == o1.num_iterations and np.array_equal(oh.s, s1.cpu().numpy())
