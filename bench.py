@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- tCG iterations/second on Stiefel(1e5,32) (BASELINE.json metric).
+
+A "step" is one whole Steihaug-Toint truncated-CG solve (reference
+IterativeSolvers.h:166-426) of the trace-min Hessian system at the
+Stiefel(100000, 32) workload `make_stiefel_critical` (block-diagonal A stored in
+bf16, fp64 tangent vectors), stopped at relative residual 1e-9 (natural CG
+convergence, about 40 iterations).  value = tCG iterations completed / second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torch.distributed.run (one rank per GPU); the tangent
+vectors are row-sharded and every rank works on ONE problem (strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "tCG iters/sec on Stiefel(1e5,32)"
+UNIT = "iterations/s"
+SOLVE = dict(Delta=1e6, max_iterations=200, kappa_fgr=1e-9, theta=0.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n):
+    return (f"Stiefel({n},32) trace-min Hessian tCG, make_stiefel_critical(seed=21), block-diag A bf16 "
+            f"(128x128 blocks), fp64 vectors, Delta=1e6 kappa_fgr=1e-9 theta=0 max_iterations=200")
+
+
+# ----------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------
+# CPU reference arm: the reference's own STPCG header (oracle/_ref) on host cores
+# ----------------------------------------------------------------------------------
+def cpu_reference(prob, max_iterations, repeats=1):
+    """Times the reference CPU path on a bounded sample: ONE solve of the same
+    workload capped at `max_iterations` CG iterations, all host threads."""
+    from oracle import refapi
+    kind = "reference"
+    try:
+        R = refapi.RefOracle()
+        threads = R.max_threads()
+        R.set_threads(threads)
+        rs = R.stiefel(prob)
+
+        def run():
+            return rs.stpcg(prob.Y0, prob.g, **dict(SOLVE, max_iterations=max_iterations))[2]
+    except (FileNotFoundError, OSError):
+        kind = "port"
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+        Pt = refapi.PortOracle()
+        threads = 1
+
+        def run():
+            return Pt.stpcg_stiefel(prob, prob.Y0, prob.g, **dict(SOLVE, max_iterations=max_iterations))[2]
+    best = None
+    its = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        its = run()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return dict(value=its / best, unit=UNIT, cores=threads, kind=kind, seconds=best, iterations=its,
+                sample=f"one solve capped at {max_iterations} CG iterations ({its} run) of the same workload, "
+                       f"{threads} OpenMP threads of {os.cpu_count()} host cores; HostMat stand-in for Eigen")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from optimization_b200 import problems as P
+    prob = P.make_stiefel_critical(args.n, 32)
+    cap = 12
+    for _ in range(args.warmup):
+        cpu_reference(prob, 2)
+    t0 = time.perf_counter()
+    its = 0
+    info = None
+    for _ in range(args.steps):
+        info = cpu_reference(prob, cap)
+        its += info["iterations"]
+    dt = time.perf_counter() - t0
+    v = its / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args.n),
+                                            "step": f"one reference STPCG solve capped at {cap} iterations"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                             "sample": info["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from optimization_b200 import problems as P
+    from optimization_b200.device import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ctx = Context(local)
+    n = args.n
+    prob = P.make_stiefel_critical(n, 32)
+    N = n * 32
+    if world > 1:
+        from optimization_b200.sharded import ShardedStiefel
+        solver = ShardedStiefel(ctx, prob, rank, world)
+    else:
+        from optimization_b200.sharded import SingleStiefel
+        solver = SingleStiefel(ctx, prob)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) -------------------------------------------
+    for _ in range(args.warmup):
+        solver.solve_device(**SOLVE)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.kernel_launches
+    barrier()
+    ev0.record()
+    iters = 0
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        out = solver.solve_device(**SOLVE)
+        iters += out.num_iterations
+        kernel_ms += out.solve_kernel_ms
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        kt = torch.tensor([kernel_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+        kernel_ms = float(kt.item())
+    value = iters / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (e2e) -----------------------
+    for _ in range(2):
+        solver.solve_host(**SOLVE)
+    barrier()
+    ev0.record()
+    it_e2e = 0
+    for _ in range(args.steps):
+        it_e2e += solver.solve_host(**SOLVE).num_iterations
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        step_bytes = solver.step_bytes_total()           # algorithmic bytes of one CG step, whole problem
+        per_launch_bytes = step_bytes * (iters / args.steps) / world     # per GPU, per persistent-kernel launch
+        per_launch_s = (kernel_ms / args.steps) * 1e-3
+        achieved = per_launch_bytes / per_launch_s / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(n), "cg_iterations_per_step": iters / args.steps,
+                           "l2": "working set 7 x 25.6 MB vectors + 25.6 MB A per solve exceeds the 126 MB L2; "
+                                 "no explicit flush", "parallelism": f"row-shard x{world}"},
+                "roofline": {"bound": "hbm", "kernel": solver.kernel_name, "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                             "traffic": solver.ncu_traffic_per_launch(iters / args.steps),
+                             "algorithmic_bytes_per_cg_step": step_bytes,
+                             "kernel_ms_per_launch": kernel_ms / args.steps,
+                             "kernel_share_of_step": kernel_ms / ms},
+                "e2e": {"value": it_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * N,
+                        "d2h_bytes_per_step": 8 * N, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks}
+        if not args.no_cpu_baseline:
+            info = cpu_reference(prob, 12)
+            line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,11 @@ int ob200_synchronize(ob200_context *ctx);
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 uint64_t ob200_kernel_launches(const ob200_context *ctx);
 
+/* Profiling aid: when enabled, the persistent tCG kernels accumulate, per CTA, the
+ * nanoseconds spent in {phase A, A reduction+barrier, phase B, B reduction+barrier};
+ * a call with non-null outputs returns the max / min over CTAs and resets them. */
+int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, uint64_t *out4_min);
+
 /* ---- Hessian operator descriptors -----------------------------------------
  * Replaces the user's `Riemannian::LinearOperator` Hessian functor
  * (reference Riemannian/Concepts.h:49-51, bound to x at TNT.h:400-403 and
@@ -115,6 +120,8 @@ typedef struct {
   double r0_norm;            /* l.275 */
   double final_rv;           /* last <r, v> */
   uint64_t kernel_launches;  /* kernels launched by this call */
+  float solve_kernel_ms;     /* device time of the persistent fused tCG kernel alone
+                                (CUDA events on the context's stream around its launch) */
 } ob200_stpcg_result;
 
 /* Steihaug-Toint truncated preconditioned CG, whole solve on the device.
@@ -183,13 +190,20 @@ int ob200_malloc_host(ob200_context *ctx, size_t bytes, void **ptr_host); /* pin
 int ob200_free_host(ob200_context *ctx, void *ptr_host);
 
 /* ---- multi-GPU (row-block sharding, one process per GPU) --------------------
- * Each rank holds a contiguous row block (multiple of 128 rows) of every n x p
- * matrix.  Reductions are exchanged as exact integer accumulators, so results
- * are bit-identical for any world size.  The host (torch.distributed or MPI)
- * supplies the all-reduce as a callback over int64 buffers in DEVICE memory. */
-typedef int (*ob200_allreduce_i64_fn)(void *user, void *buf_dev, uint64_t count);
-int ob200_set_allreduce(ob200_context *ctx, ob200_allreduce_i64_fn fn, void *user, int rank,
-                        int world_size);
+ * Each rank holds a contiguous row block (a multiple of 128 rows) of every n x p
+ * matrix and passes its LOCAL row count / pointers to the calls above.  All
+ * reductions are exchanged as exact integer accumulators through NVLink peer
+ * memory from inside the kernels (no host round trip, no NCCL call on the data
+ * path), so results are bit-identical for any world size.  Set-up: every rank
+ * exports a 64-byte CUDA IPC handle, the host exchanges the handles (e.g.
+ * torch.distributed all_gather), every rank connects.  All ranks must then issue
+ * the same sequence of library calls. */
+#define OB200_COMM_HANDLE_BYTES 64
+int ob200_comm_export(ob200_context *ctx, void *handle_out /* 64 bytes */);
+int ob200_comm_connect(ob200_context *ctx, int rank, int world_size,
+                       const void *handles /* world_size x 64 bytes, rank order */);
+int ob200_comm_rank(const ob200_context *ctx);
+int ob200_comm_world(const ob200_context *ctx);
 
 #ifdef __cplusplus
 }

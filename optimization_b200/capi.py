@@ -28,7 +28,8 @@ EXPORTS = [
     "ob200_dot", "ob200_dots", "ob200_axpby", "ob200_hadamard", "ob200_stiefel_model",
     "ob200_stiefel_retract", "ob200_malloc",
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
-    "ob200_set_allreduce", "ob200_stpcg_step_bytes", "ob200_hvp_bytes",
+    "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
+    "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
 ]
 
 
@@ -52,7 +53,7 @@ class StpcgParams(C.Structure):
 class StpcgResult(C.Structure):
     _fields_ = [("update_step_M_norm", C.c_double), ("num_iterations", C.c_uint64),
                 ("exit_reason", C.c_int), ("r0_norm", C.c_double), ("final_rv", C.c_double),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("solve_kernel_ms", C.c_float)]
 
 
 class TntParams(C.Structure):
@@ -79,7 +80,7 @@ class TntResult(C.Structure):
                 ("gradient_norms", C.POINTER(C.c_double)), ("kernel_launches", C.c_uint64)]
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+COMM_HANDLE_BYTES = 64
 
 
 def load_library(path: str = LIB_PATH) -> C.CDLL:
@@ -114,11 +115,15 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     lib.ob200_malloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.ob200_free_host.argtypes = [vp, vp]
-    lib.ob200_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, i, i]
+    lib.ob200_comm_export.argtypes = [vp, vp]
+    lib.ob200_comm_connect.argtypes = [vp, i, i, vp]
+    lib.ob200_comm_rank.argtypes = [vp]
+    lib.ob200_comm_world.argtypes = [vp]
     lib.ob200_stpcg_step_bytes.argtypes = [C.POINTER(Operator), C.POINTER(Precon)]
     lib.ob200_stpcg_step_bytes.restype = u64
     lib.ob200_hvp_bytes.argtypes = [C.POINTER(Operator)]
     lib.ob200_hvp_bytes.restype = u64
+    lib.ob200_debug_phase_times.argtypes = [vp, i, C.POINTER(u64), C.POINTER(u64)]
     return lib
 
 

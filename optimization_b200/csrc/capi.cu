@@ -12,6 +12,8 @@
 #include <vector>
 
 namespace ob200 {
+cudaError_t launch_tcg_exchange(const CommDev &cm, unsigned long long gphase, u64 *set, int off, int count,
+                                int mode, int *abort_flag, cudaStream_t st);
 cudaError_t launch_tcg_init(const TcgCommon &a, int grid, cudaStream_t st);
 cudaError_t launch_tcg_finalize(const u64 *acc, int slot, double *out, cudaStream_t st);
 cudaError_t launch_tcg_diag(const TcgCommon &a, const double *hdiag, int grid, cudaStream_t st);
@@ -62,10 +64,16 @@ struct ob200_context {
   u64 *hacc = nullptr;            // ACC_WORDS
   double *hmat = nullptr;         // 32*32
   // multi-GPU
-  ob200_allreduce_i64_fn allreduce = nullptr;
-  void *allreduce_user = nullptr;
-  int rank = 0, world = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned long long *dbg = nullptr;   // per-CTA phase timers (ob200_debug_phase_times)
+  // multi-GPU exchange (CUDA IPC peer memory)
+  CommDev cm;                     // rank, world, epoch, peer pointers
+  u64 *comm_buf = nullptr;        // own inbox + flags
+  void *peer_base[MAX_RANKS] = {nullptr};
 };
+
+static const size_t COMM_INBOX_WORDS = (size_t)ACC_SLOTS * MAX_RANKS * ACC_WORDS;
+static const size_t COMM_FLAG_WORDS = (size_t)ACC_SLOTS * MAX_RANKS;
 
 #define CK(call)                                                                        \
   do {                                                                                  \
@@ -118,6 +126,11 @@ int ob200_create(int device, void *stream, ob200_context **out) {
   CK(cudaMallocHost(&ctx->hscal, sizeof(double) * 8));
   CK(cudaMallocHost(&ctx->hacc, sizeof(u64) * ACC_WORDS));
   CK(cudaMallocHost(&ctx->hmat, sizeof(double) * 32 * 32));
+  CK(cudaEventCreate(&ctx->ev0));
+  CK(cudaEventCreate(&ctx->ev1));
+  memset(&ctx->cm, 0, sizeof(ctx->cm));
+  ctx->cm.world = 1;
+  ctx->cm.words_per_set = ACC_WORDS;
   *out = ctx;
   return OB200_OK;
 }
@@ -130,6 +143,11 @@ int ob200_destroy(ob200_context *ctx) {
   cudaFree(ctx->acc); cudaFree(ctx->barrier); cudaFree(ctx->dres); cudaFree(ctx->dscal);
   cudaFree(ctx->dmat); cudaFree(ctx->dbits);
   cudaFreeHost(ctx->hres); cudaFreeHost(ctx->hscal); cudaFreeHost(ctx->hacc); cudaFreeHost(ctx->hmat);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  for (int r = 0; r < MAX_RANKS; ++r)
+    if (ctx->peer_base[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+  cudaFree(ctx->comm_buf);
+  cudaFree(ctx->dbg);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OB200_OK;
@@ -145,14 +163,74 @@ int ob200_synchronize(ob200_context *ctx) {
   return OB200_OK;
 }
 
-int ob200_set_allreduce(ob200_context *ctx, ob200_allreduce_i64_fn fn, void *user, int rank, int world) {
-  if (!ctx || world < 1 || rank < 0 || rank >= world) return OB200_INVALID_ARGUMENT;
-  ctx->allreduce = fn;
-  ctx->allreduce_user = user;
-  ctx->rank = rank;
-  ctx->world = world;
+int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, uint64_t *out4_min) {
+  if (!ctx) return OB200_INVALID_ARGUMENT;
+  const size_t words = 4 * 1024;
+  if (enable && !ctx->dbg) {
+    CK(cudaMalloc(&ctx->dbg, words * 8));
+    CK(cudaMemset(ctx->dbg, 0, words * 8));
+  }
+  if (ctx->dbg && out4_max && out4_min) {
+    std::vector<unsigned long long> h(words);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(h.data(), ctx->dbg, words * 8, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k) { out4_max[k] = 0; out4_min[k] = ~0ull; }
+    for (size_t b = 0; b < 1024; ++b) {
+      if (!(h[4 * b] | h[4 * b + 1] | h[4 * b + 2] | h[4 * b + 3])) continue;
+      for (int k = 0; k < 4; ++k) {
+        if (h[4 * b + k] > out4_max[k]) out4_max[k] = h[4 * b + k];
+        if (h[4 * b + k] < out4_min[k]) out4_min[k] = h[4 * b + k];
+      }
+    }
+    CK(cudaMemset(ctx->dbg, 0, words * 8));
+  }
+  if (!enable && ctx->dbg) { cudaFree(ctx->dbg); ctx->dbg = nullptr; }
   return OB200_OK;
 }
+
+int ob200_comm_export(ob200_context *ctx, void *handle_out) {
+  if (!ctx || !handle_out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->comm_buf) {
+    CK(cudaMalloc(&ctx->comm_buf, sizeof(u64) * (COMM_INBOX_WORDS + COMM_FLAG_WORDS)));
+    CK(cudaMemset(ctx->comm_buf, 0, sizeof(u64) * (COMM_INBOX_WORDS + COMM_FLAG_WORDS)));
+    CK(cudaDeviceSynchronize());
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == OB200_COMM_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->comm_buf));
+  memcpy(handle_out, &h, sizeof(h));
+  return OB200_OK;
+}
+
+int ob200_comm_connect(ob200_context *ctx, int rank, int world, const void *handles) {
+  if (!ctx || !handles || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
+    return fail(ctx, OB200_INVALID_ARGUMENT, "comm_connect: bad rank / world (max 8 ranks)");
+  if (!ctx->comm_buf) return fail(ctx, OB200_INVALID_ARGUMENT, "comm_connect before comm_export");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    u64 *base;
+    if (r == rank) {
+      base = ctx->comm_buf;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)handles + (size_t)r * OB200_COMM_HANDLE_BYTES, sizeof(h));
+      void *p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      ctx->peer_base[r] = p;
+      base = (u64 *)p;
+    }
+    ctx->cm.inbox[r] = base;
+    ctx->cm.flags[r] = (unsigned long long *)(base + COMM_INBOX_WORDS);
+  }
+  ctx->cm.rank = rank;
+  ctx->cm.world = world;
+  ctx->cm.epoch = 0;
+  return OB200_OK;
+}
+
+int ob200_comm_rank(const ob200_context *ctx) { return ctx ? ctx->cm.rank : 0; }
+int ob200_comm_world(const ob200_context *ctx) { return ctx ? ctx->cm.world : 1; }
 
 // ---- memory helpers ---------------------------------------------------------
 int ob200_malloc(ob200_context *ctx, size_t bytes, void **p) {
@@ -215,12 +293,26 @@ static int ensure_staging(ob200_context *ctx, size_t N) {
   return OB200_OK;
 }
 
+// Cross-rank fold of set[off, off+count) (no-op on one GPU).  All ranks call it in lockstep.
+static int exchange(ob200_context *ctx, u64 *set, int off, int count, int mode = 0) {
+  if (ctx->cm.world <= 1) return OB200_OK;
+  CK(launch_tcg_exchange(ctx->cm, ctx->cm.epoch, set, off, count, mode, reinterpret_cast<int *>(ctx->barrier + 1),
+                         ctx->stream));
+  ctx->cm.epoch += 1;
+  ctx->launches += 1;
+  return OB200_OK;
+}
+
 // exact dot products (<= 4) -> host doubles; synchronises the stream
 static int dots_sync(ob200_context *ctx, uint64_t N, int count, const double *const *a, const double *const *b,
                      double *out) {
   u64 *set = ctx->acc;  // set 0
   CK(cudaMemsetAsync(set, 0, sizeof(u64) * ACC_SCAL_WORDS, ctx->stream));
   CK(launch_dots(N, count, a, b, set, ctx->sm_count, ctx->stream));
+  {
+    int rc = exchange(ctx, set, 0, count * KUL_STRIDE);
+    if (rc) return rc;
+  }
   CK(launch_finalize_many(set, count, ctx->dscal, ctx->stream));
   ctx->launches += 2;
   CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
@@ -231,6 +323,10 @@ static int dots_sync(ob200_context *ctx, uint64_t N, int count, const double *co
 
 // read the fixed-point Gram of set 0 back to the host as doubles (p x p = 32 x 32)
 static int read_gram(ob200_context *ctx, int e, double *G /* 1024 */, double *scal2 /* nullable: 2 scalars */) {
+  {
+    int rc = exchange(ctx, ctx->acc, 0, ACC_WORDS);
+    if (rc) return rc;
+  }
   if (scal2) {
     CK(launch_finalize_many(ctx->acc, 2, ctx->dscal, ctx->stream));
     ctx->launches += 1;
@@ -304,11 +400,14 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   a.barrier = ctx->barrier;
   a.abort_flag = reinterpret_cast<int *>(ctx->barrier + 1);
   a.result = ctx->dres;
+  a.dbg = ctx->dbg;
+  a.cm = ctx->cm;
 
   // s = 0, r = g, <r, v>  (IterativeSolvers.h:211-266)
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SETS * ACC_WORDS, st));
   CK(cudaMemsetAsync(ctx->barrier, 0, 64, st));
   CK(launch_tcg_init(a, ctx->sm_count * 2, st));
+  if ((rc = exchange(ctx, ctx->acc, SC_RV * KUL_STRIDE, KUL_STRIDE))) return rc;
   CK(launch_tcg_finalize(ctx->acc, SC_RV, ctx->dscal, st));
   ctx->launches += 2;
   CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -321,7 +420,9 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   const double target = r0_norm * std::min(prm->kappa_fgr, std::pow(r0_norm, prm->theta));  // l.278-279
   a.rv0 = rv0;
   a.target = target;
+  a.cm = ctx->cm;
 
+  CK(cudaEventRecord(ctx->ev0, st));
   if (H->kind == OB200_OP_DIAG) {
     CK(launch_tcg_diag(a, H->diag_dev, ctx->sm_count, st));
   } else {
@@ -330,15 +431,19 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     if ((unsigned long long)grid > nblk) grid = (int)nblk;
     CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
   }
+  CK(cudaEventRecord(ctx->ev1, st));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(ctx->hres, ctx->dres, sizeof(TcgDeviceResult), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  res->solve_kernel_ms = 0.f;
+  cudaEventElapsedTime(&res->solve_kernel_ms, ctx->ev0, ctx->ev1);
   res->update_step_M_norm = ctx->hres->update_step_M_norm;
   res->num_iterations = ctx->hres->num_iterations;
   res->exit_reason = ctx->hres->exit_reason;
   res->r0_norm = r0_norm;
   res->final_rv = ctx->hres->final_rv;
   res->kernel_launches = ctx->launches - launches0;
+  ctx->cm.epoch += ctx->hres->phases;
   if (ctx->hres->status == OB200_NUMERIC_RANGE) return fail(ctx, OB200_NUMERIC_RANGE, "fixed-point Gram bound exceeded or non-finite data");
   if (ctx->hres->status == OB200_ABORTED) return fail(ctx, OB200_ABORTED, "device grid barrier watchdog fired");
   return OB200_OK;
@@ -431,6 +536,7 @@ int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16
   CK(cudaMemsetAsync(ctx->dbits, 0, 8, st));
   CK(launch_stiefel_absrowsum(A, nblk * 128, ctx->dbits, st));
   ctx->launches += 1;
+  if ((rc = exchange(ctx, reinterpret_cast<u64 *>(ctx->dbits), 0, 1, /*max*/ 1))) return rc;
   unsigned long long bits = 0;
   CK(cudaMemcpyAsync(&bits, ctx->dbits, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -143,6 +143,68 @@ __host__ __device__ inline double kul_finalize(Load ld) {
   return neg ? -v : v;
 }
 
+#ifdef __CUDACC__
+// Warp-cooperative finalize: all 32 lanes call it with the same accumulator and
+// all return the same correctly rounded value as kul_finalize.  The limbs are
+// fetched with three coalesced loads; the serial carry chain only runs over the
+// window of non-zero limbs (a handful in practice) and is executed redundantly
+// by every lane from warp shuffles, so there is no local-memory array and no
+// dependent global-memory latency chain.
+template <class Load>
+__device__ __forceinline__ double kul_finalize_warp(Load ld) {
+  const int lane = threadIdx.x & 31;
+  const i64 v0 = (i64)ld(lane);
+  const i64 v1 = (i64)ld(lane + 32);
+  const i64 v2 = (lane + 64 <= KUL_LIMBS) ? (i64)ld(lane + 64) : 0;   // limbs 64..67 and the non-finite counter [68]
+  const unsigned bad = __ballot_sync(0xffffffffu, lane + 64 == KUL_LIMBS && v2 != 0);
+  if (bad) return __longlong_as_double(0x7ff8000000000000ll);
+  const unsigned b0 = __ballot_sync(0xffffffffu, v0 != 0);
+  const unsigned b1 = __ballot_sync(0xffffffffu, v1 != 0);
+  const unsigned b2 = __ballot_sync(0xffffffffu, v2 != 0) & 0xfu;
+  if ((b0 | b1 | b2) == 0) return 0.0;
+  const int lo = b0 ? (__ffs(b0) - 1) : (b1 ? 32 + __ffs(b1) - 1 : 64 + __ffs(b2) - 1);
+  int hi = b2 ? 64 + (31 - __clz(b2)) : (b1 ? 32 + (31 - __clz(b1)) : (31 - __clz(b0)));
+  hi = min(hi + 3, KUL_LIMBS - 1);   // room for the carry out of the top non-zero limb (< 2^33) and the sign
+  auto limb = [&](int j) -> i64 {
+    const i64 src = j < 32 ? v0 : (j < 64 ? v1 : v2);
+    return __shfl_sync(0xffffffffu, src, j & 31);
+  };
+  i64 carry = 0;
+  for (int j = lo; j <= hi; ++j) carry = (limb(j) + carry) >> 32;
+  const bool neg = carry < 0;
+  carry = 0;
+  // sliding window over the magnitude digits: (d_top, d_mid, d_low, sticky) at the last non-zero digit
+  uint32_t h0 = 0, h1 = 0, h2 = 0;
+  bool stk = false;
+  uint32_t t0 = 0, t1 = 0, t2 = 0;
+  bool tstk = false;
+  int top = -1;
+  for (int j = lo; j <= hi; ++j) {
+    const i64 r = limb(j);
+    const i64 t = (neg ? -r : r) + carry;
+    const uint32_t d = (uint32_t)(t & 0xFFFFFFFFll);
+    carry = t >> 32;
+    stk = stk || (h2 != 0);
+    h2 = h1; h1 = h0; h0 = d;
+    if (d) { top = j; t0 = h0; t1 = h1; t2 = h2; tstk = stk; }
+  }
+  if (top < 0) return 0.0;
+  const u64 hi64 = ((u64)t0 << 32) | (u64)t1;
+  const int lz = __clzll((i64)hi64);
+  u64 m64 = hi64;
+  uint32_t rem = t2;
+  if (lz) {
+    m64 = (hi64 << lz) | ((u64)t2 >> (32 - lz));
+    rem = t2 << lz;
+  }
+  if (rem != 0 || tstk) m64 |= 1ull;
+  const double m = __ull2double_rn(m64);
+  const int ex = 32 * (top - 1) - KUL_BIAS - lz;
+  const double v = scalbn(m, ex);
+  return neg ? -v : v;
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // Bounded two-limb fixed point for the p x p Gram of the tangent projection.
 // x is quantised to q = 2^(e-90) with |x| < 2^e guaranteed by the caller's
@@ -181,27 +243,129 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ bool grid_barrier(unsigned *counter, unsigned &gen, int *abort_flag) {
-  __shared__ int s_ok;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned atom_add_acqrel_u32(unsigned *p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory (one process per GPU, buffers shared
+// with CUDA IPC).  Every rank owns an inbox of ACC_SLOTS x MAX_RANKS accumulator
+// sets plus one arrival flag per (slot, source rank).  After the local grid
+// barrier the LAST CTA of a rank stores the rank's exact integer partial sums
+// into every rank's inbox (plain stores on peer pointers), fences at system
+// scope and raises the flags; every CTA of every rank then waits for all flags in
+// its OWN memory and reads the reduced value as the integer sum over the source
+// slots.  Integer addition is associative, so the result is bit-identical for any
+// number of GPUs.  Flags carry a monotonically increasing global phase number.
+// ---------------------------------------------------------------------------
+constexpr int MAX_RANKS = 8;
+constexpr int ACC_SLOTS = 3;
+struct CommDev {
+  int rank, world;
+  unsigned long long epoch;                 // global phase counter at kernel start (same on all ranks)
+  u64 *inbox[MAX_RANKS];                    // [ACC_SLOTS][MAX_RANKS][words_per_set] on rank r
+  unsigned long long *flags[MAX_RANKS];     // [ACC_SLOTS][MAX_RANKS] on rank r
+  int words_per_set;
+};
+
+struct RedView {   // reduced word j = sum_r base[r][j]
+  const u64 *base[MAX_RANKS];
+  int world;
+  __device__ __forceinline__ u64 load(int j) const {
+    u64 v = __ldcg(base[0] + j);
+    for (int r = 1; r < world; ++r) v += __ldcg(base[r] + j);
+    return v;
+  }
+};
+
+// Grid-wide (and, when cm.world > 1, machine-wide) barrier for the persistent
+// kernels.  Cooperative launch guarantees co-residency.  `counter` is a
+// monotonically increasing arrival counter, `gen` the caller's private
+// generation.  On return `view` addresses the reduced copy of set[off, off+count).
+// Returns false if the watchdog expired (a peer is gone): callers abandon the
+// solve instead of hanging the device.
+// `stamps` (optional, thread 0 only): [0] = time this CTA arrived, [1] = released.
+__device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned &gen, int *abort_flag,
+                                                    const CommDev &cm, unsigned long long gphase, u64 *set,
+                                                    int off, int count, RedView &view,
+                                                    unsigned long long *stamps = nullptr) {
+  __shared__ int s_ok, s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     gen += 1;
     const unsigned target = gen * gridDim.x;
     __threadfence();
-    red_release_add_u32(counter, 1u);
+    if (stamps) stamps[0] = globaltimer_ns();
+    const unsigned old = atom_add_acqrel_u32(counter, 1u);
     int ok = 1;
-    unsigned spins = 0;
-    while (ld_acquire_u32(counter) < target) {
-      if (++spins > (1u << 24)) {  // ~ seconds: a peer CTA is gone; bail out
-        if (*((volatile int *)abort_flag) || spins > (1u << 25)) { ok = 0; break; }
+    s_last = (old + 1u == target);
+    if (cm.world == 1) {
+      unsigned spins = 0;
+      while (ld_acquire_u32(counter) < target) {
+        if (++spins > (1u << 24)) {  // ~ seconds: a peer CTA is gone; bail out
+          if (*((volatile int *)abort_flag) || spins > (1u << 25)) { ok = 0; break; }
+        }
+        if (spins > 64) __nanosleep(64);
       }
-      if (spins > 64) __nanosleep(64);
+      if (stamps) stamps[1] = globaltimer_ns();
+      if (!ok) atomicExch(abort_flag, 1);
+      __threadfence();
     }
-    if (!ok) atomicExch(abort_flag, 1);
-    __threadfence();
     s_ok = ok;
   }
   __syncthreads();
+  view.world = cm.world;
+  if (cm.world == 1) {
+    view.base[0] = set;
+    return s_ok != 0;
+  }
+  const int slot = (int)(gphase % ACC_SLOTS);
+  const size_t slot_off = (size_t)(slot * MAX_RANKS) * cm.words_per_set;
+  if (s_last) {   // CTA-uniform: this CTA completed the local reduction -> publish it to every rank
+    __threadfence();
+    for (int r = 0; r < cm.world; ++r) {
+      u64 *dst = cm.inbox[r] + slot_off + (size_t)cm.rank * cm.words_per_set + off;
+      for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldcg(set + off + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < cm.world)
+      st_release_sys_u64(cm.flags[threadIdx.x] + slot * MAX_RANKS + cm.rank, gphase + 1ull);
+  }
+  if ((int)threadIdx.x < cm.world) {
+    const unsigned long long *f = cm.flags[cm.rank] + slot * MAX_RANKS + threadIdx.x;
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(f) < gphase + 1ull) {
+      if (++spins > (1u << 24)) {
+        if (*((volatile int *)abort_flag) || spins > (1u << 25)) { atomicExch(abort_flag, 1); break; }
+      }
+      if (spins > 256) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (stamps) stamps[1] = globaltimer_ns();
+    s_ok = (*((volatile int *)abort_flag) == 0);
+  }
+  __syncthreads();
+  for (int r = 0; r < cm.world; ++r)
+    view.base[r] = cm.inbox[cm.rank] + slot_off + (size_t)r * cm.words_per_set;
   return s_ok != 0;
 }
 

@@ -64,9 +64,11 @@ __global__ void __launch_bounds__(TCG_THREADS) dots_kernel(unsigned long long N,
 }
 
 __global__ void finalize_many_kernel(const u64 *set, int count, double *out) {
-  if (blockIdx.x == 0 && (int)threadIdx.x < count) {
-    const u64 *p = set + threadIdx.x * KUL_STRIDE;
-    out[threadIdx.x] = kul_finalize([p](int j) { return p[j]; });
+  const int warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && warp < count) {
+    const u64 *p = set + warp * KUL_STRIDE;
+    const double v = kul_finalize_warp([p](int j) { return p[j]; });
+    if ((threadIdx.x & 31) == 0) out[warp] = v;
   }
 }
 
@@ -134,7 +136,7 @@ cudaError_t launch_dots(unsigned long long N, int count, const double *const *a,
   return cudaGetLastError();
 }
 cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st) {
-  finalize_many_kernel<<<1, 32, 0, st>>>(set, count, out);
+  finalize_many_kernel<<<1, 32 * (count < 1 ? 1 : count), 0, st>>>(set, count, out);
   return cudaGetLastError();
 }
 cudaError_t launch_axpby(unsigned long long N, double alpha, const double *x, double beta, const double *y,

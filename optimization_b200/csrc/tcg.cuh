@@ -24,7 +24,7 @@ constexpr int ACC_GRAM_OFF = ACC_SCAL_WORDS;                  // 32x32 entries x
 constexpr int ACC_GRAM_WORDS = 2048;
 constexpr int ACC_FLAG_OFF = ACC_GRAM_OFF + ACC_GRAM_WORDS;   // [0] fixed-point overflow
 constexpr int ACC_WORDS = ACC_FLAG_OFF + 8;                   // 2632
-constexpr int ACC_SETS = 3;
+constexpr int ACC_SETS = ACC_SLOTS;
 
 // scalar slots
 enum { SC_PHP = 0, SC_HPHP = 1, SC_PP = 2, SC_PR = 3, SC_RV = 4 };
@@ -36,7 +36,8 @@ struct TcgDeviceResult {
   unsigned long long num_iterations;
   int exit_reason;
   int status;      // OB200_OK / OB200_NUMERIC_RANGE / OB200_ABORTED
-  int pad[2];
+  unsigned phases; // reduction phases consumed (advances the global exchange epoch)
+  int pad[1];
 };
 
 struct TcgCommon {
@@ -50,7 +51,10 @@ struct TcgCommon {
   unsigned *barrier;           // monotonically increasing arrival counter
   int *abort_flag;
   TcgDeviceResult *result;
+  CommDev cm;                  // multi-GPU exchange (world == 1: unused)
+  unsigned long long *dbg;     // optional: [0..3] ns spent in phase A / A-sync / phase B / B-sync (max over CTAs)
 };
+
 
 // CTA-shared solver scalars (written by thread 0 only, between barriers)
 struct CgShared {
@@ -75,13 +79,15 @@ __device__ __forceinline__ void flush_scalars(u64 *sacc, u64 *gacc, int nscal) {
   }
 }
 
-// After the barrier: threads 0..nscal-1 each finalize one scalar into sh.red[].
-static __device__ __noinline__ double kul_finalize_global(const u64 *a) {
-  return kul_finalize([a](int j) { return __ldcg(a + j); });
-}
-__device__ __forceinline__ void finalize_scalars(const u64 *gacc, CgShared &sh, int first, int count) {
-  if ((int)threadIdx.x < count)
-    sh.red[first + threadIdx.x] = kul_finalize_global(gacc + (first + threadIdx.x) * KUL_STRIDE);
+// After the barrier: warp w < count finalizes scalar first+w into sh.red[] (callers
+// __syncthreads() before reading sh.red).
+__device__ __forceinline__ void finalize_scalars(const RedView &v, CgShared &sh, int first, int count) {
+  const int warp = threadIdx.x >> 5;
+  if (warp < count) {
+    const int o = (first + warp) * KUL_STRIDE;
+    const double x = kul_finalize_warp([&v, o](int j) { return v.load(o + j); });
+    if ((threadIdx.x & 31) == 0) sh.red[first + warp] = x;
+  }
 }
 
 // Scalar logic after phase A.  Reference IterativeSolvers.h:300-362.

@@ -72,9 +72,10 @@ __global__ void __launch_bounds__(TCG_THREADS) tcg_init_kernel(TcgCommon a) {
 
 // Finalize scalar slot `slot` of accumulator set 0 into result->final_rv (host reads it).
 __global__ void tcg_finalize_kernel(const u64 *acc, int slot, double *out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
     const u64 *p = acc + slot * KUL_STRIDE;
-    *out = kul_finalize([p](int j) { return p[j]; });
+    const double v = kul_finalize_warp([p](int j) { return p[j]; });
+    if (threadIdx.x == 0) *out = v;
   }
 }
 
@@ -151,8 +152,12 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_diag_kernel(TcgCommon a, c
     }
     __syncthreads();
     flush_scalars(sacc, set, 4);
-    if (!grid_barrier(a.barrier, gen, a.abort_flag)) { exit_reason = -2; break; }
-    finalize_scalars(set, sh, 0, 4);
+    RedView rvw;
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, 4 * KUL_STRIDE, rvw)) {
+      exit_reason = -2;
+      break;
+    }
+    finalize_scalars(rvw, sh, 0, 4);
     __syncthreads();
     if (threadIdx.x == 0)
       decide_after_A(sh, sh.red[SC_PHP], sh.red[SC_HPHP], sh.red[SC_PP], sh.red[SC_PR], a.Delta, a.epsilon);
@@ -207,8 +212,12 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_diag_kernel(TcgCommon a, c
     }
     __syncthreads();
     flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
-    if (!grid_barrier(a.barrier, gen, a.abort_flag)) { exit_reason = -2; break; }
-    finalize_scalars(set, sh, SC_RV, 1);
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
+                             KUL_STRIDE, rvw)) {
+      exit_reason = -2;
+      break;
+    }
+    finalize_scalars(rvw, sh, SC_RV, 1);
     __syncthreads();
     if (threadIdx.x == 0) update_after_B(sh, sh.red[SC_RV]);
     __syncthreads();
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_diag_kernel(TcgCommon a, c
     TcgDeviceResult *res = a.result;
     res->num_iterations = sh.k;
     res->final_rv = sh.rv;
+    res->phases = phase;
     if (exit_reason == -2) {
       res->status = 5;  // OB200_ABORTED
       res->exit_reason = -1;
@@ -231,7 +241,48 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_diag_kernel(TcgCommon a, c
   }
 }
 
+// Host-driven reductions (init <r,v>, level-1 dots, Grams) across ranks: one CTA
+// publishes set[off, off+count) to every rank, waits for all ranks and folds the
+// integer total back into `set` in place.  mode 1: element-wise max instead of sum
+// (for order-independent maxima stored as non-negative double bit patterns).
+__global__ void __launch_bounds__(TCG_THREADS) tcg_exchange_kernel(CommDev cm, unsigned long long gphase, u64 *set,
+                                                                   int off, int count, int mode, int *abort_flag) {
+  const int slot = (int)(gphase % ACC_SLOTS);
+  const size_t slot_off = (size_t)(slot * MAX_RANKS) * cm.words_per_set;
+  for (int r = 0; r < cm.world; ++r) {
+    u64 *dst = cm.inbox[r] + slot_off + (size_t)cm.rank * cm.words_per_set + off;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldcg(set + off + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < cm.world) {
+    st_release_sys_u64(cm.flags[threadIdx.x] + slot * MAX_RANKS + cm.rank, gphase + 1ull);
+    const unsigned long long *f = cm.flags[cm.rank] + slot * MAX_RANKS + threadIdx.x;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys_u64(f) < gphase + 1ull) {
+      if (++spins > (1ull << 26)) { atomicExch(abort_flag, 1); break; }
+      if (spins > 256) __nanosleep(64);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const u64 *in = cm.inbox[cm.rank] + slot_off + off;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    u64 v = __ldcg(in + i);
+    for (int r = 1; r < cm.world; ++r) {
+      const u64 x = __ldcg(in + (size_t)r * cm.words_per_set + i);
+      v = mode ? (x > v ? x : v) : v + x;
+    }
+    set[off + i] = v;
+  }
+}
+
 // ---- host launchers ---------------------------------------------------------
+cudaError_t launch_tcg_exchange(const CommDev &cm, unsigned long long gphase, u64 *set, int off, int count,
+                                int mode, int *abort_flag, cudaStream_t st) {
+  tcg_exchange_kernel<<<1, TCG_THREADS, 0, st>>>(cm, gphase, set, off, count, mode, abort_flag);
+  return cudaGetLastError();
+}
 cudaError_t launch_tcg_init(const TcgCommon &a, int grid, cudaStream_t st) {
   tcg_init_kernel<<<grid, TCG_THREADS, 0, st>>>(a);
   return cudaGetLastError();

@@ -85,12 +85,24 @@ __device__ __forceinline__ void strip_apply(const unsigned short *Ablock, const 
 }
 
 // --- step 3: 8x8 tile (mt, nt) of X^T Z over one staged 128-row block ----------
-__device__ __forceinline__ void gram_tile(const double *Xsm, const double *Zsm, int warp, int lane,
+__device__ __forceinline__ void gram_tile(const double *Xsm, const double *Zsm, int tile, int lane,
                                           double &g0, double &g1) {
-  const int mt = warp >> 2, nt = warp & 3, m = lane >> 2, j = lane & 3;
+  const int mt = tile >> 2, nt = tile & 3, m = lane >> 2, j = lane & 3;
   g0 = 0.0; g1 = 0.0;
 #pragma unroll 8
   for (int q = 0; q < 32; ++q) {
+    const int krow = 4 * q + j;
+    dmma884(g0, g1, Xsm[krow * WS + 8 * mt + m], Zsm[krow * WS + 8 * nt + m]);
+  }
+}
+
+// same over 64 rows (one half block)
+__device__ __forceinline__ void gram_tile_half(const double *Xsm, const double *Zsm, int tile, int lane,
+                                               double &g0, double &g1) {
+  const int mt = tile >> 2, nt = tile & 3, m = lane >> 2, j = lane & 3;
+  g0 = 0.0; g1 = 0.0;
+#pragma unroll 8
+  for (int q = 0; q < 16; ++q) {
     const int krow = 4 * q + j;
     dmma884(g0, g1, Xsm[krow * WS + 8 * mt + m], Zsm[krow * WS + 8 * nt + m]);
   }
@@ -116,8 +128,8 @@ __device__ __forceinline__ void gram_accumulate(double g0, double g1, double inv
   gfix[0] += f0.hi; gfix[1] += f0.lo; gfix[2] += f1.hi; gfix[3] += f1.lo;
 }
 
-__device__ __forceinline__ void gram_flush(u64 *set, int warp, int lane, i64 (&gfix)[4], unsigned ovf) {
-  const int mt = warp >> 2, nt = warp & 3, m = lane >> 2, j = lane & 3;
+__device__ __forceinline__ void gram_flush(u64 *set, int tile, int lane, i64 (&gfix)[4], unsigned ovf) {
+  const int mt = tile >> 2, nt = tile & 3, m = lane >> 2, j = lane & 3;
   const int e = (8 * mt + m) * ST_P + 8 * nt + 2 * j;
   u64 *g = set + ACC_GRAM_OFF + 2 * e;
   if (gfix[0]) atomicAdd(g + 0, (u64)gfix[0]);
@@ -134,41 +146,54 @@ __host__ __device__ __forceinline__ int gram_exponent(double bound) {
   return ilogb(bound) + 2;
 }
 
-// After the barrier: Gsm = -sym(G) from the global fixed-point set; returns ||sym G||_F^2
-// (identical in every CTA: same data, same order).
-__device__ __forceinline__ double load_symG(const u64 *set, double q, double *Gsm, double *scratch) {
-  for (int e = threadIdx.x; e < ST_P * ST_P; e += blockDim.x) {
-    const int i = e >> 5, jj = e & 31, et = jj * ST_P + i;
-    const double v1 = fix2_to_double((i64)__ldcg(set + ACC_GRAM_OFF + 2 * e), (i64)__ldcg(set + ACC_GRAM_OFF + 2 * e + 1), q);
-    const double v2 = fix2_to_double((i64)__ldcg(set + ACC_GRAM_OFF + 2 * et), (i64)__ldcg(set + ACC_GRAM_OFF + 2 * et + 1), q);
-    Gsm[i * WS + jj] = -0.5 * (v1 + v2);
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double c = 0.0;
-    for (int i = 0; i < ST_P; ++i) { const double v = Gsm[i * WS + threadIdx.x]; c = fma(v, v, c); }
-    c = warp_sum(c);
-    if (threadIdx.x == 0) *scratch = c;
-  }
-  __syncthreads();
-  return *scratch;
-}
-
 extern __shared__ __align__(16) unsigned char st_smem[];
+
+// ---- persistent kernel, v2: warp-specialised phase A -----------------------------
+// 16 warps.  Phase A: warps 0-7 ("L") stream r, p_old, Y of the next 128-row block,
+// form p, write it back and stage p / Y in a double-buffered shared-memory ring;
+// warps 8-15 ("M") run the fp64 tensor-core contractions of the current block
+// (W strips, then the projection Gram).  L and M hand buffers over with named
+// barriers, so HBM streaming overlaps the DMMA pipe.  Work is split between CTAs
+// in 64-row half blocks (balanced to 4 %); a block shared by two CTAs is staged
+// by both, computed/written only for the owned half.
+// Phase B: all 16 warps, 8-row strips, traversed in REVERSE so the p / W / Y / r
+// lines written or read last in phase A are still L2 resident.
+constexpr size_t V2_PSZ = sizeof(double) * ST_NB * PS;   // 33792
+constexpr size_t V2_YSZ = sizeof(double) * ST_NB * WS;   // 36864
+constexpr size_t V2_P = 0;
+constexpr size_t V2_Y = V2_P + 2 * V2_PSZ;
+constexpr size_t V2_W = V2_Y + 2 * V2_YSZ;
+constexpr size_t V2_S = V2_W + V2_YSZ;
+constexpr size_t V2_G = V2_S + sizeof(double) * ST_P * WS;
+constexpr size_t V2_ACC = V2_G + sizeof(double) * ST_P * WS;
+constexpr size_t V2_TOTAL = V2_ACC + sizeof(u64) * ACC_NSCAL * KUL_STRIDE;
+
+enum { NB_FULL = 1, NB_EMPTY = 3, NB_MSYNC = 5, NB_MSYNC2 = 6 };
+__device__ __forceinline__ void nbar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_stiefel_kernel(TcgCommon a, StiefelArgs st) {
   __shared__ CgShared sh;
-  __shared__ double s_scratch;
+  __shared__ double s_part[TCG_WARPS];
   __shared__ double s_invq, s_q;
-  double *Psm = reinterpret_cast<double *>(st_smem + SM_P);
-  double *Wsm = reinterpret_cast<double *>(st_smem + SM_W);
-  double *Ysm = reinterpret_cast<double *>(st_smem + SM_Y);
-  double *Ssm = reinterpret_cast<double *>(st_smem + SM_S);
-  double *Gsm = reinterpret_cast<double *>(st_smem + SM_G);
-  u64 *sacc = reinterpret_cast<u64 *>(st_smem + SM_ACC);
+  double *Psm0 = reinterpret_cast<double *>(st_smem + V2_P);
+  double *Ysm0 = reinterpret_cast<double *>(st_smem + V2_Y);
+  double *Wsm = reinterpret_cast<double *>(st_smem + V2_W);
+  double *Ssm = reinterpret_cast<double *>(st_smem + V2_S);
+  double *Gsm = reinterpret_cast<double *>(st_smem + V2_G);
+  u64 *sacc = reinterpret_cast<u64 *>(st_smem + V2_ACC);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = lane >> 2, j = lane & 3;
+  const bool is_L = warp < 8;
+  const int mw = warp - 8;
   for (int i = tid; i < ACC_NSCAL * KUL_STRIDE; i += blockDim.x) sacc[i] = 0;
   for (int e = tid; e < ST_P * ST_P; e += blockDim.x) Ssm[(e >> 5) * WS + (e & 31)] = -st.S[e];
   if (tid == 0) {
@@ -180,14 +205,25 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_stiefel_kernel(TcgCommon a
     sh.k = 0;
     sh.action = ACT_CONTINUE;
     sh.status = 0;
+    // |G_ij| <= ||Y e_i|| ||W e_j|| <= (||A|| + ||S||) ||p||_F ; ||p||_F^2 = pk_M_2 (l.266,417)
+    const int e = gram_exponent(st.op_norm_bound * sqrt(a.rv0) * 4.0);
+    s_invq = scalbn(1.0, 90 - e);
+    s_q = scalbn(1.0, e - 90);
   }
   __syncthreads();
 
-  const unsigned long long nblk = (st.n_rows + ST_NB - 1) / ST_NB;
-  const unsigned long long b0 = nblk * blockIdx.x / gridDim.x, b1 = nblk * (blockIdx.x + 1ull) / gridDim.x;
+  // ownership: 64-row half blocks [h0, h1)
+  const unsigned long long nhalf = (st.n_rows + 63ull) / 64ull;
+  const unsigned long long h0 = nhalf * blockIdx.x / gridDim.x, h1 = nhalf * (blockIdx.x + 1ull) / gridDim.x;
+  const unsigned long long row_lo = h0 * 64ull;
+  const unsigned long long row_hi = (h1 * 64ull < st.n_rows) ? h1 * 64ull : st.n_rows;
+  const unsigned long long bfirst = h0 >> 1;
+  const int nb_local = (h1 > h0) ? (int)(((h1 - 1) >> 1) - bfirst + 1) : 0;
+  const long long s_lo = (long long)(row_lo >> 3), s_hi = (long long)((row_hi + 7ull) >> 3);   // 8-row strips
   unsigned gen = 0, phase = 0;
   int exit_reason = -1;
-  i64 gfix[4] = {0, 0, 0, 0};
+  i64 gfix[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  unsigned long long dbg_prev = 0;
 
   for (;;) {
     const unsigned long long k = sh.k;
@@ -196,13 +232,6 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_stiefel_kernel(TcgCommon a
     const double beta = sh.beta;
     const double *p_old = (k & 1ull) ? a.p1 : a.p0;
     double *p_new = (k & 1ull) ? a.p0 : a.p1;
-    if (tid == 0) {
-      // |G_ij| <= ||Y e_i|| ||W e_j|| <= (||A|| + ||S||) ||p||_F ; ||p||_F^2 = pk_M_2 (l.266,417)
-      const int e = gram_exponent(st.op_norm_bound * sqrt(sh.pk_M_2) * 4.0);
-      s_invq = scalbn(1.0, 90 - e);
-      s_q = scalbn(1.0, e - 90);
-    }
-    __syncthreads();
     const double inv_q = s_invq, q = s_q;
 
     // ------------------------------ phase A ------------------------------
@@ -211,91 +240,158 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_stiefel_kernel(TcgCommon a
       u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
       for (int i = tid; i < ACC_WORDS; i += blockDim.x) nxt[i] = 0;
     }
+    unsigned long long stA[2] = {0, 0}, stB[2] = {0, 0};
     unsigned ovf = 0;
-    for (unsigned long long b = b0; b < b1; ++b) {
-      const unsigned long long r0 = b * ST_NB;
-      // step 1: form p, stage p and Y
-      double pp = 0.0, pr = 0.0;
+    if (is_L) {
+      // ===== loader warps: stream, form p, stage =====
+      for (int i = 0; i < nb_local; ++i) {
+        const int buf = i & 1;
+        const unsigned long long b = bfirst + i, r0 = b * ST_NB;
+        double *Psm = Psm0 + buf * (ST_NB * PS);
+        double *Ysm = Ysm0 + buf * (ST_NB * WS);
+        if (i + 1 < nb_local)   // next block's A (32 KB = 256 lines) into L2 for the M warps
+          prefetch_l2(reinterpret_cast<const char *>(st.A + (size_t)(b + 1) * ST_NB * ST_NB) + 128 * tid);
+        if (i >= 2) nbar_sync(NB_EMPTY + buf, TCG_THREADS);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx2 = tid + TCG_THREADS * i;
-        const int row = idx2 >> 4, c2 = (idx2 & 15) * 2;
-        const unsigned long long grow = r0 + row;
-        double2 pv = make_double2(0.0, 0.0), yv = make_double2(0.0, 0.0);
-        if (grow < st.n_rows) {
-          const size_t off = (size_t)grow * ST_P + c2;
-          const double2 rv = ldcg2(a.r + off);
-          yv = ldcg2(st.Y + off);
-          if (k) {
-            const double2 po = ldcg2(p_old + off);
-            pv.x = fma(beta, po.x, -rv.x);        // l.420
-            pv.y = fma(beta, po.y, -rv.y);
-          } else {
-            pv.x = -rv.x;                         // l.256
-            pv.y = -rv.y;
+        for (int chunk = 0; chunk < 2; ++chunk) {   // chunk == 64-row half: the unit of the exact reduction
+          double pp = 0.0, pr = 0.0;
+          double2 rv[4], yv[4], po[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx2 = tid + 256 * (4 * chunk + u);
+            const int row = idx2 >> 4, c2 = (idx2 & 15) * 2;
+            const unsigned long long grow = r0 + row;
+            rv[u] = yv[u] = po[u] = make_double2(0.0, 0.0);
+            if (grow < st.n_rows) {
+              const size_t off = (size_t)grow * ST_P + c2;
+              rv[u] = ldcg2(a.r + off);
+              yv[u] = ldcg2(st.Y + off);
+              if (k) po[u] = ldcg2(p_old + off);
+            }
           }
-          stcg2(p_new + off, pv);
-          pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
-          pr = fma(pv.x, rv.x, pr); pr = fma(pv.y, rv.y, pr);
-        }
-        Psm[row * PS + c2] = pv.x;
-        Psm[row * PS + c2 + 1] = pv.y;
-        *reinterpret_cast<double2 *>(Ysm + row * WS + c2) = yv;
-      }
-      pp = warp_sum(pp);
-      pr = warp_sum(pr);
-      if (lane == 0) {
-        kul_add_atomic(sacc + SC_PP * KUL_STRIDE, pp);
-        kul_add_atomic(sacc + SC_PR * KUL_STRIDE, pr);
-      }
-      __syncthreads();
-      // step 2: W strip on the tensor cores
-      double acc[4][2];
-      strip_apply(st.A + (size_t)b * ST_NB * ST_NB, Psm, Ssm, warp, lane, acc);
-      {
-        const int row = 8 * warp + m;
-        const unsigned long long grow = r0 + row;
-        double pw = 0.0, ww = 0.0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int col = 8 * t + 2 * j;
-          const double p0v = Psm[row * PS + col], p1v = Psm[row * PS + col + 1];
-          pw = fma(p0v, acc[t][0], pw); pw = fma(p1v, acc[t][1], pw);
-          ww = fma(acc[t][0], acc[t][0], ww); ww = fma(acc[t][1], acc[t][1], ww);
-          const double2 wv = make_double2(acc[t][0], acc[t][1]);
-          *reinterpret_cast<double2 *>(Wsm + row * WS + col) = wv;
-          if (grow < st.n_rows) stcg2(a.Hp + (size_t)grow * ST_P + col, wv);
+          for (int u = 0; u < 4; ++u) {
+            const int idx2 = tid + 256 * (4 * chunk + u);
+            const int row = idx2 >> 4, c2 = (idx2 & 15) * 2;
+            const unsigned long long grow = r0 + row;
+            double2 pv;
+            if (k) {
+              pv.x = fma(beta, po[u].x, -rv[u].x);        // l.420
+              pv.y = fma(beta, po[u].y, -rv[u].y);
+            } else {
+              pv.x = -rv[u].x;                            // l.256
+              pv.y = -rv[u].y;
+            }
+            if (grow >= row_lo && grow < row_hi) {
+              stcg2(p_new + (size_t)grow * ST_P + c2, pv);
+              pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
+              pr = fma(pv.x, rv[u].x, pr); pr = fma(pv.y, rv[u].y, pr);
+            }
+            Psm[row * PS + c2] = pv.x;
+            Psm[row * PS + c2 + 1] = pv.y;
+            *reinterpret_cast<double2 *>(Ysm + row * WS + c2) = yv[u];
+          }
+          pp = warp_sum(pp);
+          pr = warp_sum(pr);
+          if (lane == 0) {
+            kul_add_atomic(sacc + SC_PP * KUL_STRIDE, pp);
+            kul_add_atomic(sacc + SC_PR * KUL_STRIDE, pr);
+          }
         }
-        pw = warp_sum(pw);
-        ww = warp_sum(ww);
-        if (lane == 0) {
-          kul_add_atomic(sacc + SC_PHP * KUL_STRIDE, pw);
-          kul_add_atomic(sacc + SC_HPHP * KUL_STRIDE, ww);
-        }
+        nbar_arrive(NB_FULL + buf, TCG_THREADS);
       }
-      __syncthreads();
-      // step 3: projection Gram tile, exact fixed-point accumulation
-      double g0, g1;
-      gram_tile(Ysm, Wsm, warp, lane, g0, g1);
-      gram_accumulate(g0, g1, inv_q, gfix, &ovf);
-      __syncthreads();
-    }
-    gram_flush(set, warp, lane, gfix, ovf);
-    flush_scalars(sacc, set, 4);
-    if (!grid_barrier(a.barrier, gen, a.abort_flag)) { exit_reason = -2; break; }
-    if (__ldcg(set + ACC_FLAG_OFF) != 0) { exit_reason = -3; break; }
-    finalize_scalars(set, sh, 0, 4);
-    const double nG2 = load_symG(set, q, Gsm, &s_scratch);   // contains __syncthreads
-    if (tid == 0) {
-      const double nHp2 = fmax(sh.red[SC_HPHP] - nG2, 0.0);
-      decide_after_A(sh, sh.red[SC_PHP], nHp2, sh.red[SC_PP], sh.red[SC_PR], a.Delta, a.epsilon);
+    } else {
+      // ===== math warps: W strips and projection Gram on the fp64 tensor cores =====
+      for (int i = 0; i < nb_local; ++i) {
+        const int buf = i & 1;
+        const unsigned long long b = bfirst + i, r0 = b * ST_NB;
+        const double *Psm = Psm0 + buf * (ST_NB * PS);
+        const double *Ysm = Ysm0 + buf * (ST_NB * WS);
+        nbar_sync(NB_FULL + buf, TCG_THREADS);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          double pw = 0.0, ww = 0.0;
+          const int strip = half * 8 + mw;
+          const int row = 8 * strip + m;
+          const unsigned long long grow = r0 + row;
+          const unsigned long long hh = 2ull * b + half;
+          if (hh >= h0 && hh < h1) {
+            double acc[4][2];
+            strip_apply(st.A + (size_t)b * ST_NB * ST_NB, Psm, Ssm, strip, lane, acc);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = 8 * t + 2 * j;
+              const double p0v = Psm[row * PS + col], p1v = Psm[row * PS + col + 1];
+              pw = fma(p0v, acc[t][0], pw); pw = fma(p1v, acc[t][1], pw);
+              ww = fma(acc[t][0], acc[t][0], ww); ww = fma(acc[t][1], acc[t][1], ww);
+              const double2 wv = make_double2(acc[t][0], acc[t][1]);
+              *reinterpret_cast<double2 *>(Wsm + row * WS + col) = wv;
+              if (grow < st.n_rows) stcg2(a.Hp + (size_t)grow * ST_P + col, wv);
+            }
+            pw = warp_sum(pw);       // unit of the exact reduction: one 8-row strip
+            ww = warp_sum(ww);
+            if (lane == 0) {
+              kul_add_atomic(sacc + SC_PHP * KUL_STRIDE, pw);
+              kul_add_atomic(sacc + SC_HPHP * KUL_STRIDE, ww);
+            }
+          }
+        }
+        nbar_sync(NB_MSYNC, 256);
+        // projection Gram, one exact unit per owned 64-row half (partition independent)
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const unsigned long long hh = 2ull * b + half;
+          if (hh < h0 || hh >= h1) continue;
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            double g0, g1;
+            gram_tile_half(Ysm + half * 64 * WS, Wsm + half * 64 * WS, 2 * mw + tt, lane, g0, g1);
+            gram_accumulate(g0, g1, inv_q, gfix[tt], &ovf);
+          }
+        }
+        nbar_sync(NB_MSYNC2, 256);
+        if (i + 2 < nb_local) nbar_arrive(NB_EMPTY + buf, TCG_THREADS);
+      }
+      gram_flush(set, 2 * mw, lane, gfix[0], ovf);
+      gram_flush(set, 2 * mw + 1, lane, gfix[1], 0);
     }
     __syncthreads();
+    flush_scalars(sacc, set, 4);
+    RedView rvw;
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
+                             a.dbg ? stA : nullptr)) { exit_reason = -2; break; }
+    {
+      // everything that depends on the reduced data is fetched in one round trip
+      const u64 flag = rvw.load(ACC_FLAG_OFF);
+      double c = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int e = tid + TCG_THREADS * h;
+        const int i = e >> 5, jj = e & 31, et = jj * ST_P + i;
+        const double v1 = fix2_to_double((i64)rvw.load(ACC_GRAM_OFF + 2 * e), (i64)rvw.load(ACC_GRAM_OFF + 2 * e + 1), q);
+        const double v2 = fix2_to_double((i64)rvw.load(ACC_GRAM_OFF + 2 * et), (i64)rvw.load(ACC_GRAM_OFF + 2 * et + 1), q);
+        const double sg = 0.5 * (v1 + v2);
+        Gsm[i * WS + jj] = -sg;
+        c = fma(sg, sg, c);
+      }
+      finalize_scalars(rvw, sh, 0, 4);
+      c = warp_sum(c);
+      if (lane == 0) s_part[warp] = c;
+      __syncthreads();
+      if (flag != 0) { exit_reason = -3; break; }
+      if (tid == 0) {
+        double nG2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < TCG_WARPS; ++w) nG2 += s_part[w];
+        const double nHp2 = fmax(sh.red[SC_HPHP] - nG2, 0.0);
+        decide_after_A(sh, sh.red[SC_PHP], nHp2, sh.red[SC_PP], sh.red[SC_PR], a.Delta, a.epsilon);
+      }
+      __syncthreads();
+    }
     ++phase;
     const double step = sh.step;
     if (sh.action != ACT_CONTINUE) {
-      const size_t e0 = (size_t)b0 * ST_NB * ST_P;
-      const size_t e1 = (size_t)((b1 * ST_NB < st.n_rows) ? b1 * ST_NB : st.n_rows) * ST_P;
+      const size_t e0 = (size_t)row_lo * ST_P, e1 = (size_t)row_hi * ST_P;
       for (size_t e = e0 + 2 * (size_t)tid; e < e1; e += 2 * TCG_THREADS) {
         double2 sv = ldcg2(a.s + e);
         const double2 pv = ldcg2(p_new + e);
@@ -313,10 +409,15 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_stiefel_kernel(TcgCommon a
       u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
       for (int i = tid; i < ACC_WORDS; i += blockDim.x) nxt[i] = 0;
     }
-    for (unsigned long long b = b0; b < b1; ++b) {
-      const unsigned long long grow = b * ST_NB + 8 * warp + m;
+    for (long long sidx = s_hi - 1 - warp; sidx >= s_lo; sidx -= TCG_WARPS) {
+      const unsigned long long grow = (unsigned long long)sidx * 8ull + m;
       const bool valid = grow < st.n_rows;
       const size_t rowoff = (size_t)grow * ST_P;
+      if (sidx - TCG_WARPS >= s_lo && lane < 16) {   // this warp's next strip -> L2 (5 x 2 KB)
+        const size_t noff = (size_t)(sidx - TCG_WARPS) * 8 * ST_P + 16 * lane;
+        prefetch_l2(a.Hp + noff); prefetch_l2(a.s + noff); prefetch_l2(p_new + noff);
+        prefetch_l2(a.r + noff); prefetch_l2(st.Y + noff);
+      }
       double acc[4][2];
       double2 sv[4], pv[4], rv[4];
 #pragma unroll
@@ -351,18 +452,32 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_stiefel_kernel(TcgCommon a
     }
     __syncthreads();
     flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
-    if (!grid_barrier(a.barrier, gen, a.abort_flag)) { exit_reason = -2; break; }
-    finalize_scalars(set, sh, SC_RV, 1);
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
+                             KUL_STRIDE, rvw, a.dbg ? stB : nullptr)) { exit_reason = -2; break; }
+    finalize_scalars(rvw, sh, SC_RV, 1);
     __syncthreads();
-    if (tid == 0) update_after_B(sh, sh.red[SC_RV]);
+    if (tid == 0) {
+      update_after_B(sh, sh.red[SC_RV]);
+      const int e = gram_exponent(st.op_norm_bound * sqrt(sh.pk_M_2) * 4.0);
+      s_invq = scalbn(1.0, 90 - e);
+      s_q = scalbn(1.0, e - 90);
+    }
     __syncthreads();
     ++phase;
+    if (a.dbg && tid == 0) {   // [work A, wait A, work B, wait B]; work = previous release -> arrival
+      if (dbg_prev) atomicAdd(a.dbg + 4 * blockIdx.x + 0, stA[0] - dbg_prev);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 1, stA[1] - stA[0]);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 2, stB[0] - stA[1]);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 3, stB[1] - stB[0]);
+      dbg_prev = stB[1];
+    }
   }
 
   if (blockIdx.x == 0 && tid == 0) {
     TcgDeviceResult *res = a.result;
     res->num_iterations = sh.k;
     res->final_rv = sh.rv;
+    res->phases = phase;
     if (exit_reason < 0) {
       res->status = (exit_reason == -3) ? 4 /*OB200_NUMERIC_RANGE*/ : 5 /*OB200_ABORTED*/;
       res->exit_reason = -1;
@@ -533,7 +648,7 @@ static bool g_attr_done = false;
 static cudaError_t ensure_attrs() {
   if (g_attr_done) return cudaSuccess;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(tcg_stiefel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL))) return e;
+  if ((e = cudaFuncSetAttribute(tcg_stiefel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_TOTAL))) return e;
   if ((e = cudaFuncSetAttribute(stiefel_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL))) return e;
   if ((e = cudaFuncSetAttribute(stiefel_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL))) return e;
   if ((e = cudaFuncSetAttribute(stiefel_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL))) return e;
@@ -550,7 +665,7 @@ cudaError_t launch_tcg_stiefel(const TcgCommon &a, unsigned long long n_rows, co
   StiefelArgs sa{n_rows, A, Y, S_dev, op_norm_bound};
   void *args[] = {(void *)&ac, (void *)&sa};
   return cudaLaunchCooperativeKernel((const void *)tcg_stiefel_kernel, dim3(grid), dim3(TCG_THREADS), args,
-                                     SM_TOTAL, stm);
+                                     V2_TOTAL, stm);
 }
 cudaError_t launch_stiefel_apply(unsigned long long n_rows, const unsigned short *A, const double *V,
                                  const double *S_dev, const double *Y, double *Wout, u64 *set, double inv_q,

@@ -39,6 +39,7 @@ class StpcgOutput:
     r0_norm: float
     final_rv: float
     kernel_launches: int
+    solve_kernel_ms: float = 0.0
 
 
 class Context:
@@ -68,6 +69,27 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    # -- multi-GPU ---------------------------------------------------------------
+    def connect(self, rank: int, world: int, all_gather_bytes=None):
+        """Join the NVLink peer-memory exchange of a `world`-rank job (one process
+        per GPU).  `all_gather_bytes(b) -> [bytes per rank]` exchanges the 64-byte
+        IPC handles; default: torch.distributed.all_gather_object."""
+        buf = (C.c_ubyte * capi.COMM_HANDLE_BYTES)()
+        self._check(self.lib.ob200_comm_export(self.h, buf))
+        mine = bytes(buf)
+        if all_gather_bytes is None:
+            import torch.distributed as dist
+
+            def all_gather_bytes(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+        handles = all_gather_bytes(mine)
+        assert len(handles) == world and handles[rank] == mine
+        blob = b"".join(handles)
+        self._check(self.lib.ob200_comm_connect(self.h, int(rank), int(world), blob))
+        self.rank, self.world = int(rank), int(world)
 
     # -- helpers ---------------------------------------------------------------
     def _check(self, rc):
@@ -154,7 +176,8 @@ class Context:
         self._check(rc)
         return StpcgOutput(s_out, res.update_step_M_norm, int(res.num_iterations),
                            capi.EXIT_NAMES.get(res.exit_reason, str(res.exit_reason)),
-                           res.r0_norm, res.final_rv, int(res.kernel_launches))
+                           res.r0_norm, res.final_rv, int(res.kernel_launches),
+                           float(res.solve_kernel_ms))
 
     def hvp(self, H: "OperatorHandle", v: torch.Tensor, out=None):
         if out is None:
