@@ -61,10 +61,24 @@ int ob200_synchronize(ob200_context *ctx);
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 uint64_t ob200_kernel_launches(const ob200_context *ctx);
 
+/* Options.  "tcgen05" (default 1): run the block contraction A*p of
+ * OB200_OP_STIEFEL_BLOCKDIAG on the 5th-generation tensor cores through the exact bf16
+ * digit-plane scheme whenever every block of A is 16-bit block-fixed-point; 0 forces the
+ * fp64 tensor-core (mma.sync) kernel.  ob200_last_path: 1 if the last ob200_stpcg ran the
+ * tcgen05 kernel, 0 otherwise. */
+int ob200_set_option(ob200_context *ctx, const char *name, int value);
+int ob200_last_path(const ob200_context *ctx);
+
 /* Profiling aid: when enabled, the persistent tCG kernels accumulate, per CTA, the
  * nanoseconds spent in {phase A, A reduction+barrier, phase B, B reduction+barrier};
  * a call with non-null outputs returns the max / min over CTAs and resets them. */
 int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, uint64_t *out4_min);
+
+/* Validation aid: out = A V for the block-diagonal bf16 A (n x 32 V), either on the
+ * fp64 tensor cores (use_tcgen05 = 0, mma.sync DMMA) or through the exact bf16
+ * digit-plane scheme on tcgen05 (use_tcgen05 = 1). */
+int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A_bf16_dev, const double *V_dev,
+                            double *out_dev, int use_tcgen05);
 
 /* ---- Hessian operator descriptors -----------------------------------------
  * Replaces the user's `Riemannian::LinearOperator` Hessian functor

@@ -30,6 +30,7 @@ EXPORTS = [
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
+    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path",
 ]
 
 
@@ -123,6 +124,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_stpcg_step_bytes.restype = u64
     lib.ob200_hvp_bytes.argtypes = [C.POINTER(Operator)]
     lib.ob200_hvp_bytes.restype = u64
+    lib.ob200_set_option.argtypes = [vp, C.c_char_p, i]
+    lib.ob200_last_path.argtypes = [vp]
+    lib.ob200_debug_block_apply.argtypes = [vp, u64, vp, vp, vp, i]
     lib.ob200_debug_phase_times.argtypes = [vp, i, C.POINTER(u64), C.POINTER(u64)]
     return lib
 

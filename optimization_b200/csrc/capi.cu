@@ -30,6 +30,14 @@ cudaError_t launch_stiefel_rowgemm(unsigned long long n_rows, const double *W, d
 cudaError_t launch_stiefel_absrowsum(const unsigned short *A, unsigned long long nrows_padded,
                                      unsigned long long *out_bits, cudaStream_t stm);
 int gram_exponent_host(double bound);
+cudaError_t launch_stiefel_planes(const unsigned short *A, unsigned long long nblk, unsigned char *planes,
+                                  int *plane_exp, int *unsupported, int sm_count, cudaStream_t st);
+cudaError_t launch_stiefel_ap_tc(unsigned long long n_rows, const unsigned char *planes, const int *plane_exp,
+                                 const double *P, double *Wout, int grid, cudaStream_t st);
+size_t stiefel_planes_bytes(unsigned long long nblk);
+cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
+                                  const double *Y, const double *S_dev, double op_norm_bound,
+                                  const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm);
 cudaError_t launch_dots(unsigned long long N, int count, const double *const *a, const double *const *b,
                         u64 *set, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st);
@@ -66,6 +74,15 @@ struct ob200_context {
   // multi-GPU
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long *dbg = nullptr;   // per-CTA phase timers (ob200_debug_phase_times)
+  // tcgen05 operand cache: digit planes of the last block-diagonal A seen (keyed by pointer + size)
+  unsigned char *planes = nullptr;
+  int *plane_exp = nullptr;       // [nblk] + [nblk] = unsupported flag
+  const void *planes_key = nullptr;
+  uint64_t planes_n = 0;
+  size_t planes_cap = 0;
+  bool planes_ok = false;
+  int opt_tcgen05 = 1;            // use the tcgen05 digit-plane contraction when A allows it
+  int last_path = 0;              // 1 = tcgen05 kernel, 0 = fp64 tensor-core kernel
   // multi-GPU exchange (CUDA IPC peer memory)
   CommDev cm;                     // rank, world, epoch, peer pointers
   u64 *comm_buf = nullptr;        // own inbox + flags
@@ -148,6 +165,8 @@ int ob200_destroy(ob200_context *ctx) {
     if (ctx->peer_base[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
   cudaFree(ctx->comm_buf);
   cudaFree(ctx->dbg);
+  cudaFree(ctx->planes);
+  cudaFree(ctx->plane_exp);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OB200_OK;
@@ -165,7 +184,7 @@ int ob200_synchronize(ob200_context *ctx) {
 
 int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, uint64_t *out4_min) {
   if (!ctx) return OB200_INVALID_ARGUMENT;
-  const size_t words = 4 * 1024;
+  const size_t words = 4 * 1024 + 64;
   if (enable && !ctx->dbg) {
     CK(cudaMalloc(&ctx->dbg, words * 8));
     CK(cudaMemset(ctx->dbg, 0, words * 8));
@@ -182,11 +201,23 @@ int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, 
         if (h[4 * b + k] < out4_min[k]) out4_min[k] = h[4 * b + k];
       }
     }
+    if (getenv("OB200_TIMELINE")) {
+      fprintf(stderr, "timeline (ns rel. to L start):");
+      for (int k = 0; k < 18; ++k) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - h[4096]));
+      fprintf(stderr, "\n");
+    }
     CK(cudaMemset(ctx->dbg, 0, words * 8));
   }
   if (!enable && ctx->dbg) { cudaFree(ctx->dbg); ctx->dbg = nullptr; }
   return OB200_OK;
 }
+
+int ob200_set_option(ob200_context *ctx, const char *name, int value) {
+  if (!ctx || !name) return OB200_INVALID_ARGUMENT;
+  if (!strcmp(name, "tcgen05")) { ctx->opt_tcgen05 = value; return OB200_OK; }
+  return fail(ctx, OB200_INVALID_ARGUMENT, "unknown option");
+}
+int ob200_last_path(const ob200_context *ctx) { return ctx ? ctx->last_path : -1; }
 
 int ob200_comm_export(ob200_context *ctx, void *handle_out) {
   if (!ctx || !handle_out) return OB200_INVALID_ARGUMENT;
@@ -293,6 +324,32 @@ static int ensure_staging(ob200_context *ctx, size_t N) {
   return OB200_OK;
 }
 
+// Digit planes of A for the tcgen05 contraction (built once per A; see tc_common.cuh).
+// Sets ctx->planes_ok = false when some block is not 16-bit block-fixed-point: the
+// caller then stays on the fp64 tensor-core path.
+static int ensure_planes(ob200_context *ctx, const uint16_t *A, uint64_t n) {
+  if (ctx->planes_key == A && ctx->planes_n == n) return OB200_OK;
+  const unsigned long long nblk = (n + 127) / 128;
+  const size_t bytes = stiefel_planes_bytes(nblk);
+  if (bytes > ctx->planes_cap) {
+    cudaFree(ctx->planes); cudaFree(ctx->plane_exp);
+    ctx->planes = nullptr; ctx->plane_exp = nullptr; ctx->planes_cap = 0; ctx->planes_key = nullptr;
+    CK(cudaMalloc(&ctx->planes, bytes));
+    CK(cudaMalloc(&ctx->plane_exp, sizeof(int) * (nblk + 1)));
+    ctx->planes_cap = bytes;
+  }
+  CK(cudaMemsetAsync(ctx->plane_exp + nblk, 0, sizeof(int), ctx->stream));
+  CK(launch_stiefel_planes(A, nblk, ctx->planes, ctx->plane_exp, ctx->plane_exp + nblk, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->plane_exp + nblk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->planes_ok = (bad == 0);
+  ctx->planes_key = A;
+  ctx->planes_n = n;
+  return OB200_OK;
+}
+
 // Cross-rank fold of set[off, off+count) (no-op on one GPU).  All ranks call it in lockstep.
 static int exchange(ob200_context *ctx, u64 *set, int off, int count, int mode = 0) {
   if (ctx->cm.world <= 1) return OB200_OK;
@@ -380,6 +437,11 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   }
   CK(cudaSetDevice(ctx->device));
   if ((rc = ensure_vectors(ctx, N))) return rc;
+  bool use_tc = false;
+  if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG && ctx->opt_tcgen05) {
+    if ((rc = ensure_planes(ctx, H->A_bf16_dev, H->n))) return rc;
+    use_tc = ctx->planes_ok;
+  }
   const uint64_t launches0 = ctx->launches;
   cudaStream_t st = ctx->stream;
 
@@ -429,7 +491,12 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     const unsigned long long nblk = (H->n + 127) / 128;
     int grid = ctx->sm_count;
     if ((unsigned long long)grid > nblk) grid = (int)nblk;
-    CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
+    if (use_tc)
+      CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
+                               ctx->plane_exp, grid, st));
+    else
+      CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
+    ctx->last_path = use_tc ? 1 : 0;
   }
   CK(cudaEventRecord(ctx->ev1, st));
   ctx->launches += 1;
@@ -567,6 +634,27 @@ int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16
     ctx->launches += 1;
     CK(cudaStreamSynchronize(st));  // hmat is reused
   }
+  return OB200_OK;
+}
+
+int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A, const double *V, double *out,
+                            int use_tcgen05) {
+  if (!ctx || !A || !V || !out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const unsigned long long nblk = (n + 127) / 128;
+  int grid = ctx->sm_count;
+  if ((unsigned long long)grid > nblk) grid = (int)nblk;
+  if (use_tcgen05) {
+    int rc = ensure_planes(ctx, A, n);
+    if (rc) return rc;
+    if (!ctx->planes_ok) return fail(ctx, OB200_UNSUPPORTED, "A is not 16-bit block-fixed-point: tcgen05 path unavailable");
+    CK(launch_stiefel_ap_tc(n, ctx->planes, ctx->plane_exp, V, out, grid, ctx->stream));
+  } else {
+    CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, ctx->stream));
+    CK(launch_stiefel_apply(n, A, V, nullptr, nullptr, out, ctx->acc, 1.0, grid, ctx->stream));
+  }
+  ctx->launches += 1;
+  CK(cudaStreamSynchronize(ctx->stream));
   return OB200_OK;
 }
 

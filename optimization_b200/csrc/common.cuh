@@ -229,6 +229,64 @@ __host__ __device__ __forceinline__ double fix2_to_double(i64 hi, i64 lo, double
 }
 
 // ---------------------------------------------------------------------------
+// Register-resident exact accumulation of bounded partial sums (hot loops).
+// A lane quantises its fp64 partial x (|x| <= bound < 2^e) to the integer
+// t = x / 2^(e-90) split as hi * 2^45 + lo (lo signed, |lo| <= 2^44) and adds both
+// halves to private int64 accumulators; integer adds are exact, so the total is
+// independent of which warp / CTA / GPU handled which unit.  At the end of a phase
+// the warp folds the 32 lanes with shuffles and lane 0 adds hi * 2^(e-45) and
+// lo * 2^(e-90) into the CTA's Kulisch accumulator.
+// ---------------------------------------------------------------------------
+struct FixAcc { i64 hi, lo; };
+
+__device__ __forceinline__ void fixacc_add(FixAcc &a, double x, double inv_q /* 2^(90-e) */, unsigned &ovf) {
+  const double t = x * inv_q;                         // exact power-of-two scaling
+  if (!(fabs(t) < 0x1p89)) { ovf = 1u; return; }      // also catches nan / inf
+  const double h = rint(t * 0x1p-45);
+  const double r = fma(-h, 0x1p45, t);                // exact, |r| <= 2^44
+  a.hi += (i64)h;
+  a.lo += (i64)rint(r);
+}
+
+#ifdef __CUDACC__
+// acc += v * 2^ex  (v any int64), 64-bit shared-memory atomics on the 32-bit-digit limbs
+__device__ __forceinline__ void kul_add_scaled_i64(u64 *acc, i64 v, int ex) {
+  if (v == 0) return;
+  const bool neg = v < 0;
+  const u64 mag = neg ? (u64)(-v) : (u64)v;           // < 2^63
+  const int P = ex + KUL_BIAS;                        // bit position of the LSB (callers keep it >= 0)
+  const int j = P >> 5, off = P & 31;
+  const u64 lo = mag << off;
+  const u64 hi = off ? (mag >> (64 - off)) : 0ull;
+  i64 d0 = (i64)(lo & 0xFFFFFFFFull), d1 = (i64)(lo >> 32), d2 = (i64)hi;
+  if (neg) { d0 = -d0; d1 = -d1; d2 = -d2; }
+  if (d0) atomicAdd(acc + j, (u64)d0);
+  if (d1) atomicAdd(acc + j + 1, (u64)d1);
+  if (d2) atomicAdd(acc + j + 2, (u64)d2);
+}
+// warp fold + flush into the CTA accumulator; e = exponent the lanes quantised with
+__device__ __forceinline__ void fixacc_flush(FixAcc &a, u64 *kul, int e) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a.hi += __shfl_xor_sync(0xffffffffu, a.hi, o);
+    a.lo += __shfl_xor_sync(0xffffffffu, a.lo, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    kul_add_scaled_i64(kul, a.hi, e - 45);
+    kul_add_scaled_i64(kul, a.lo, e - 90);
+  }
+  a.hi = 0;
+  a.lo = 0;
+}
+// exponent for a bound: |x| <= bound  =>  e = ilogb(bound) + 2, clamped so that e - 90 + KUL_BIAS >= 0
+__device__ __forceinline__ int fixacc_exponent(double bound) {
+  if (!(bound > 0.0) || !(bound < 1.0e300)) return 0;
+  const int e = ilogb(bound) + 2;
+  return e < -990 ? -990 : e;
+}
+#endif
+
+// ---------------------------------------------------------------------------
 // Grid-wide barrier for the persistent kernels (cooperative launch guarantees
 // co-residency).  Monotonic counter; `gen` is the caller's private generation.
 // Returns false if the watchdog expired (never on a healthy run): callers then
@@ -283,12 +341,13 @@ struct CommDev {
   int words_per_set;
 };
 
-struct RedView {   // reduced word j = sum_r base[r][j]
-  const u64 *base[MAX_RANKS];
+struct RedView {   // reduced word j = sum_r base0[r * stride + j]
+  const u64 *base0;
+  size_t stride;
   int world;
   __device__ __forceinline__ u64 load(int j) const {
-    u64 v = __ldcg(base[0] + j);
-    for (int r = 1; r < world; ++r) v += __ldcg(base[r] + j);
+    u64 v = __ldcg(base0 + j);
+    for (int r = 1; r < world; ++r) v += __ldcg(base0 + (size_t)r * stride + j);
     return v;
   }
 };
@@ -303,7 +362,7 @@ struct RedView {   // reduced word j = sum_r base[r][j]
 __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned &gen, int *abort_flag,
                                                     const CommDev &cm, unsigned long long gphase, u64 *set,
                                                     int off, int count, RedView &view,
-                                                    unsigned long long *stamps = nullptr) {
+                                                    unsigned long long *stamps = nullptr /* shared memory */) {
   __shared__ int s_ok, s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -330,8 +389,9 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
   }
   __syncthreads();
   view.world = cm.world;
+  view.stride = (size_t)cm.words_per_set;
   if (cm.world == 1) {
-    view.base[0] = set;
+    view.base0 = set;
     return s_ok != 0;
   }
   const int slot = (int)(gphase % ACC_SLOTS);
@@ -364,8 +424,7 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
     s_ok = (*((volatile int *)abort_flag) == 0);
   }
   __syncthreads();
-  for (int r = 0; r < cm.world; ++r)
-    view.base[r] = cm.inbox[cm.rank] + slot_off + (size_t)r * cm.words_per_set;
+  view.base0 = cm.inbox[cm.rank] + slot_off;
   return s_ok != 0;
 }
 

@@ -1,0 +1,560 @@
+// Persistent fused truncated-CG for the Stiefel trace-minimisation Hessian, v3:
+// the block contraction A * p runs on the 5th-generation tensor cores (tcgen05,
+// accumulators in TMEM) through the exact bf16 digit-plane scheme of tc_common.cuh;
+// the small fp64 x fp64 products (p S, the projection Gram Y^T W, Y symG) stay on
+// the fp64 tensor cores.  Same iteration structure, reductions and scalar logic as
+// tcg_stiefel_kernel (see tcg_stiefel.cu / tcg.cuh for the reference line map).
+//
+// 17 warps.  Phase A roles per 128-row block:
+//   L (warps 0-7)  : stream r, p_old -> p (written back), block maximum, digit slicing of
+//                    p into shared memory (UMMA operand image), then Y -> shared memory
+//   X (warp 16)    : one thread: bulk-copies (TMA 1-D) the precomputed A digit planes and
+//                    issues the 112 tcgen05.mma of the block; double-buffered TMEM accumulators
+//   M (warps 8-15) : TMEM -> registers, fp64 recombination, W -= p S, W written back,
+//                    projection Gram, exact accumulation of all partial sums
+// hand-offs through mbarriers (TMA / UMMA completion) and named barriers.
+#include "tcg.cuh"
+#include "stiefel_dev.cuh"
+#include "tc_common.cuh"
+
+namespace ob200 {
+using namespace tc;
+
+constexpr int V3_THREADS = 512;
+constexpr size_t V3_A = 0;                                   // 64 KB digit planes of A (1024-aligned)
+constexpr size_t V3_Q = V3_A + TC_ABLOCK;                    // 56 KB digit images of p
+constexpr size_t V3_W = V3_Q + TC_QBYTES;                    // 128 x 36 doubles
+constexpr size_t V3_Y = V3_W + sizeof(double) * ST_NB * WS;
+constexpr size_t V3_S = V3_Y + sizeof(double) * ST_NB * WS;
+constexpr size_t V3_G = V3_S + sizeof(double) * ST_P * WS;
+constexpr size_t V3_ACC = V3_G + sizeof(double) * ST_P * WS;
+constexpr size_t V3_BAR = V3_ACC + sizeof(u64) * ACC_NSCAL * KUL_STRIDE;
+constexpr size_t V3_TOTAL = V3_BAR + 256 + 1024;             // + alignment slack
+
+// mbarrier slots
+enum { MB_A_FULL = 0, MB_Q_FULL = 1, MB_MMA_DONE = 4 /*,5*/, MB_ACC_EMPTY = 6 /*,7*/ };
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Two 8x8 tiles (mt, nt0) and (mt, nt0 + 1) of Y^T W over one 64-row half block; the Y
+// fragments (shared by both tiles) come straight from global memory (L1, prefetched).
+__device__ __forceinline__ void gram_pair_half(const double *Yg /* row 0 of the half, or null */, int rows_valid,
+                                               const double *Zsm, int mt, int nt0, int lane, double (&g)[2][2]) {
+  const int m = lane >> 2, j = lane & 3;
+  g[0][0] = g[0][1] = g[1][0] = g[1][1] = 0.0;
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    double av[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int krow = 4 * (8 * qq + q) + j;
+      av[q] = (krow < rows_valid) ? __ldg(Yg + (size_t)krow * ST_P + 8 * mt + m) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int krow = 4 * (8 * qq + q) + j;
+      dmma884(g[0][0], g[0][1], av[q], Zsm[krow * WS + 8 * nt0 + m]);
+      dmma884(g[1][0], g[1][1], av[q], Zsm[krow * WS + 8 * (nt0 + 1) + m]);
+    }
+  }
+}
+
+// Two 8-row strips (rows 8*mw.. and 64+8*mw.. of the block) of W = (A p) - p S on the fp64 tensor
+// cores, interleaved so that eight independent accumulator chains are in flight: accumulators start
+// from the tcgen05 result staged in Wsm, A fragments pa0 / pa1 hold the strips' rows of p; W goes back
+// to Wsm (for the projection Gram) and to the Hp buffer; partials of <p,W> and <W,W>.
+__device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (&pa1)[8], bool own0, bool own1, int mw,
+                                          unsigned r0, double *Wsm, const double *Ssm, double *Hp,
+                                          unsigned n_rows, int lane, FixAcc &fa0, FixAcc &fa1, double fq0,
+                                          double fq1, unsigned &ovf) {
+  const int m = lane >> 2, j = lane & 3;
+  const int row0 = 8 * mw + m, row1 = 64 + 8 * mw + m;
+  double acc0[4][2], acc1[4][2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const double2 w0 = *reinterpret_cast<const double2 *>(Wsm + row0 * WS + 8 * t + 2 * j);
+    const double2 w1 = *reinterpret_cast<const double2 *>(Wsm + row1 * WS + 8 * t + 2 * j);
+    acc0[t][0] = w0.x; acc0[t][1] = w0.y;
+    acc1[t][0] = w1.x; acc1[t][1] = w1.y;
+  }
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq) {                        // W = A p - p S   (Ssm holds -S)
+    const double *Mrow = Ssm + (4 * qq + j) * WS + m;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const double sv = Mrow[8 * t];
+      dmma884(acc0[t][0], acc0[t][1], pa0[qq], sv);
+      dmma884(acc1[t][0], acc1[t][1], pa1[qq], sv);
+    }
+  }
+  const int src0 = 4 * m + 2 * (j & 1);
+#pragma unroll
+  for (int hs = 0; hs < 2; ++hs) {
+    if (!(hs ? own1 : own0)) continue;
+    const int row = hs ? row1 : row0;
+    const unsigned grow = r0 + row;
+    const bool valid = grow < n_rows;
+    double pw = 0.0, ww = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int col = 8 * t + 2 * j;
+      const double e0 = hs ? pa1[2 * t] : pa0[2 * t], e1 = hs ? pa1[2 * t + 1] : pa0[2 * t + 1];
+      // p[row][8t + 2j + c] lives in lane (m, 2(j&1) + c) as A-fragment element q = 2t + (j >> 1)
+      const double a0 = __shfl_sync(0xffffffffu, e0, src0), b0 = __shfl_sync(0xffffffffu, e1, src0);
+      const double a1 = __shfl_sync(0xffffffffu, e0, src0 + 1), b1 = __shfl_sync(0xffffffffu, e1, src0 + 1);
+      const double px = (j >> 1) ? b0 : a0, py = (j >> 1) ? b1 : a1;
+      const double wx = hs ? acc1[t][0] : acc0[t][0], wy = hs ? acc1[t][1] : acc0[t][1];
+      pw = fma(px, wx, pw); pw = fma(py, wy, pw);
+      ww = fma(wx, wx, ww); ww = fma(wy, wy, ww);
+      const double2 wv = make_double2(wx, wy);
+      *reinterpret_cast<double2 *>(Wsm + row * WS + col) = wv;
+      if (valid) stcg2(Hp + (size_t)grow * ST_P + col, wv);
+    }
+    fixacc_add(fa0, pw, fq0, ovf);   // exact-reduction unit: this lane's 8 elements of the strip
+    fixacc_add(fa1, ww, fq1, ovf);
+  }
+}
+
+extern __shared__ __align__(16) unsigned char v3_smem_raw[];
+
+// debug timeline (CTA 0, third block of an iteration): slot <- globaltimer
+#ifdef OB200_TIMELINE_BUILD
+#define TL(slot) do { if (a.dbg && blockIdx.x == 0 && i == 2 && lane == 0 && (warp == 0 || warp == 8)) \
+    a.dbg[4096 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(V3_THREADS, 1)
+tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, const int *plane_exp) {
+  __shared__ CgShared sh;
+  __shared__ double s_part[16];
+  __shared__ double s_invq, s_q;
+  __shared__ double s_lmax[16];
+  __shared__ int s_E[4];
+  __shared__ int s_fe[5];      // fixacc exponents: <p,W>, <W,W>, <p,p>, <p,r>, <r,r>
+  __shared__ uint32_t s_tmem;
+  __shared__ unsigned long long s_stamp[4];   // barrier arrival / release times (profiling aid)
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(v3_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *Asm = base + V3_A;
+  unsigned char *Qsm = base + V3_Q;
+  double *Wsm = reinterpret_cast<double *>(base + V3_W);
+  double *Ysm = reinterpret_cast<double *>(base + V3_Y);
+  double *Ssm = reinterpret_cast<double *>(base + V3_S);
+  double *Gsm = reinterpret_cast<double *>(base + V3_G);
+  u64 *sacc = reinterpret_cast<u64 *>(base + V3_ACC);
+  uint64_t *mb = reinterpret_cast<uint64_t *>(base + V3_BAR);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = lane >> 2, j = lane & 3;
+  const bool is_L = warp < 8;
+  const int mw = warp - 8;
+  for (int i = tid; i < ACC_NSCAL * KUL_STRIDE; i += blockDim.x) sacc[i] = 0;
+  for (int e = tid; e < ST_P * ST_P; e += blockDim.x) Ssm[(e >> 5) * WS + (e & 31)] = -st.S[e];
+  if (tid == 0) {
+    sh.rv = a.rv0;
+    sh.sk_M_pk = 0.0;
+    sh.sk_M_2 = 0.0;
+    sh.pk_M_2 = a.rv0;
+    sh.alpha = sh.beta = sh.kappa = sh.step = 0.0;
+    sh.k = 0;
+    sh.action = ACT_CONTINUE;
+    sh.status = 0;
+    const int e = gram_exponent(st.op_norm_bound * sqrt(a.rv0) * 4.0);
+    s_invq = scalbn(1.0, 90 - e);
+    s_q = scalbn(1.0, e - 90);
+    s_fe[SC_PHP] = fixacc_exponent(st.op_norm_bound * a.rv0);                         // |<p,W>| <= ||H|| ||p||^2
+    s_fe[SC_HPHP] = fixacc_exponent(st.op_norm_bound * st.op_norm_bound * a.rv0);
+    s_fe[SC_PP] = fixacc_exponent(a.rv0);                                             // ||p||^2 = pk_M_2 (l.266)
+    s_fe[SC_PR] = fixacc_exponent(a.rv0);                                             // |<p,r>| <= ||p|| ||r||
+    mbar_init(&mb[MB_A_FULL], 1);
+    mbar_init(&mb[MB_Q_FULL], 256);
+    mbar_init(&mb[MB_MMA_DONE], 1);
+    mbar_init(&mb[MB_MMA_DONE + 1], 1);
+    mbar_init(&mb[MB_ACC_EMPTY], 256);
+    mbar_init(&mb[MB_ACC_EMPTY + 1], 256);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  // ownership: 64-row half blocks [h0, h1)
+  // (32-bit row bookkeeping: local row counts stay below 2^31)
+  const unsigned n_rows32 = (unsigned)st.n_rows;
+  const unsigned nhalf = (n_rows32 + 63u) / 64u;
+  const unsigned h0 = (unsigned)((unsigned long long)nhalf * blockIdx.x / gridDim.x);
+  const unsigned h1 = (unsigned)((unsigned long long)nhalf * (blockIdx.x + 1ull) / gridDim.x);
+  const unsigned row_lo = h0 * 64u;
+  const unsigned row_hi = (h1 * 64u < n_rows32) ? h1 * 64u : n_rows32;
+  const unsigned bfirst = h0 >> 1;
+  const int nb_local = (h1 > h0) ? (int)(((h1 - 1) >> 1) - bfirst + 1) : 0;
+  const int s_lo = (int)(row_lo >> 3), s_hi = (int)((row_hi + 7u) >> 3);
+  unsigned gen = 0, phase = 0;
+  unsigned use = 0;            // blocks processed so far by this CTA (mbarrier phase bookkeeping)
+  int exit_reason = -1;
+  unsigned long long dbg_prev = 0;
+
+  for (;;) {
+    const unsigned long long k = sh.k;
+    if (k >= a.max_iterations) { exit_reason = 1; break; }
+    if (sqrt(sh.rv) <= a.target) { exit_reason = 0; break; }
+    const double beta = sh.beta;
+    const double *p_old = (k & 1ull) ? a.p1 : a.p0;
+    double *p_new = (k & 1ull) ? a.p0 : a.p1;
+    const double inv_q = s_invq, q = s_q;
+    FixAcc fa0 = {0, 0}, fa1 = {0, 0};            // L: <p,p>, <p,r> ; M: <p,W>, <W,W>
+    const int fe0 = is_L ? s_fe[SC_PP] : s_fe[SC_PHP], fe1 = is_L ? s_fe[SC_PR] : s_fe[SC_HPHP];
+    const double fq0 = scalbn(1.0, 90 - fe0), fq1 = scalbn(1.0, 90 - fe1);
+
+    // ------------------------------ phase A ------------------------------
+    u64 *set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
+    if (blockIdx.x == 0) {
+      u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
+      for (int i = tid; i < ACC_WORDS; i += blockDim.x) nxt[i] = 0;
+    }
+    unsigned ovf = 0;
+    if (is_L) {
+      // ===== loader warps (thread 0 also drives the TMA copies and issues the MMAs) =====
+      const int cp = tid & 15, g = tid >> 4;           // columns 2cp, 2cp+1 ; rows 8g .. 8g+7 of the block
+      for (int i = 0; i < nb_local; ++i) {
+        const unsigned u = use + i;
+        const unsigned b = bfirst + i, r0 = b * ST_NB;
+        TL(0);
+        if (i + 1 < nb_local) {   // next block's r, p_old, Y -> L2 (3 x 32 KB = 768 lines)
+          const size_t noff = (size_t)(r0 + ST_NB) * ST_P + 16 * (size_t)tid;
+          if (r0 + ST_NB + (tid >> 1) < n_rows32) {
+            prefetch_l2(a.r + noff);
+            prefetch_l2(st.Y + noff);
+            if (k) prefetch_l2(p_old + noff);
+          }
+        }
+        const unsigned hh = 2u * b + (g >> 3);      // this thread's half block
+        const bool own = hh >= h0 && hh < h1;
+        double p[8][2];
+        double pp = 0.0, pr = 0.0, mx = 0.0;
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          double2 rv[4], po[4];
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const unsigned grow = r0 + 8 * g + 4 * hrow + ii;
+            rv[ii] = po[ii] = make_double2(0.0, 0.0);
+            if (grow < n_rows32) {
+              const size_t off = (size_t)grow * ST_P + 2 * cp;
+              rv[ii] = ldcg2(a.r + off);
+              if (k) po[ii] = ldcg2(p_old + off);
+            }
+          }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const unsigned grow = r0 + 8 * g + 4 * hrow + ii;
+            double2 pv;
+            if (k) {
+              pv.x = fma(beta, po[ii].x, -rv[ii].x);        // l.420
+              pv.y = fma(beta, po[ii].y, -rv[ii].y);
+            } else {
+              pv.x = -rv[ii].x;                             // l.256
+              pv.y = -rv[ii].y;
+            }
+            if (own && grow < n_rows32) {
+              stcg2(p_new + (size_t)grow * ST_P + 2 * cp, pv);
+              pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
+              pr = fma(pv.x, rv[ii].x, pr); pr = fma(pv.y, rv[ii].y, pr);
+            }
+            p[4 * hrow + ii][0] = pv.x;
+            p[4 * hrow + ii][1] = pv.y;
+            mx = fmax(mx, fmax(fabs(pv.x), fabs(pv.y)));
+          }
+        }
+        TL(1);
+        // exact-reduction unit: this lane's 8 x 2 elements (all inside one half block)
+        if (own) {
+          fixacc_add(fa0, pp, fq0, ovf);
+          fixacc_add(fa1, pr, fq1, ovf);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) s_lmax[(u & 1) * 8 + warp] = mx;
+        nbar_sync(NB_LSYNC, 256);
+        mx = s_lmax[(u & 1) * 8];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) mx = fmax(mx, s_lmax[(u & 1) * 8 + w]);
+        // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
+        const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
+        TL(2);
+        if (u >= 1) mbar_wait(&mb[MB_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // A and digit images free
+        TL(3);
+        if (tid == 0) {
+          s_E[u & 3] = E;
+          mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
+          bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+        }
+        slice_tile_to_smem(p, scalbn(1.0, 56 - E), Qsm, tid);
+        fence_proxy_async_smem();
+        mbar_arrive(&mb[MB_Q_FULL]);
+        TL(4);
+        if (tid == 0) {
+          if (u >= 2) mbar_wait(&mb[MB_ACC_EMPTY + (u & 1)], ((u >> 1) - 1) & 1);         // accumulators drained
+          mbar_wait(&mb[MB_Q_FULL], u & 1);
+          TL(6);
+          mbar_wait(&mb[MB_A_FULL], u & 1);
+          TL(7);
+          tc_fence_after();
+          issue_block_mmas(smem_u32(Asm), smem_u32(Qsm), tmem_base + (u & 1) * TC_TMEM_COLS);
+          umma_commit(&mb[MB_MMA_DONE + (u & 1)]);
+          TL(8);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ===== math warps =====
+      const int q4 = warp & 3, chalf = mw >> 2;
+      i64 gfix[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      for (int i = 0; i < nb_local; ++i) {
+        const unsigned u = use + i;
+        const unsigned b = bfirst + i, r0 = b * ST_NB;
+        {   // Y of this block -> shared memory (free since the Gram of the previous block: NB_MSYNC3)
+          const int mt_ = tid - 256, cpy = mt_ & 15, gy = mt_ >> 4;
+          double2 yv[8];
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const unsigned grow = r0 + 8 * gy + ii;
+            yv[ii] = (grow < n_rows32) ? ldcg2(st.Y + (size_t)grow * ST_P + 2 * cpy) : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) *reinterpret_cast<double2 *>(Ysm + (8 * gy + ii) * WS + 2 * cpy) = yv[ii];
+        }
+        TL(9);
+        mbar_wait(&mb[MB_MMA_DONE + (u & 1)], (u >> 1) & 1);
+        TL(10);
+        tc_fence_after();
+        const int E = *((volatile int *)&s_E[u & 3]);              // written by L before the digits of block u
+        // p rows of this warp's strips as DMMA A fragments (from L2; p_new of block u was written by L before
+        // its digits); half 0 is in flight during the TMEM read-back, half 1 during the first p S product
+        bool hown[2];
+        double pa0[8], pa1[8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const unsigned hh = 2u * b + half;
+          hown[half] = hh >= h0 && hh < h1;
+        }
+        {
+          const unsigned grow = r0 + 8 * mw + m;
+          const bool ld = hown[0] && grow < n_rows32;
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) pa0[qq] = ld ? __ldcg(p_new + (size_t)grow * ST_P + 4 * qq + j) : 0.0;
+        }
+        {
+          double out[16];
+          recombine_row16(tmem_base + (u & 1) * TC_TMEM_COLS + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
+          tc_fence_before();
+          mbar_arrive(&mb[MB_ACC_EMPTY + (u & 1)]);
+          const double sc = scalbn(1.0, __ldg(plane_exp + b) + E);
+          double *wrow = Wsm + (32 * q4 + lane) * WS + 16 * chalf;
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(wrow + c) = make_double2(out[c] * sc, out[c + 1] * sc);
+        }
+        {
+          const unsigned grow = r0 + 8 * (8 + mw) + m;
+          const bool ld = hown[1] && grow < n_rows32;
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) pa1[qq] = ld ? __ldcg(p_new + (size_t)grow * ST_P + 4 * qq + j) : 0.0;
+        }
+        nbar_sync(NB_MSYNC, 256);                                // A p complete in Wsm
+        TL(11);
+        ps_strips(pa0, pa1, hown[0], hown[1], mw, r0, Wsm, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf);
+        nbar_sync(NB_MSYNC2, 256);                               // W complete in Wsm
+        TL(12);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (hown[half]) {
+            double g00, g01, g10, g11;
+            gram_pair_half_split(Ysm + half * 64 * WS, Wsm + half * 64 * WS, mw >> 1, 2 * (mw & 1), lane, g00, g01, g10, g11);
+            gram_accumulate(g00, g01, inv_q, gfix[0], &ovf);
+            gram_accumulate(g10, g11, inv_q, gfix[1], &ovf);
+          }
+        }
+        nbar_sync(NB_MSYNC3, 256);                               // Wsm free for the next block
+        TL(13);
+      }
+      gram_flush(set, 2 * mw, lane, gfix[0], ovf);
+      gram_flush(set, 2 * mw + 1, lane, gfix[1], 0);
+    }
+    use += (unsigned)nb_local;
+    fixacc_flush(fa0, sacc + (is_L ? SC_PP : SC_PHP) * KUL_STRIDE, fe0);
+    fixacc_flush(fa1, sacc + (is_L ? SC_PR : SC_HPHP) * KUL_STRIDE, fe1);
+    if (is_L && ovf) atomicOr((unsigned long long *)(set + ACC_FLAG_OFF), 1ull);
+    __syncthreads();
+    flush_scalars(sacc, set, 4);
+    RedView rvw;
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
+                             a.dbg ? s_stamp : nullptr)) { exit_reason = -2; break; }
+    {
+      const u64 flag = rvw.load(ACC_FLAG_OFF);
+      double c = 0.0;
+      {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = tid + 512 * h;
+          const int i = e >> 5, jj = e & 31, et = jj * ST_P + i;
+          const double v1 = fix2_to_double((i64)rvw.load(ACC_GRAM_OFF + 2 * e), (i64)rvw.load(ACC_GRAM_OFF + 2 * e + 1), q);
+          const double v2 = fix2_to_double((i64)rvw.load(ACC_GRAM_OFF + 2 * et), (i64)rvw.load(ACC_GRAM_OFF + 2 * et + 1), q);
+          const double sg = 0.5 * (v1 + v2);
+          Gsm[i * WS + jj] = -sg;
+          c = fma(sg, sg, c);
+        }
+      }
+      finalize_scalars(rvw, sh, 0, 4);
+      c = warp_sum(c);
+      if (lane == 0) s_part[warp] = c;
+      __syncthreads();
+      if (flag != 0) { exit_reason = -3; break; }
+      if (tid == 0) {
+        double nG2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) nG2 += s_part[w];
+        const double nHp2 = fmax(sh.red[SC_HPHP] - nG2, 0.0);
+        decide_after_A(sh, sh.red[SC_PHP], nHp2, sh.red[SC_PP], sh.red[SC_PR], a.Delta, a.epsilon);
+        const double rb = sqrt(sh.rv) + fabs(sh.step) * sqrt(sh.red[SC_HPHP]);        // ||r + alpha Hp|| <= ...
+        s_fe[SC_RV] = fixacc_exponent(rb * rb);
+      }
+      __syncthreads();
+    }
+    ++phase;
+    const double step = sh.step;
+    if (sh.action != ACT_CONTINUE) {
+      const size_t e0 = (size_t)row_lo * ST_P, e1 = (size_t)row_hi * ST_P;
+      for (size_t e = e0 + 2 * (size_t)tid; e < e1; e += 2 * (size_t)blockDim.x) {
+        double2 sv = ldcg2(a.s + e);
+        const double2 pv = ldcg2(p_new + e);
+        sv.x = fma(step, pv.x, sv.x);
+        sv.y = fma(step, pv.y, sv.y);
+        stcg2(a.s + e, sv);
+      }
+      exit_reason = sh.action - 1;
+      break;
+    }
+
+    // ------------------------------ phase B ------------------------------
+    set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
+    if (blockIdx.x == 0) {
+      u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
+      for (int i = tid; i < ACC_WORDS; i += blockDim.x) nxt[i] = 0;
+    }
+    unsigned ovfb = 0;
+    {
+      FixAcc fb = {0, 0};
+      const int feb = s_fe[SC_RV];
+      const double fqb = scalbn(1.0, 90 - feb);
+      for (int sidx = s_hi - 1 - warp; sidx >= s_lo; sidx -= 16) {
+        const unsigned grow = (unsigned)sidx * 8u + m;
+        const bool valid = grow < n_rows32;
+        const size_t rowoff = (size_t)grow * ST_P;
+        if (sidx - 16 >= s_lo && lane < 16) {   // this warp's next strip -> L2 (5 x 2 KB)
+          const size_t noff = (size_t)(sidx - 16) * 8 * ST_P + 16 * lane;
+          prefetch_l2(a.Hp + noff); prefetch_l2(a.s + noff); prefetch_l2(p_new + noff);
+          prefetch_l2(a.r + noff); prefetch_l2(st.Y + noff);
+        }
+        double acc[4][2];
+        double2 sv[4], pv[4], rv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = 8 * t + 2 * j;
+          if (valid) {
+            const double2 w = ldcg2(a.Hp + rowoff + col);
+            acc[t][0] = w.x; acc[t][1] = w.y;
+            sv[t] = ldcg2(a.s + rowoff + col);
+            pv[t] = ldcg2(p_new + rowoff + col);
+            rv[t] = ldcg2(a.r + rowoff + col);
+          } else {
+            acc[t][0] = acc[t][1] = 0.0;
+            sv[t] = pv[t] = rv[t] = make_double2(0.0, 0.0);
+          }
+        }
+        strip_rightmul(valid ? st.Y + rowoff : nullptr, Gsm, lane, acc);   // Hp = W - Y symG
+        double rr = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = 8 * t + 2 * j;
+          sv[t].x = fma(step, pv[t].x, sv[t].x);  sv[t].y = fma(step, pv[t].y, sv[t].y);      // l.374
+          rv[t].x = fma(step, acc[t][0], rv[t].x); rv[t].y = fma(step, acc[t][1], rv[t].y);   // l.377
+          rr = fma(rv[t].x, rv[t].x, rr); rr = fma(rv[t].y, rv[t].y, rr);                      // l.383,408
+          if (valid) {
+            stcg2(a.s + rowoff + col, sv[t]);
+            stcg2(a.r + rowoff + col, rv[t]);
+          }
+        }
+        fixacc_add(fb, rr, fqb, ovfb);      // exact-reduction unit: this lane's 8 elements of the strip
+      }
+      fixacc_flush(fb, sacc + SC_RV * KUL_STRIDE, feb);
+      if (ovfb) atomicAdd(sacc + SC_RV * KUL_STRIDE + KUL_LIMBS, 1ull);   // non-finite / bound violated: poison <r,r>
+    }
+    __syncthreads();
+    flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
+                             KUL_STRIDE, rvw, a.dbg ? s_stamp + 2 : nullptr)) { exit_reason = -2; break; }
+    finalize_scalars(rvw, sh, SC_RV, 1);
+    __syncthreads();
+    if (tid == 0) {
+      update_after_B(sh, sh.red[SC_RV]);
+      const int e = gram_exponent(st.op_norm_bound * sqrt(sh.pk_M_2) * 4.0);
+      s_invq = scalbn(1.0, 90 - e);
+      s_q = scalbn(1.0, e - 90);
+      s_fe[SC_PHP] = fixacc_exponent(st.op_norm_bound * sh.pk_M_2);
+      s_fe[SC_HPHP] = fixacc_exponent(st.op_norm_bound * st.op_norm_bound * sh.pk_M_2);
+      s_fe[SC_PP] = fixacc_exponent(sh.pk_M_2);
+      s_fe[SC_PR] = fixacc_exponent(sqrt(sh.pk_M_2) * sqrt(sh.rv));
+    }
+    __syncthreads();
+    ++phase;
+    if (a.dbg && tid == 0) {   // [work A, wait A, work B, wait B]; work = previous release -> arrival
+      if (dbg_prev) atomicAdd(a.dbg + 4 * blockIdx.x + 0, s_stamp[0] - dbg_prev);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 1, s_stamp[1] - s_stamp[0]);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 2, s_stamp[2] - s_stamp[1]);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 3, s_stamp[3] - s_stamp[2]);
+      dbg_prev = s_stamp[3];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (blockIdx.x == 0 && tid == 0) {
+    TcgDeviceResult *res = a.result;
+    res->num_iterations = sh.k;
+    res->final_rv = sh.rv;
+    res->phases = phase;
+    if (exit_reason < 0) {
+      res->status = (exit_reason == -3) ? 4 /*OB200_NUMERIC_RANGE*/ : 5 /*OB200_ABORTED*/;
+      res->exit_reason = -1;
+      res->update_step_M_norm = 0.0;
+    } else {
+      res->status = 0;
+      res->exit_reason = exit_reason;
+      res->update_step_M_norm = (exit_reason >= 2) ? a.Delta : sqrt(sh.sk_M_2);
+    }
+  }
+}
+
+cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
+                                  const double *Y, const double *S_dev, double op_norm_bound,
+                                  const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tcg_stiefel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_TOTAL);
+    if (e) return e;
+    attr = true;
+  }
+  TcgCommon ac = a;
+  StiefelArgs sa{n_rows, A, Y, S_dev, op_norm_bound};
+  const unsigned char *pl = planes;
+  const int *pe = plane_exp;
+  void *args[] = {(void *)&ac, (void *)&sa, (void *)&pl, (void *)&pe};
+  return cudaLaunchCooperativeKernel((const void *)tcg_stiefel_tc_kernel, dim3(grid), dim3(V3_THREADS), args,
+                                     V3_TOTAL, stm);
+}
+
+}  // namespace ob200

@@ -111,6 +111,13 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.ob200_kernel_launches(self.h))
 
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.ob200_set_option(self.h, name.encode(), int(value)))
+
+    @property
+    def last_path(self):
+        return {1: "tcgen05", 0: "dmma"}.get(self.lib.ob200_last_path(self.h), "?")
+
     def synchronize(self):
         self._check(self.lib.ob200_synchronize(self.h))
 
