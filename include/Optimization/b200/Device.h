@@ -1,0 +1,299 @@
+// B200 device layer for the drop-in headers: a device-resident matrix type that satisfies the
+// Vector requirements of the Krylov loops, descriptor functors that the solvers
+// recognise (std::function::target) to run the fused CUDA path, and the Stiefel trace-minimisation
+// model.  Everything here is a thin C++ veneer over the C ABI (include/optimization_b200.h); there is
+// no host arithmetic on n x p data.
+#pragma once
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "Optimization/LinearAlgebra/IterativeSolvers.h"
+#include "Optimization/Riemannian/Concepts.h"
+#include "Optimization/Riemannian/TNT.h"
+#include "optimization_b200.h"
+
+namespace Optimization {
+namespace b200 {
+
+inline void check(ob200_context *ctx, int rc) {
+  if (rc == OB200_OK) return;
+  const std::string msg = ob200_last_error(ctx);
+  if (rc == OB200_INVALID_ARGUMENT) throw std::invalid_argument(msg);   // the reference's error convention
+  throw std::runtime_error("optimization_b200 (status " + std::to_string(rc) + "): " + msg);
+}
+
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    if (ob200_create(device, nullptr, &h_) != OB200_OK)
+      throw std::runtime_error("optimization_b200: no usable CUDA device (there is no CPU fallback)");
+  }
+  ~Context() { ob200_destroy(h_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  ob200_context *get() const { return h_; }
+
+ private:
+  ob200_context *h_ = nullptr;
+};
+
+// n x p row-major fp64 matrix in device memory.  Value semantics (copies are device copies).
+class DeviceMatrix {
+ public:
+  DeviceMatrix() = default;
+  DeviceMatrix(ob200_context *ctx, size_t n, size_t p) : ctx_(ctx), n_(n), p_(p) { alloc(); }
+  DeviceMatrix(ob200_context *ctx, size_t n, size_t p, const double *host) : DeviceMatrix(ctx, n, p) {
+    check(ctx_, ob200_memcpy_h2d(ctx_, d_, host, bytes()));
+  }
+  DeviceMatrix(const DeviceMatrix &o) : ctx_(o.ctx_), n_(o.n_), p_(o.p_) {
+    if (o.d_) {
+      alloc();
+      check(ctx_, ob200_axpby(ctx_, size(), 1.0, o.d_, 0.0, nullptr, d_));
+    }
+  }
+  DeviceMatrix(DeviceMatrix &&o) noexcept { swap(o); }
+  DeviceMatrix &operator=(DeviceMatrix o) noexcept {
+    swap(o);
+    return *this;
+  }
+  ~DeviceMatrix() {
+    if (d_) ob200_free(ctx_, d_);
+  }
+  void swap(DeviceMatrix &o) noexcept {
+    std::swap(ctx_, o.ctx_);
+    std::swap(n_, o.n_);
+    std::swap(p_, o.p_);
+    std::swap(d_, o.d_);
+  }
+  size_t rows() const { return n_; }
+  size_t cols() const { return p_; }
+  size_t size() const { return n_ * p_; }
+  size_t bytes() const { return size() * sizeof(double); }
+  double *data() { return d_; }
+  const double *data() const { return d_; }
+  ob200_context *context() const { return ctx_; }
+  std::vector<double> to_host() const {
+    std::vector<double> h(size());
+    check(ctx_, ob200_memcpy_d2h(ctx_, h.data(), d_, bytes()));
+    return h;
+  }
+  DeviceMatrix like() const { return DeviceMatrix(ctx_, n_, p_); }
+
+  // out = a * x + b * y  (device level-1 kernel)
+  static DeviceMatrix axpby(double a, const DeviceMatrix &x, double b, const DeviceMatrix *y) {
+    DeviceMatrix out = x.like();
+    check(x.ctx_, ob200_axpby(x.ctx_, x.size(), a, x.d_, b, y ? y->d_ : nullptr, out.d_));
+    return out;
+  }
+  DeviceMatrix &operator+=(const DeviceMatrix &o) {
+    check(ctx_, ob200_axpby(ctx_, size(), 1.0, d_, 1.0, o.d_, d_));
+    return *this;
+  }
+  DeviceMatrix &operator-=(const DeviceMatrix &o) {
+    check(ctx_, ob200_axpby(ctx_, size(), 1.0, d_, -1.0, o.d_, d_));
+    return *this;
+  }
+  DeviceMatrix &operator*=(double a) {
+    check(ctx_, ob200_axpby(ctx_, size(), a, d_, 0.0, nullptr, d_));
+    return *this;
+  }
+
+ private:
+  void alloc() {
+    void *p = nullptr;
+    check(ctx_, ob200_malloc(ctx_, bytes() ? bytes() : 16, &p));
+    d_ = static_cast<double *>(p);
+  }
+  ob200_context *ctx_ = nullptr;
+  size_t n_ = 0, p_ = 0;
+  double *d_ = nullptr;
+};
+
+inline DeviceMatrix operator*(double a, const DeviceMatrix &v) { return DeviceMatrix::axpby(a, v, 0.0, nullptr); }
+inline DeviceMatrix operator*(int a, const DeviceMatrix &v) { return DeviceMatrix::axpby(double(a), v, 0.0, nullptr); }
+inline DeviceMatrix operator-(const DeviceMatrix &v) { return DeviceMatrix::axpby(-1.0, v, 0.0, nullptr); }
+inline DeviceMatrix operator+(const DeviceMatrix &x, const DeviceMatrix &y) { return DeviceMatrix::axpby(1.0, x, 1.0, &y); }
+inline DeviceMatrix operator-(const DeviceMatrix &x, const DeviceMatrix &y) { return DeviceMatrix::axpby(1.0, x, -1.0, &y); }
+
+inline double dot(const DeviceMatrix &a, const DeviceMatrix &b) {
+  double r = 0;
+  check(a.context(), ob200_dot(a.context(), a.size(), a.data(), b.data(), &r));
+  return r;
+}
+
+// ---- descriptor functors --------------------------------------------------------------------
+// Frobenius inner product / metric (the only metric the reference uses in-tree).
+struct FrobeniusProduct {
+  template <typename... Args>
+  double operator()(const DeviceMatrix &a, const DeviceMatrix &b, Args &...) const { return dot(a, b); }
+};
+struct FrobeniusMetric {
+  template <typename... Args>
+  double operator()(const DeviceMatrix &, const DeviceMatrix &a, const DeviceMatrix &b, Args &...) const {
+    return dot(a, b);
+  }
+};
+
+// State of a Hessian operator at the current point (what QM refreshes).
+struct OperatorState {
+  ob200_context *ctx = nullptr;
+  ob200_operator op{};
+  std::vector<double> S;        // host copy of sym(Y^T A Y) (op.S_host points here)
+  DeviceMatrix Y;               // base point the descriptor refers to (op.Y_dev points here)
+};
+
+// Hessian with the point already bound: SymmetricLinearOperator<DeviceMatrix, Args...>.
+struct BoundHessian {
+  std::shared_ptr<const OperatorState> st;
+  template <typename... Args>
+  DeviceMatrix operator()(const DeviceMatrix &v, Args &...) const {
+    DeviceMatrix out = v.like();
+    check(st->ctx, ob200_hvp(st->ctx, &st->op, v.data(), out.data()));
+    return out;
+  }
+};
+// Riemannian::LinearOperator<DeviceMatrix, DeviceMatrix, Args...> form (what QM hands to TNT).
+struct FusedHessian {
+  std::shared_ptr<const OperatorState> st;
+  template <typename... Args>
+  DeviceMatrix operator()(const DeviceMatrix &, const DeviceMatrix &v, Args &...a) const {
+    return BoundHessian{st}(v, a...);
+  }
+};
+// Pointwise (Jacobi) preconditioner v = minv .* r.
+struct BoundJacobi {
+  std::shared_ptr<const DeviceMatrix> minv;
+  template <typename... Args>
+  std::pair<DeviceMatrix, std::nullptr_t> operator()(const DeviceMatrix &r, Args &...) const {
+    DeviceMatrix out = r.like();
+    check(r.context(), ob200_hadamard(r.context(), r.size(), minv->data(), r.data(), out.data()));
+    return {std::move(out), nullptr};
+  }
+};
+
+// One fused tCG solve through the C ABI (ob200_stpcg): the whole STPCG loop in one persistent kernel.
+inline DeviceMatrix fused_stpcg(const OperatorState &st, const DeviceMatrix *minv, const DeviceMatrix &g,
+                                double &update_step_M_norm, size_t &num_iterations, double Delta,
+                                size_t max_iterations, double kappa_fgr, double theta, double epsilon) {
+  DeviceMatrix s = g.like();
+  ob200_stpcg_params prm{Delta, max_iterations, kappa_fgr, theta, epsilon};
+  ob200_precon pc{minv ? OB200_PRECON_JACOBI : OB200_PRECON_NONE, minv ? minv->data() : nullptr};
+  ob200_stpcg_result res{};
+  check(st.ctx, ob200_stpcg(st.ctx, &st.op, &pc, g.data(), &prm, s.data(), &res));
+  update_step_M_norm = res.update_step_M_norm;
+  num_iterations = res.num_iterations;
+  return s;
+}
+
+// ---- Stiefel trace minimisation  f(Y) = 1/2 tr(Y^T A Y),  A block-diagonal bf16 -----------------
+// Provides the functor set TNT<DeviceMatrix, DeviceMatrix, double>(f, QM, metric, retract, Y0, ...) takes.
+class StiefelTraceMin {
+ public:
+  StiefelTraceMin(ob200_context *ctx, size_t n, size_t p, const uint16_t *A_bf16_host) : ctx_(ctx), n_(n), p_(p) {
+    const size_t nblk = (n + 127) / 128, bytes = nblk * 128 * 128 * sizeof(uint16_t);
+    void *d = nullptr;
+    check(ctx_, ob200_malloc(ctx_, bytes, &d));
+    A_ = static_cast<uint16_t *>(d);
+    check(ctx_, ob200_memcpy_h2d(ctx_, A_, A_bf16_host, bytes));
+  }
+  ~StiefelTraceMin() { ob200_free(ctx_, A_); }
+  StiefelTraceMin(const StiefelTraceMin &) = delete;
+
+  Objective<DeviceMatrix, double> objective() const {
+    return [this](const DeviceMatrix &Y) {
+      double f = 0, bound = 0;
+      std::vector<double> S(p_ * p_);
+      check(ctx_, ob200_stiefel_model(ctx_, n_, p_, A_, Y.data(), S.data(), &f, nullptr, &bound));
+      return f;
+    };
+  }
+  Riemannian::QuadraticModel<DeviceMatrix, DeviceMatrix> quadratic_model() const {
+    return [this](const DeviceMatrix &Y, DeviceMatrix &grad,
+                  Riemannian::LinearOperator<DeviceMatrix, DeviceMatrix> &Hess) {
+      auto st = std::make_shared<OperatorState>();
+      st->ctx = ctx_;
+      st->S.assign(p_ * p_, 0.0);
+      st->Y = Y;
+      grad = Y.like();
+      double f = 0, bound = 0;
+      check(ctx_, ob200_stiefel_model(ctx_, n_, p_, A_, st->Y.data(), st->S.data(), &f, grad.data(), &bound));
+      st->op.kind = OB200_OP_STIEFEL_BLOCKDIAG;
+      st->op.n = n_;
+      st->op.p = p_;
+      st->op.A_bf16_dev = A_;
+      st->op.Y_dev = st->Y.data();
+      st->op.S_host = st->S.data();
+      st->op.op_norm_bound = bound;
+      Hess = FusedHessian{st};
+    };
+  }
+  Riemannian::RiemannianMetric<DeviceMatrix, DeviceMatrix, double> metric() const { return FrobeniusMetric{}; }
+  Riemannian::Retraction<DeviceMatrix, DeviceMatrix> retraction() const {
+    return [this](const DeviceMatrix &Y, const DeviceMatrix &V) {
+      DeviceMatrix out = Y.like();
+      check(ctx_, ob200_stiefel_retract(ctx_, n_, p_, Y.data(), V.data(), out.data()));
+      return out;
+    };
+  }
+
+ private:
+  ob200_context *ctx_;
+  size_t n_, p_;
+  uint16_t *A_ = nullptr;
+};
+
+}  // namespace b200
+
+// ---- TNT builds its inner views through this hook: descriptor functors stay visible ----------------
+namespace Riemannian {
+namespace detail {
+template <typename... Args>
+struct InnerViews<b200::DeviceMatrix, b200::DeviceMatrix, double, Args...> {
+  using M = b200::DeviceMatrix;
+  static LinearAlgebra::SymmetricLinearOperator<M, Args...>
+  hessian(const M &x, const LinearOperator<M, M, Args...> &Hess) {
+    if (const b200::FusedHessian *fh = Hess.template target<b200::FusedHessian>()) return b200::BoundHessian{fh->st};
+    return [&x, &Hess](const M &v, Args &...a) -> M { return Hess(x, v, a...); };
+  }
+  static LinearAlgebra::InnerProduct<M, double, Args...>
+  inner_product(const M &x, const RiemannianMetric<M, M, double, Args...> &metric) {
+    if (metric.template target<b200::FrobeniusMetric>()) return b200::FrobeniusProduct{};
+    return [&x, &metric](const M &a1, const M &a2, Args &...a) -> double { return metric(x, a1, a2, a...); };
+  }
+};
+}  // namespace detail
+}  // namespace Riemannian
+
+// ---- dispatch hook of STPCG for device matrices ---------------------------------------------------
+namespace LinearAlgebra {
+namespace detail {
+template <typename... Args>
+struct FusedSTPCG<b200::DeviceMatrix, std::nullptr_t, double, Args...> {
+  using V = b200::DeviceMatrix;
+  static bool run(const V &g, const SymmetricLinearOperator<V, Args...> &H, const InnerProduct<V, double, Args...> &ip,
+                  double &update_step_M_norm, size_t &num_iterations, double Delta, size_t max_iterations,
+                  double kappa_fgr, double theta,
+                  const std::optional<STPCGPreconditioner<V, std::nullptr_t, Args...>> &P,
+                  const std::optional<LinearOperator<std::nullptr_t, V, Args...>> &At,
+                  const std::optional<STPCGUserFunction<V, std::nullptr_t, double, Args...>> &user, double epsilon,
+                  V &out) {
+    if (At || user) return false;
+    const b200::BoundHessian *bh = H.template target<b200::BoundHessian>();
+    if (!bh || !ip.template target<b200::FrobeniusProduct>()) return false;
+    const b200::DeviceMatrix *minv = nullptr;
+    if (P) {
+      const b200::BoundJacobi *bj = P->template target<b200::BoundJacobi>();
+      if (!bj) return false;
+      minv = bj->minv.get();
+    }
+    out = b200::fused_stpcg(*bh->st, minv, g, update_step_M_norm, num_iterations, Delta, max_iterations, kappa_fgr,
+                            theta, epsilon);
+    return true;
+  }
+};
+}  // namespace detail
+}  // namespace LinearAlgebra
+}  // namespace Optimization
