@@ -204,6 +204,8 @@ int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, 
     if (getenv("OB200_TIMELINE")) {
       fprintf(stderr, "timeline (ns rel. to L start):");
       for (int k = 0; k < 18; ++k) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - h[4096]));
+      fprintf(stderr, "\nphase B timeline (ns rel. to barrier-A release):");
+      for (int k = 0; k < 14; ++k) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + 20 + k] - h[4096 + 20]));
       fprintf(stderr, "\n");
     }
     CK(cudaMemset(ctx->dbg, 0, words * 8));

@@ -278,6 +278,11 @@ __device__ __forceinline__ void fixacc_flush(FixAcc &a, u64 *kul, int e) {
   a.hi = 0;
   a.lo = 0;
 }
+// e with sqrt(x2) < 2^e, from integer exponent arithmetic (no square root on the scalar critical path)
+__device__ __forceinline__ int half_exponent(double x2) {
+  if (!(x2 > 0.0) || !(x2 < 1.0e300)) return 0;
+  return (ilogb(x2) + 2) >> 1;
+}
 // exponent for a bound: |x| <= bound  =>  e = ilogb(bound) + 2, clamped so that e - 90 + KUL_BIAS >= 0
 __device__ __forceinline__ int fixacc_exponent(double bound) {
   if (!(bound > 0.0) || !(bound < 1.0e300)) return 0;

@@ -110,6 +110,40 @@ __device__ __forceinline__ void gram_pair_half_split(const double *Xsm, const do
   g11 = (a1[0][1] + a1[1][1]) + (a1[2][1] + a1[3][1]);
 }
 
+// out strip += X_strip * M with vectorised operand loads: lane (m, j) reads its 8 CONTIGUOUS elements
+// X[row m][8j .. 8j+7] (four 16-byte loads) and k-step q contracts over the column set {8j + q}; the
+// B operand is indexed with the same permutation, so no shuffles are needed.  M is staged with row
+// stride GS (odd: the four j groups fall on disjoint bank halves).  Two k-halves run as independent
+// accumulator chains (the fp64 MMA has a long dependent-issue latency) and are added at the end.
+constexpr int GS = 33;
+__device__ __forceinline__ void strip_rightmul_load(const double *Xrow /* row of this lane or null */, int lane,
+                                                    double2 (&x)[4]) {
+  const int j = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = Xrow ? ldcg2(Xrow + 8 * j + 2 * i) : make_double2(0.0, 0.0);
+}
+__device__ __forceinline__ void strip_rightmul_v(const double2 (&x)[4], const double *Msm, int lane,
+                                                 double (&acc)[4][2]) {
+  const int m = lane >> 2, j = lane & 3;
+  double acc2[4][2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc2[t][0] = acc2[t][1] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double a_lo = (q & 1) ? x[q >> 1].y : x[q >> 1].x;              // column 8j + q
+    const double a_hi = (q & 1) ? x[2 + (q >> 1)].y : x[2 + (q >> 1)].x;  // column 8j + 4 + q
+    const double *Mlo = Msm + (8 * j + q) * GS + m;
+    const double *Mhi = Msm + (8 * j + 4 + q) * GS + m;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      dmma884(acc[t][0], acc[t][1], a_lo, Mlo[8 * t]);
+      dmma884(acc2[t][0], acc2[t][1], a_hi, Mhi[8 * t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { acc[t][0] += acc2[t][0]; acc[t][1] += acc2[t][1]; }
+}
+
 // out strip = C + X_strip * M  (M staged with stride WS); X read from global
 __device__ __forceinline__ void strip_rightmul(const double *Xrow /* row of this lane or null */,
                                                const double *Msm, int lane, double (&acc)[4][2]) {

@@ -12,9 +12,9 @@ namespace ob200 {
 using namespace tc;
 
 // ---------------------------------------------------------------------------------
-// planes[b] : 64 KB = [plane hi | lo][k-block 0 | 1][128 rows x 128 B, SW128]
+// planes[b] : 48 KB = [digit plane a2 | a1 | a0][128 rows x 128 B, SW128]   (int8)
 // plane_exp[b] = e_lsb (A = 2^e_lsb * A'), or INT_MIN if the block is not representable
-// with |A'| < 2^16 (then the operator stays on the fp64 tensor-core path).
+// with |A'| < 2^22 (then the operator stays on the fp64 tensor-core path).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stiefel_planes_kernel(const unsigned short *A, unsigned long long nblk,
                                                               unsigned char *planes, int *plane_exp,
@@ -42,41 +42,42 @@ __global__ void __launch_bounds__(256) stiefel_planes_kernel(const unsigned shor
     if (bad) atomicExch(unsupported, 1);
     __syncthreads();
     const int e_lsb = (s_msb < s_lsb) ? 0 : s_lsb;             // all-zero block -> 0
-    const bool ok = (s_msb < s_lsb) || (s_msb - s_lsb + 1 <= 16);
+    const bool ok = (s_msb < s_lsb) || (s_msb - s_lsb + 1 <= 22);
     if (threadIdx.x == 0) {
       plane_exp[b] = ok ? e_lsb : (int)0x80000000;
       if (!ok) atomicExch(unsupported, 1);
     }
     unsigned char *Pb = planes + b * (size_t)TC_ABLOCK;
-    // one thread per (row, 16-byte chunk): 128 rows x 16 chunks of 8 k
-    for (int idx = threadIdx.x; idx < TC_NB * 16; idx += blockDim.x) {
-      const int r = idx >> 4, ch = idx & 15;                   // k = 8 ch .. 8 ch + 7
-      const int kb = ch >> 3, c = ch & 7;
-      uint32_t hiw[4], low[4];
+    // one thread per (row, 16-byte chunk): 128 rows x 8 chunks of 16 k
+    for (int idx = threadIdx.x; idx < TC_NB * 8; idx += blockDim.x) {
+      const int r = idx >> 3, c = idx & 7;                     // k = 16 c .. 16 c + 15
+      uint32_t w2[4], w1[4], w0[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t hw = 0, lw = 0;
+        uint32_t x2 = 0, x1 = 0, x0 = 0;
 #pragma unroll
-        for (int z = 0; z < 2; ++z) {
-          const unsigned v = Ab[r * TC_NB + 8 * ch + 2 * q + z];
+        for (int z = 0; z < 4; ++z) {
+          const unsigned v = Ab[r * TC_NB + 16 * c + 4 * q + z];
           const int e = (v >> 7) & 0xff;
           const unsigned frac = v & 0x7f;
-          unsigned mag = 0;
+          int val = 0;
           if (ok && !(e == 0 && frac == 0) && e != 0xff) {
             const unsigned m = e ? (0x80u | frac) : frac;
             const int sh = (e ? e : 1) - 127 - 7 - e_lsb;      // value = m * 2^(sh + e_lsb)
-            mag = sh >= 0 ? (m << sh) : (m >> (-sh));          // exact (low bits are zero), < 2^16
+            const unsigned mag = sh >= 0 ? (m << sh) : (m >> (-sh));   // exact, < 2^22
+            val = (v & 0x8000u) ? -(int)mag : (int)mag;
           }
-          const uint32_t sgn = (v & 0x8000u);
-          hw |= bf16_of_u8(mag >> 8, sgn) << (16 * z);
-          lw |= bf16_of_u8(mag & 255u, sgn) << (16 * z);
+          const unsigned u = ((unsigned)val + 0x808080u) ^ 0x808080u;  // balanced base-256 digits in bytes 0..2
+          x0 |= (u & 255u) << (8 * z);
+          x1 |= ((u >> 8) & 255u) << (8 * z);
+          x2 |= ((u >> 16) & 255u) << (8 * z);
         }
-        hiw[q] = hw;
-        low[q] = lw;
+        w2[q] = x2; w1[q] = x1; w0[q] = x0;
       }
-      const uint32_t off = kb * TC_ATILE + sw128_chunk_off(r, c);
-      *reinterpret_cast<uint4 *>(Pb + off) = make_uint4(hiw[0], hiw[1], hiw[2], hiw[3]);
-      *reinterpret_cast<uint4 *>(Pb + TC_APLANE + off) = make_uint4(low[0], low[1], low[2], low[3]);
+      const uint32_t off = sw128_chunk_off(r, c);
+      *reinterpret_cast<uint4 *>(Pb + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+      *reinterpret_cast<uint4 *>(Pb + TC_APLANE + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+      *reinterpret_cast<uint4 *>(Pb + 2 * TC_APLANE + off) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
     }
     __syncthreads();
   }
@@ -137,7 +138,7 @@ stiefel_ap_tc_kernel(unsigned long long n_rows, const unsigned char *planes, con
     for (int w = 1; w < 8; ++w) mx = fmax(mx, s_max[w]);
     // |P| < 2^E
     const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
-    slice_tile_to_smem(p, scalbn(1.0, 56 - E), Qsm, tid);
+    slice_tile_to_smem(p, scalbn(1.0, 54 - E), Qsm, tid);
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -153,7 +154,7 @@ stiefel_ap_tc_kernel(unsigned long long n_rows, const unsigned char *planes, con
       const int row = 32 * q4 + lane;
       double out[16];
       recombine_row16(tmem_base + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
-      const double sc = scalbn(1.0, plane_exp[b] + E);
+      const double sc = scalbn(1.0, plane_exp[b] + E + 10);
       const unsigned long long grow = r0 + row;
       if (grow < n_rows) {
 #pragma unroll

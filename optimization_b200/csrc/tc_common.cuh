@@ -1,20 +1,21 @@
-// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers (sm_100a) and the exact
-// bf16 digit-plane scheme used to run the block contraction A * P on the 5th
-// generation tensor cores without giving up fp64 accuracy.
+// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers (sm_100a) and the exact integer
+// digit-plane scheme used to run the block contraction A * P on the 5th generation
+// tensor cores without giving up fp64 accuracy.
 //
-// Scheme.  A block of A (bf16) is a block-fixed-point matrix:
-// A = sa * A', A' integer, |A'| < 2^16, sa = 2^e_lsb.  Sign-magnitude byte planes
-//   A' = sgn * (hi * 256 + lo),   hi, lo in [0, 255]      (both exact in bf16)
+// Scheme.  A block of A (bf16 storage) is a block-fixed-point matrix:
+// A = 2^e_lsb * A', A' integer, |A'| < 2^22.  Its three balanced base-256 digits
+//   A' = a2 * 2^16 + a1 * 2^8 + a0,   a_h in [-128, 127]            (int8 planes)
 // are precomputed once per operator in the UMMA K-major SWIZZLE_128B shared-memory
 // image.  The fp64 tangent tile P (128 x 32) is scaled by the block maximum,
-// |P| < 2^E, rounded to a 56-bit fixed-point magnitude F and cut into seven
-// sign-magnitude 8-bit digits  F = sum_t d_t 2^(48-8t)  (each exact in bf16).
-// Every product plane_h x digit_t is < 2^16 and a K = 128 sum of them < 2^23, so
-// the fp32 accumulation in TMEM is EXACT; the eight accumulators
-//   D_u = hi * digit_u + lo * digit_(u-1)        (two pairs each: < 2^24, exact)
-// are recombined in fp64:  (A P) = 2^(e_lsb + E) * sum_u D_u 2^(-8u).
-// The only rounding is the 2^(E-56) quantisation of P (below fp64 resolution of
-// the block maximum) and the final fp64 Horner sum.
+// |P| < 2^E, rounded to the 55-bit signed fixed point F = rint(P * 2^(54-E)) and cut
+// into seven balanced int8 digits  F = sum_i d_i 2^(8i).  The tensor cores
+// (tcgen05.mma kind::i8, int32 accumulators in TMEM: integer arithmetic, exact)
+// form   D_u = sum_{h + i = 8 - u} a_h * d_i ,  u = 0 .. 7   (|D_u| < 2^23),
+// the pair (a0, d0) -- weight 2^-64 of the leading one -- being dropped, and
+//   A P = 2^(e_lsb + E + 10) * sum_u D_u 2^(-8u)
+// is recombined with 64-bit integer adds and one fp64 FMA per element.  The only
+// roundings are the quantisation of P (2^-54 of the block maximum, below the fp64
+// resolution of that maximum) and the final fp64 rounding.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -103,18 +104,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = n (multiple of 16, <= 256)
-__host__ __device__ constexpr uint32_t idesc_bf16_m128(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// kind::i8, A = B = signed int8 (K-major), D = s32, M = 128, N = n (multiple of 16, <= 256)
+__host__ __device__ constexpr uint32_t idesc_s8_m128(uint32_t n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; single thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+__device__ __forceinline__ void umma_s8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -125,115 +126,112 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 }
 
 // ---- layout of the operand images -------------------------------------------------------
-// One K-major SW128 tile: `rows` rows x 64 bf16 (128 B per row).  Byte offset of the
-// 16-byte chunk c (8 elements: k = 8c .. 8c+7) of row r:
+// One K-major SW128 tile of int8: `rows` rows x 128 elements (128 B per row = the whole K = 128).
+// Byte offset of the 16-byte chunk c (k = 16c .. 16c+15) of row r:
 __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);
 }
 constexpr uint32_t TC_NB = 128;                       // block rows / cols (M and K)
 constexpr uint32_t TC_N = 32;                         // p
-constexpr uint32_t TC_ATILE = TC_NB * 128;            // 16 KB: 128 rows x 64 k
-constexpr uint32_t TC_APLANE = 2 * TC_ATILE;          // 32 KB: K = 128 -> 2 k-blocks
-constexpr uint32_t TC_ABLOCK = 2 * TC_APLANE;         // 64 KB: hi + lo planes   [plane][kb]
-constexpr uint32_t TC_QTILE = TC_N * 128;             // 4 KB: one digit slice, 32 rows(n) x 64 k
+constexpr int TC_PLANES = 3;
+constexpr uint32_t TC_APLANE = TC_NB * 128;           // 16 KB: 128 rows x 128 k (int8)
+constexpr uint32_t TC_ABLOCK = TC_PLANES * TC_APLANE; // 48 KB                      [plane h = 2, 1, 0]
 constexpr int TC_SLICES = 7;
-constexpr uint32_t TC_QKB = TC_SLICES * TC_QTILE;     // 28 KB: the 7 slices stacked along N (224 rows) for one k-block
-constexpr uint32_t TC_QBYTES = 2 * TC_QKB;            // 56 KB                     [kb][slice][n]
-constexpr int TC_NACC = TC_SLICES + 1;                // 8 accumulators x 32 columns = 256 TMEM columns
+constexpr uint32_t TC_QTILE = TC_N * 128;             // 4 KB: one digit slice, 32 rows(n) x 128 k
+constexpr uint32_t TC_QBYTES = TC_SLICES * TC_QTILE;  // 28 KB: slices stacked along N   [slice s <-> digit i = 6 - s][n]
+constexpr int TC_NACC = 8;                            // 8 accumulators x 32 columns = 256 TMEM columns
 constexpr uint32_t TC_TMEM_COLS = 256;
+constexpr unsigned long long TC_DIGIT_BIAS = 0x0080808080808080ull;
 
-// bf16 bit pattern of the integer d in [0, 255] with sign bit sgn (0 / 0x8000): exact
-__device__ __forceinline__ uint32_t bf16_of_u8(uint32_t d, uint32_t sgn) {
-  const float f = __uint_as_float(0x4B000000u | d) - 8388608.0f;   // (float)d, exact
-  return (__float_as_uint(f) >> 16) | sgn;
-}
-
-// Issue the MMAs of one block.  The seven digit slices are stacked along N, so one instruction
-// multiplies an A plane with all of them (N = 224: the 4 KB A tile is read from shared memory once per
-// 224 columns instead of once per 32).  The lo plane accumulates one slice to the right of the hi
-// plane (columns [32, 256) vs [0, 224)), which realises  D_u = hi * d_u + lo * d_(u-1)  in place:
-//   first k-step : lo -> [32,256) (overwrite) ; hi -> [0,32) (overwrite) and [32,224) (accumulate)
-//   other k-steps: lo -> [32,256), hi -> [0,224), accumulate.                       17 instructions.
+// Issue the MMAs of one block (13 instructions).  The digit slices are stacked along N, so one
+// instruction multiplies an A plane with all of them; plane h lands (2 - h) accumulators to the right,
+// which realises  D_u = sum_{h+i = 8-u} a_h d_i  in place:
+//   plane 2 (most significant) x slices 0..6 -> columns [0, 224)
+//   plane 1                    x slices 0..6 -> columns [32, 256)
+//   plane 0                    x slices 0..5 -> columns [64, 256)     (a0 x d0 dropped)
+// K = 32 per instruction -> 4 k-steps.  First k-step: plane 1 overwrites [32,256), plane 2 overwrites
+// [0,32) and accumulates into [32,224), plane 0 accumulates.
 __device__ __forceinline__ void issue_block_mmas(uint32_t a_base, uint32_t q_base, uint32_t tmem_base) {
   const uint64_t ad0 = umma_desc_k_sw128(a_base);
   const uint64_t bd0 = umma_desc_k_sw128(q_base);
 #pragma unroll
-  for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-    for (int k16 = 0; k16 < 4; ++k16) {
-      const uint64_t a_hi = ad0 + (uint64_t)((kb * TC_ATILE + 32 * k16) >> 4);
-      const uint64_t a_lo = a_hi + (uint64_t)(TC_APLANE >> 4);
-      const uint64_t bd = bd0 + (uint64_t)((kb * TC_QKB + 32 * k16) >> 4);
-      if (kb == 0 && k16 == 0) {
-        umma_bf16(tmem_base + TC_N, a_lo, bd, idesc_bf16_m128(224), 0u);
-        umma_bf16(tmem_base, a_hi, bd, idesc_bf16_m128(32), 0u);
-        umma_bf16(tmem_base + TC_N, a_hi, bd + (uint64_t)(TC_QTILE >> 4), idesc_bf16_m128(192), 1u);
-      } else {
-        umma_bf16(tmem_base + TC_N, a_lo, bd, idesc_bf16_m128(224), 1u);
-        umma_bf16(tmem_base, a_hi, bd, idesc_bf16_m128(224), 1u);
-      }
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t a2 = ad0 + (uint64_t)((32 * ks) >> 4);
+    const uint64_t a1 = a2 + (uint64_t)(TC_APLANE >> 4);
+    const uint64_t a0 = a1 + (uint64_t)(TC_APLANE >> 4);
+    const uint64_t bd = bd0 + (uint64_t)((32 * ks) >> 4);
+    if (ks == 0) {
+      umma_s8(tmem_base + TC_N, a1, bd, idesc_s8_m128(224), 0u);
+      umma_s8(tmem_base, a2, bd, idesc_s8_m128(32), 0u);
+      umma_s8(tmem_base + TC_N, a2, bd + (uint64_t)(TC_QTILE >> 4), idesc_s8_m128(192), 1u);
+    } else {
+      umma_s8(tmem_base + TC_N, a1, bd, idesc_s8_m128(224), 1u);
+      umma_s8(tmem_base, a2, bd, idesc_s8_m128(224), 1u);
     }
+    umma_s8(tmem_base + 2 * TC_N, a0, bd, idesc_s8_m128(192), 1u);
   }
 }
 
 // ---------------------------------------------------------------------------------
-// Digit slicing of a 128 x 32 fp64 tile into the seven bf16 digit images.
+// Digit slicing of a 128 x 32 fp64 tile into the seven int8 digit images.
 // Thread mapping (256 threads): cp = tid & 15 -> columns n = 2cp, 2cp+1 ; g = tid >> 4 ->
-// rows k = 8g .. 8g+7, i.e. exactly one 16-byte chunk per (slice, n).
-// `p[i][z]` = P[8g + i][2cp + z]; scale = 2^(56 - E) with |P| < 2^E over the whole tile.
+// rows k = 8g .. 8g+7, i.e. one 8-byte half chunk per (slice, n).
+// `p[i][z]` = P[8g + i][2cp + z]; scale = 2^(54 - E) with |P| < 2^E over the whole tile.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void slice_tile_to_smem(const double (&p)[8][2], double scale, unsigned char *Qsm,
                                                    int tid) {
   const int cp = tid & 15, g = tid >> 4;
-  const int kb = g >> 3, c = g & 7;
+  const uint32_t c = g >> 1, hbyte = (g & 1) * 8;
 #pragma unroll
   for (int z = 0; z < 2; ++z) {
-    const int n = 2 * cp + z;
-    unsigned long long F[8];
-    uint32_t sg[8];
+    const uint32_t n = 2 * cp + z;
+    uint32_t lo[8], hi[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      F[i] = (unsigned long long)__double2ll_rn(fabs(p[i][z]) * scale);     // < 2^56
-      sg[i] = (uint32_t)(((unsigned long long)__double_as_longlong(p[i][z])) >> 63) << 15;
+      // balanced digits: byte j of ((F + bias) ^ bias) is the int8 digit d_j
+      const unsigned long long u =
+          ((unsigned long long)__double2ll_rn(p[i][z] * scale) + TC_DIGIT_BIAS) ^ TC_DIGIT_BIAS;
+      lo[i] = (uint32_t)u;
+      hi[i] = (uint32_t)(u >> 32);
     }
-    const uint32_t off = kb * TC_QKB + sw128_chunk_off(n, c);
+    const uint32_t off = sw128_chunk_off(n, c) + hbyte;
 #pragma unroll
-    for (int t = 0; t < TC_SLICES; ++t) {
-      uint32_t w[4];
+    for (int s = 0; s < TC_SLICES; ++s) {
+      const int d = 6 - s;                                    // digit index held by slice s
+      const uint32_t sel = (d & 3) | (((d & 3) + 4) << 4);    // byte d of a -> pos 0, byte d of b -> pos 1
+      uint32_t w[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t d0 = (uint32_t)(F[2 * q] >> (48 - 8 * t)) & 255u;
-        const uint32_t d1 = (uint32_t)(F[2 * q + 1] >> (48 - 8 * t)) & 255u;
-        w[q] = bf16_of_u8(d0, sg[2 * q]) | (bf16_of_u8(d1, sg[2 * q + 1]) << 16);
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t x0 = d < 4 ? lo[4 * q] : hi[4 * q], x1 = d < 4 ? lo[4 * q + 1] : hi[4 * q + 1];
+        const uint32_t x2 = d < 4 ? lo[4 * q + 2] : hi[4 * q + 2], x3 = d < 4 ? lo[4 * q + 3] : hi[4 * q + 3];
+        const uint32_t t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
+        w[q] = __byte_perm(t01, t23, 0x5410);
       }
-      *reinterpret_cast<uint4 *>(Qsm + t * TC_QTILE + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint2 *>(Qsm + s * TC_QTILE + off) = make_uint2(w[0], w[1]);
     }
   }
 }
 
-// fp64 recombination of the eight fp32 accumulators of this thread's row:
-// out[c] = sum_u D_u[row][col0 + c] 2^(-8u)   (Horner, smallest first), 16 columns.
-// The eight TMEM loads of an 8-column group are issued back to back and waited for once.
+// Recombination of the eight int32 accumulators of this thread's row:
+// out[c] = sum_u D_u[row][col0 + c] 2^(-8u), 16 columns; 64-bit integer adds, one fp64 FMA.
 __device__ __forceinline__ void recombine_row16(uint32_t tmem_row_addr /* lane | col0 */, double (&out)[16]) {
 #pragma unroll
   for (int hcol = 0; hcol < 2; ++hcol) {
-    double acc[8];
+    long long part[2][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
-#pragma unroll
-    for (int ub = TC_NACC - 4; ub >= 0; ub -= 4) {          // accumulators 7..4, then 3..0
+    for (int gq = 0; gq < 2; ++gq) {                          // accumulators 0..3 -> part[0], 4..7 -> part[1]
       uint32_t v[4][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) tmem_ld8(tmem_row_addr + (ub + u) * TC_N + 8 * hcol, v[u]);
+      for (int u = 0; u < 4; ++u) tmem_ld8(tmem_row_addr + (4 * gq + u) * TC_N + 8 * hcol, v[u]);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-#pragma unroll
-        for (int u = 3; u >= 0; --u) acc[c] = fma(acc[c], 0x1p-8, (double)__uint_as_float(v[u][c]));
-      }
+      for (int c = 0; c < 8; ++c)
+        part[gq][c] = (long long)(int)v[3][c] + ((long long)(int)v[2][c] << 8) + ((long long)(int)v[1][c] << 16) +
+                      ((long long)(int)v[0][c] << 24);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) out[8 * hcol + c] = acc[c];
+    for (int c = 0; c < 8; ++c)
+      out[8 * hcol + c] = fma((double)part[1][c], 0x1p-32, (double)part[0][c]) * 0x1p-24;
   }
 }
 

@@ -125,6 +125,40 @@ __device__ __forceinline__ void decide_after_A(CgShared &sh, double kappa, doubl
   sh.action = ACT_CONTINUE;
 }
 
+// Same decisions with the three long-latency operations (two square roots, one division) already
+// evaluated -- by different lanes, concurrently; values and rounding are identical to decide_after_A.
+__device__ __forceinline__ void decide_after_A_pre(CgShared &sh, double kappa, double sq_nHp2, double sq_np2,
+                                                   double alpha, double pr, double Delta, double epsilon) {
+  const double Delta_2 = __dmul_rn(Delta, Delta);                       // l.271
+  sh.kappa = kappa;                                                     // l.300
+  if (__ddiv_rn(sq_nHp2, sq_np2) < epsilon) {                           // l.305-307
+    double sgn = 1.0;
+    if (pr < 0) {                                                       // l.320-326
+      sgn = -1.0;
+      sh.sk_M_pk = -sh.sk_M_pk;
+    }
+    const double disc = __dadd_rn(__dmul_rn(sh.sk_M_pk, sh.sk_M_pk),
+                                  __dmul_rn(sh.pk_M_2, __dsub_rn(Delta_2, sh.sk_M_2)));
+    const double sigma = __ddiv_rn(__dadd_rn(-sh.sk_M_pk, sqrt(disc)), sh.pk_M_2);  // l.330-332
+    sh.step = __dmul_rn(sgn, sigma);
+    sh.action = 2 /*OB200_EXIT_KERNEL*/ + 1;
+    return;
+  }
+  const double skp1 = __dadd_rn(__dadd_rn(sh.sk_M_2, __dmul_rn(__dmul_rn(2.0, alpha), sh.sk_M_pk)),
+                                __dmul_rn(__dmul_rn(alpha, alpha), sh.pk_M_2));  // l.344-345
+  if (kappa <= 0 || skp1 > Delta_2) {                                   // l.347
+    const double disc = __dadd_rn(__dmul_rn(sh.sk_M_pk, sh.sk_M_pk),
+                                  __dmul_rn(sh.pk_M_2, __dsub_rn(Delta_2, sh.sk_M_2)));
+    sh.step = __ddiv_rn(__dadd_rn(-sh.sk_M_pk, sqrt(disc)), sh.pk_M_2);  // l.355-357
+    sh.action = 3 /*OB200_EXIT_BOUNDARY*/ + 1;
+    return;
+  }
+  sh.alpha = alpha;
+  sh.step = alpha;
+  sh.sk_M_2 = skp1;  // l.415 (value is consumed only after phase B)
+  sh.action = ACT_CONTINUE;
+}
+
 // Scalar logic after phase B.  Reference IterativeSolvers.h:408-417.
 // NOTE: sh.sk_M_2 already holds skplus1_M_2; sk_M_pk / pk_M_2 are updated here.
 __device__ __forceinline__ void update_after_B(CgShared &sh, double rk_vk) {

@@ -21,9 +21,9 @@ namespace ob200 {
 using namespace tc;
 
 constexpr int V3_THREADS = 512;
-constexpr size_t V3_A = 0;                                   // 64 KB digit planes of A (1024-aligned)
-constexpr size_t V3_Q = V3_A + TC_ABLOCK;                    // 56 KB digit images of p
-constexpr size_t V3_W = V3_Q + TC_QBYTES;                    // 128 x 36 doubles
+constexpr size_t V3_A = 0;                                   // 48 KB int8 digit planes of A (1024-aligned)
+constexpr size_t V3_Q = V3_A + TC_ABLOCK;                    // 2 x 28 KB int8 digit images of p (double buffered)
+constexpr size_t V3_W = V3_Q + 2 * TC_QBYTES;                // 128 x 36 doubles
 constexpr size_t V3_Y = V3_W + sizeof(double) * ST_NB * WS;
 constexpr size_t V3_S = V3_Y + sizeof(double) * ST_NB * WS;
 constexpr size_t V3_G = V3_S + sizeof(double) * ST_P * WS;
@@ -66,7 +66,7 @@ __device__ __forceinline__ void gram_pair_half(const double *Yg /* row 0 of the 
 __device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (&pa1)[8], bool own0, bool own1, int mw,
                                           unsigned r0, double *Wsm, const double *Ssm, double *Hp,
                                           unsigned n_rows, int lane, FixAcc &fa0, FixAcc &fa1, double fq0,
-                                          double fq1, unsigned &ovf) {
+                                          double fq1, unsigned &ovf, unsigned long long *tl = nullptr) {
   const int m = lane >> 2, j = lane & 3;
   const int row0 = 8 * mw + m, row1 = 64 + 8 * mw + m;
   double acc0[4][2], acc1[4][2];
@@ -77,6 +77,7 @@ __device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (
     acc0[t][0] = w0.x; acc0[t][1] = w0.y;
     acc1[t][0] = w1.x; acc1[t][1] = w1.y;
   }
+  if (tl) tl[14] = globaltimer_ns();
 #pragma unroll
   for (int qq = 0; qq < 8; ++qq) {                        // W = A p - p S   (Ssm holds -S)
     const double *Mrow = Ssm + (4 * qq + j) * WS + m;
@@ -87,6 +88,7 @@ __device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (
       dmma884(acc1[t][0], acc1[t][1], pa1[qq], sv);
     }
   }
+  if (tl) tl[15] = globaltimer_ns();
   const int src0 = 4 * m + 2 * (j & 1);
 #pragma unroll
   for (int hs = 0; hs < 2; ++hs) {
@@ -113,6 +115,7 @@ __device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (
     fixacc_add(fa0, pw, fq0, ovf);   // exact-reduction unit: this lane's 8 elements of the strip
     fixacc_add(fa1, ww, fq1, ovf);
   }
+  if (tl) tl[16] = globaltimer_ns();
 }
 
 extern __shared__ __align__(16) unsigned char v3_smem_raw[];
@@ -121,8 +124,10 @@ extern __shared__ __align__(16) unsigned char v3_smem_raw[];
 #ifdef OB200_TIMELINE_BUILD
 #define TL(slot) do { if (a.dbg && blockIdx.x == 0 && i == 2 && lane == 0 && (warp == 0 || warp == 8)) \
     a.dbg[4096 + (slot)] = globaltimer_ns(); } while (0)
+#define TLB(slot) do { if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[4096 + 20 + (slot)] = globaltimer_ns(); } while (0)
 #else
 #define TL(slot) do { } while (0)
+#define TLB(slot) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(V3_THREADS, 1)
@@ -211,9 +216,11 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
 
     // ------------------------------ phase A ------------------------------
     u64 *set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
-    if (blockIdx.x == 0) {
+    {   // recycle the set used two phases from now (every CTA clears its slice; a grid barrier intervenes)
       u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
-      for (int i = tid; i < ACC_WORDS; i += blockDim.x) nxt[i] = 0;
+      const int per = (ACC_WORDS + gridDim.x - 1) / gridDim.x;
+      const int z0 = per * blockIdx.x;
+      for (int i = tid; i < per && z0 + i < ACC_WORDS; i += blockDim.x) nxt[z0 + i] = 0;
     }
     unsigned ovf = 0;
     if (is_L) {
@@ -285,14 +292,16 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
         // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
         const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
         TL(2);
-        if (u >= 1) mbar_wait(&mb[MB_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // A and digit images free
+        if (u >= 2) mbar_wait(&mb[MB_MMA_DONE + (u & 1)], ((u - 2) >> 1) & 1);   // digit image (u & 1) free
         TL(3);
         if (tid == 0) {
           s_E[u & 3] = E;
-          mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
-          bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+          if (i == 0) {   // first block of the phase: every earlier MMA has completed; later blocks: see M
+            mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
+            bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+          }
         }
-        slice_tile_to_smem(p, scalbn(1.0, 56 - E), Qsm, tid);
+        slice_tile_to_smem(p, scalbn(1.0, 54 - E), Qsm + (u & 1) * TC_QBYTES, tid);
         fence_proxy_async_smem();
         mbar_arrive(&mb[MB_Q_FULL]);
         TL(4);
@@ -303,7 +312,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           mbar_wait(&mb[MB_A_FULL], u & 1);
           TL(7);
           tc_fence_after();
-          issue_block_mmas(smem_u32(Asm), smem_u32(Qsm), tmem_base + (u & 1) * TC_TMEM_COLS);
+          issue_block_mmas(smem_u32(Asm), smem_u32(Qsm + (u & 1) * TC_QBYTES), tmem_base + (u & 1) * TC_TMEM_COLS);
           umma_commit(&mb[MB_MMA_DONE + (u & 1)]);
           TL(8);
         }
@@ -330,6 +339,10 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
         TL(9);
         mbar_wait(&mb[MB_MMA_DONE + (u & 1)], (u >> 1) & 1);
         TL(10);
+        if (tid == 256 && i + 1 < nb_local) {   // the A image is free again: fetch the next block's digit planes
+          mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
+          bulk_g2s(Asm, planes + (size_t)(b + 1) * TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+        }
         tc_fence_after();
         const int E = *((volatile int *)&s_E[u & 3]);              // written by L before the digits of block u
         // p rows of this warp's strips as DMMA A fragments (from L2; p_new of block u was written by L before
@@ -352,7 +365,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           recombine_row16(tmem_base + (u & 1) * TC_TMEM_COLS + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
           tc_fence_before();
           mbar_arrive(&mb[MB_ACC_EMPTY + (u & 1)]);
-          const double sc = scalbn(1.0, __ldg(plane_exp + b) + E);
+          const double sc = scalbn(1.0, __ldg(plane_exp + b) + E + 10);
           double *wrow = Wsm + (32 * q4 + lane) * WS + 16 * chalf;
 #pragma unroll
           for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(wrow + c) = make_double2(out[c] * sc, out[c + 1] * sc);
@@ -365,7 +378,12 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
         }
         nbar_sync(NB_MSYNC, 256);                                // A p complete in Wsm
         TL(11);
+#ifdef OB200_TIMELINE_BUILD
+        ps_strips(pa0, pa1, hown[0], hown[1], mw, r0, Wsm, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf,
+                  (a.dbg && blockIdx.x == 0 && i == 2 && tid == 256) ? a.dbg + 4096 : nullptr);
+#else
         ps_strips(pa0, pa1, hown[0], hown[1], mw, r0, Wsm, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf);
+#endif
         nbar_sync(NB_MSYNC2, 256);                               // W complete in Wsm
         TL(12);
 #pragma unroll
@@ -392,38 +410,66 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     RedView rvw;
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
                              a.dbg ? s_stamp : nullptr)) { exit_reason = -2; break; }
+    TLB(0);
     {
       const u64 flag = rvw.load(ACC_FLAG_OFF);
       double c = 0.0;
       {
+        // G (fixed point) -> shared memory with one 16-byte load per entry, then sym(G) from shared memory
+        double *Graw = Wsm;                                     // 32 x 32 doubles of scratch (Wsm is idle here)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int e = tid + 512 * h;
-          const int i = e >> 5, jj = e & 31, et = jj * ST_P + i;
-          const double v1 = fix2_to_double((i64)rvw.load(ACC_GRAM_OFF + 2 * e), (i64)rvw.load(ACC_GRAM_OFF + 2 * e + 1), q);
-          const double v2 = fix2_to_double((i64)rvw.load(ACC_GRAM_OFF + 2 * et), (i64)rvw.load(ACC_GRAM_OFF + 2 * et + 1), q);
-          const double sg = 0.5 * (v1 + v2);
-          Gsm[i * WS + jj] = -sg;
+          u64 hi, lo;
+          if (rvw.world == 1) {
+            const ulonglong2 w = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + ACC_GRAM_OFF + 2 * e));
+            hi = w.x; lo = w.y;
+          } else {
+            hi = rvw.load(ACC_GRAM_OFF + 2 * e); lo = rvw.load(ACC_GRAM_OFF + 2 * e + 1);
+          }
+          Graw[e] = fix2_to_double((i64)hi, (i64)lo, q);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = tid + 512 * h;
+          const int i = e >> 5, jj = e & 31;
+          const double sg = 0.5 * (Graw[e] + Graw[jj * ST_P + i]);
+          Gsm[i * GS + jj] = -sg;
           c = fma(sg, sg, c);
         }
       }
+      TLB(10);
       finalize_scalars(rvw, sh, 0, 4);
+      TLB(11);
       c = warp_sum(c);
       if (lane == 0) s_part[warp] = c;
       __syncthreads();
+      TLB(12);
       if (flag != 0) { exit_reason = -3; break; }
-      if (tid == 0) {
+      if (warp == 0) {
+        // lanes 0..2 evaluate the long-latency operations concurrently, lane 0 takes the decisions
         double nG2 = 0.0;
 #pragma unroll
         for (int w = 0; w < 16; ++w) nG2 += s_part[w];
         const double nHp2 = fmax(sh.red[SC_HPHP] - nG2, 0.0);
-        decide_after_A(sh, sh.red[SC_PHP], nHp2, sh.red[SC_PP], sh.red[SC_PR], a.Delta, a.epsilon);
-        const double rb = sqrt(sh.rv) + fabs(sh.step) * sqrt(sh.red[SC_HPHP]);        // ||r + alpha Hp|| <= ...
-        s_fe[SC_RV] = fixacc_exponent(rb * rb);
+        double slow = 0.0;
+        if (lane == 0) slow = sqrt(nHp2);
+        else if (lane == 1) slow = sqrt(sh.red[SC_PP]);
+        else if (lane == 2) slow = __ddiv_rn(sh.rv, sh.red[SC_PHP]);                    // alpha, l.341
+        const double sq_nHp2 = __shfl_sync(0xffffffffu, slow, 0), sq_np2 = __shfl_sync(0xffffffffu, slow, 1);
+        const double alpha = __shfl_sync(0xffffffffu, slow, 2);
+        if (lane == 0) {
+          decide_after_A_pre(sh, sh.red[SC_PHP], sq_nHp2, sq_np2, alpha, sh.red[SC_PR], a.Delta, a.epsilon);
+          // ||r + alpha Hp||^2 <= 2 (||r||^2 + alpha^2 ||Hp||^2)
+          s_fe[SC_RV] = fixacc_exponent(2.0 * (sh.rv + sh.step * sh.step * sh.red[SC_HPHP]));
+        }
+        TLB(13);
       }
       __syncthreads();
     }
     ++phase;
+    TLB(1);
     const double step = sh.step;
     if (sh.action != ACT_CONTINUE) {
       const size_t e0 = (size_t)row_lo * ST_P, e1 = (size_t)row_hi * ST_P;
@@ -440,9 +486,11 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
 
     // ------------------------------ phase B ------------------------------
     set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
-    if (blockIdx.x == 0) {
+    {   // recycle the set used two phases from now (every CTA clears its slice; a grid barrier intervenes)
       u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
-      for (int i = tid; i < ACC_WORDS; i += blockDim.x) nxt[i] = 0;
+      const int per = (ACC_WORDS + gridDim.x - 1) / gridDim.x;
+      const int z0 = per * blockIdx.x;
+      for (int i = tid; i < per && z0 + i < ACC_WORDS; i += blockDim.x) nxt[z0 + i] = 0;
     }
     unsigned ovfb = 0;
     {
@@ -458,8 +506,10 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           prefetch_l2(a.Hp + noff); prefetch_l2(a.s + noff); prefetch_l2(p_new + noff);
           prefetch_l2(a.r + noff); prefetch_l2(st.Y + noff);
         }
+        if (sidx == s_hi - 1) TLB(2);
         double acc[4][2];
-        double2 sv[4], pv[4], rv[4];
+        double2 sv[4], pv[4], rv[4], yx[4];
+        strip_rightmul_load(valid ? st.Y + rowoff : nullptr, lane, yx);     // all 20 loads of the strip in flight
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int col = 8 * t + 2 * j;
@@ -474,7 +524,9 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
             sv[t] = pv[t] = rv[t] = make_double2(0.0, 0.0);
           }
         }
-        strip_rightmul(valid ? st.Y + rowoff : nullptr, Gsm, lane, acc);   // Hp = W - Y symG
+        if (sidx == s_hi - 1) TLB(3);
+        strip_rightmul_v(yx, Gsm, lane, acc);   // Hp = W - Y symG
+        if (sidx == s_hi - 1) TLB(4);
         double rr = 0.0;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -488,27 +540,33 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           }
         }
         fixacc_add(fb, rr, fqb, ovfb);      // exact-reduction unit: this lane's 8 elements of the strip
+        if (sidx == s_hi - 1) TLB(5);
       }
+      TLB(6);
       fixacc_flush(fb, sacc + SC_RV * KUL_STRIDE, feb);
       if (ovfb) atomicAdd(sacc + SC_RV * KUL_STRIDE + KUL_LIMBS, 1ull);   // non-finite / bound violated: poison <r,r>
     }
     __syncthreads();
+    TLB(7);
     flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
                              KUL_STRIDE, rvw, a.dbg ? s_stamp + 2 : nullptr)) { exit_reason = -2; break; }
+    TLB(8);
     finalize_scalars(rvw, sh, SC_RV, 1);
     __syncthreads();
     if (tid == 0) {
       update_after_B(sh, sh.red[SC_RV]);
-      const int e = gram_exponent(st.op_norm_bound * sqrt(sh.pk_M_2) * 4.0);
+      // bounds for the next iteration's exact accumulators (integer exponent arithmetic only)
+      const int e = half_exponent(st.op_norm_bound * st.op_norm_bound * sh.pk_M_2 * 16.0) + 2;   // |G_ij| <= ||H|| ||p||
       s_invq = scalbn(1.0, 90 - e);
       s_q = scalbn(1.0, e - 90);
       s_fe[SC_PHP] = fixacc_exponent(st.op_norm_bound * sh.pk_M_2);
       s_fe[SC_HPHP] = fixacc_exponent(st.op_norm_bound * st.op_norm_bound * sh.pk_M_2);
       s_fe[SC_PP] = fixacc_exponent(sh.pk_M_2);
-      s_fe[SC_PR] = fixacc_exponent(sqrt(sh.pk_M_2) * sqrt(sh.rv));
+      s_fe[SC_PR] = half_exponent(sh.pk_M_2 * sh.rv) + 2;                                        // |<p,r>| <= ||p|| ||r||
     }
     __syncthreads();
+    TLB(9);
     ++phase;
     if (a.dbg && tid == 0) {   // [work A, wait A, work B, wait B]; work = previous release -> arrival
       if (dbg_prev) atomicAdd(a.dbg + 4 * blockIdx.x + 0, s_stamp[0] - dbg_prev);
