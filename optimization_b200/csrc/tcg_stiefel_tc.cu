@@ -118,6 +118,26 @@ __device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (
   if (tl) tl[16] = globaltimer_ns();
 }
 
+// Phase B staging: the five 2 KB tiles (W, s, p, r, Y) of one 8-row strip are fetched with bulk
+// asynchronous copies (TMA 1-D) into this warp's 10 KB shared-memory slot, so the next strip streams in
+// while the current one is being processed.
+constexpr uint32_t STRIP_TILE = 8 * ST_P * sizeof(double);   // 2 KB
+constexpr uint32_t STRIP_SLOT = 5 * STRIP_TILE;              // 10 KB per warp
+__device__ __forceinline__ void strip_fetch(unsigned char *slot, uint64_t *bar, int sidx, unsigned n_rows,
+                                            const double *W, const double *S, const double *Pn, const double *R,
+                                            const double *Y) {
+  const unsigned row0 = (unsigned)sidx * 8u;
+  const unsigned rows = n_rows - row0 < 8u ? n_rows - row0 : 8u;
+  const uint32_t bytes = rows * ST_P * (uint32_t)sizeof(double);
+  const size_t off = (size_t)row0 * ST_P;
+  mbar_expect_tx(bar, 5 * bytes);
+  bulk_g2s(slot, W + off, bytes, bar);
+  bulk_g2s(slot + STRIP_TILE, S + off, bytes, bar);
+  bulk_g2s(slot + 2 * STRIP_TILE, Pn + off, bytes, bar);
+  bulk_g2s(slot + 3 * STRIP_TILE, R + off, bytes, bar);
+  bulk_g2s(slot + 4 * STRIP_TILE, Y + off, bytes, bar);
+}
+
 extern __shared__ __align__(16) unsigned char v3_smem_raw[];
 
 // debug timeline (CTA 0, third block of an iteration): slot <- globaltimer
@@ -137,6 +157,8 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   __shared__ double s_invq, s_q;
   __shared__ double s_lmax[16];
   __shared__ int s_E[4];
+  __shared__ int s_next_strip;
+  __shared__ __align__(8) uint64_t s_bmb[16];   // phase B: one mbarrier per warp (strip staging)
   __shared__ int s_fe[5];      // fixacc exponents: <p,W>, <W,W>, <p,p>, <p,r>, <r,r>
   __shared__ uint32_t s_tmem;
   __shared__ unsigned long long s_stamp[4];   // barrier arrival / release times (profiling aid)
@@ -165,6 +187,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     sh.k = 0;
     sh.action = ACT_CONTINUE;
     sh.status = 0;
+    s_next_strip = -1;     // set below once the partition is known
     const int e = gram_exponent(st.op_norm_bound * sqrt(a.rv0) * 4.0);
     s_invq = scalbn(1.0, 90 - e);
     s_q = scalbn(1.0, e - 90);
@@ -178,6 +201,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     mbar_init(&mb[MB_MMA_DONE + 1], 1);
     mbar_init(&mb[MB_ACC_EMPTY], 256);
     mbar_init(&mb[MB_ACC_EMPTY + 1], 256);
+    for (int w = 0; w < 16; ++w) mbar_init(&s_bmb[w], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&s_tmem, 512);
@@ -196,7 +220,13 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   const unsigned row_hi = (h1 * 64u < n_rows32) ? h1 * 64u : n_rows32;
   const unsigned bfirst = h0 >> 1;
   const int nb_local = (h1 > h0) ? (int)(((h1 - 1) >> 1) - bfirst + 1) : 0;
-  const int s_lo = (int)(row_lo >> 3), s_hi = (int)((row_hi + 7u) >> 3);
+  // phase B has its own, finer partition: 8-row strips split evenly over the CTAs and handed to the warps
+  // dynamically (results do not depend on who processes which strip: exact integer accumulation)
+  const unsigned nstrips = (n_rows32 + 7u) >> 3;
+  const int s_lo = (int)((unsigned long long)nstrips * blockIdx.x / gridDim.x);
+  const int s_hi = (int)((unsigned long long)nstrips * (blockIdx.x + 1ull) / gridDim.x);
+  if (tid == 0) s_next_strip = s_hi - 1;
+  unsigned bpar = 0;           // parity of this warp's phase-B mbarrier
   unsigned gen = 0, phase = 0;
   unsigned use = 0;            // blocks processed so far by this CTA (mbarrier phase bookkeeping)
   int exit_reason = -1;
@@ -411,12 +441,21 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
                              a.dbg ? s_stamp : nullptr)) { exit_reason = -2; break; }
     TLB(0);
+    // first strip of phase B for this warp: start streaming it in before the scalar stage
+    unsigned char *slot = base + warp * STRIP_SLOT;
+    int cur = 0;
+    if (lane == 0) cur = atomicSub(&s_next_strip, 1);      // top-down: lines touched last in phase A first
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    if (cur >= s_lo && lane == 0) {
+      fence_proxy_async_smem();
+      strip_fetch(slot, &s_bmb[warp], cur, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
+    }
     {
       const u64 flag = rvw.load(ACC_FLAG_OFF);
       double c = 0.0;
       {
         // G (fixed point) -> shared memory with one 16-byte load per entry, then sym(G) from shared memory
-        double *Graw = Wsm;                                     // 32 x 32 doubles of scratch (Wsm is idle here)
+        double *Graw = reinterpret_cast<double *>(base + 16 * STRIP_SLOT);   // 8 KB of scratch behind the strip slots
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int e = tid + 512 * h;
@@ -446,7 +485,11 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
       if (lane == 0) s_part[warp] = c;
       __syncthreads();
       TLB(12);
-      if (flag != 0) { exit_reason = -3; break; }
+      if (flag != 0) {
+        if (cur >= s_lo) mbar_wait(&s_bmb[warp], bpar);    // drain the outstanding fetch before leaving
+        exit_reason = -3;
+        break;
+      }
       if (warp == 0) {
         // lanes 0..2 evaluate the long-latency operations concurrently, lane 0 takes the decisions
         double nG2 = 0.0;
@@ -472,6 +515,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     TLB(1);
     const double step = sh.step;
     if (sh.action != ACT_CONTINUE) {
+      if (cur >= s_lo) mbar_wait(&s_bmb[warp], bpar);      // drain the outstanding fetch before leaving
       const size_t e0 = (size_t)row_lo * ST_P, e1 = (size_t)row_hi * ST_P;
       for (size_t e = e0 + 2 * (size_t)tid; e < e1; e += 2 * (size_t)blockDim.x) {
         double2 sv = ldcg2(a.s + e);
@@ -497,36 +541,47 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
       FixAcc fb = {0, 0};
       const int feb = s_fe[SC_RV];
       const double fqb = scalbn(1.0, 90 - feb);
-      for (int sidx = s_hi - 1 - warp; sidx >= s_lo; sidx -= 16) {
+      while (cur >= s_lo) {
+        const int sidx = cur;
+        int nxt = 0;
+        if (lane == 0) nxt = atomicSub(&s_next_strip, 1);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
         const unsigned grow = (unsigned)sidx * 8u + m;
         const bool valid = grow < n_rows32;
         const size_t rowoff = (size_t)grow * ST_P;
-        if (sidx - 16 >= s_lo && lane < 16) {   // this warp's next strip -> L2 (5 x 2 KB)
-          const size_t noff = (size_t)(sidx - 16) * 8 * ST_P + 16 * lane;
-          prefetch_l2(a.Hp + noff); prefetch_l2(a.s + noff); prefetch_l2(p_new + noff);
-          prefetch_l2(a.r + noff); prefetch_l2(st.Y + noff);
-        }
-        if (sidx == s_hi - 1) TLB(2);
+        mbar_wait(&s_bmb[warp], bpar);
+        bpar ^= 1;
         double acc[4][2];
         double2 sv[4], pv[4], rv[4], yx[4];
-        strip_rightmul_load(valid ? st.Y + rowoff : nullptr, lane, yx);     // all 20 loads of the strip in flight
+        {
+          const double *tW = reinterpret_cast<const double *>(slot) + m * ST_P;
+          const double *tS = tW + 8 * ST_P, *tP = tS + 8 * ST_P, *tR = tP + 8 * ST_P, *tY = tR + 8 * ST_P;
+          unsigned tok = 0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int col = 8 * t + 2 * j;
-          if (valid) {
-            const double2 w = ldcg2(a.Hp + rowoff + col);
-            acc[t][0] = w.x; acc[t][1] = w.y;
-            sv[t] = ldcg2(a.s + rowoff + col);
-            pv[t] = ldcg2(p_new + rowoff + col);
-            rv[t] = ldcg2(a.r + rowoff + col);
-          } else {
-            acc[t][0] = acc[t][1] = 0.0;
-            sv[t] = pv[t] = rv[t] = make_double2(0.0, 0.0);
+          for (int t = 0; t < 4; ++t) {
+            const int col = 8 * t + 2 * j;
+            if (valid) {
+              const double2 w = *reinterpret_cast<const double2 *>(tW + col);
+              acc[t][0] = w.x; acc[t][1] = w.y;
+              sv[t] = *reinterpret_cast<const double2 *>(tS + col);
+              pv[t] = *reinterpret_cast<const double2 *>(tP + col);
+              rv[t] = *reinterpret_cast<const double2 *>(tR + col);
+              yx[t] = *reinterpret_cast<const double2 *>(tY + 8 * j + 2 * t);
+            } else {
+              acc[t][0] = acc[t][1] = 0.0;
+              sv[t] = pv[t] = rv[t] = yx[t] = make_double2(0.0, 0.0);
+            }
+            tok |= __double2hiint(acc[t][0]) | __double2hiint(sv[t].x) | __double2hiint(pv[t].x) |
+                   __double2hiint(rv[t].x) | __double2hiint(yx[t].x);
+          }
+          // every lane's shared-memory reads have returned (tok depends on all of them): the slot may be refilled
+          tok = __reduce_or_sync(0xffffffffu, tok);
+          if (nxt >= s_lo && lane == 0 && (tok | 1u)) {
+            fence_proxy_async_smem();
+            strip_fetch(slot, &s_bmb[warp], nxt, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
           }
         }
-        if (sidx == s_hi - 1) TLB(3);
         strip_rightmul_v(yx, Gsm, lane, acc);   // Hp = W - Y symG
-        if (sidx == s_hi - 1) TLB(4);
         double rr = 0.0;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -540,7 +595,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           }
         }
         fixacc_add(fb, rr, fqb, ovfb);      // exact-reduction unit: this lane's 8 elements of the strip
-        if (sidx == s_hi - 1) TLB(5);
+        cur = nxt;
       }
       TLB(6);
       fixacc_flush(fb, sacc + SC_RV * KUL_STRIDE, feb);
@@ -548,6 +603,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     }
     __syncthreads();
     TLB(7);
+    if (tid == 0) s_next_strip = s_hi - 1;
     flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
                              KUL_STRIDE, rvw, a.dbg ? s_stamp + 2 : nullptr)) { exit_reason = -2; break; }
