@@ -403,11 +403,24 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
   const size_t slot_off = (size_t)(slot * MAX_RANKS) * cm.words_per_set;
   if (s_last) {   // CTA-uniform: this CTA completed the local reduction -> publish it to every rank
     __threadfence();
+    // (all loads first: one L2 round trip, then the peer stores stream out back to back)
+    constexpr int PUB_MAX = 8;                       // count <= PUB_MAX * blockDim.x (2632 words, >= 384 threads)
+    u64 wv[PUB_MAX];
+#pragma unroll
+    for (int k = 0; k < PUB_MAX; ++k) {
+      const int i = threadIdx.x + k * blockDim.x;
+      wv[k] = (i < count) ? __ldcg(set + off + i) : 0ull;
+    }
     for (int r = 0; r < cm.world; ++r) {
       u64 *dst = cm.inbox[r] + slot_off + (size_t)cm.rank * cm.words_per_set + off;
-      for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldcg(set + off + i);
+#pragma unroll
+      for (int k = 0; k < PUB_MAX; ++k) {
+        const int i = threadIdx.x + k * blockDim.x;
+        if (i < count) dst[i] = wv[k];
+      }
     }
-    __threadfence_system();
+    // the CTA barrier orders every thread's (weak) peer stores before the flag writers; their
+    // st.release.sys then publishes them at system scope (one fence per destination, not per thread)
     __syncthreads();
     if ((int)threadIdx.x < cm.world)
       st_release_sys_u64(cm.flags[threadIdx.x] + slot * MAX_RANKS + cm.rank, gphase + 1ull);
@@ -419,9 +432,7 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
       if (++spins > (1u << 24)) {
         if (*((volatile int *)abort_flag) || spins > (1u << 25)) { atomicExch(abort_flag, 1); break; }
       }
-      if (spins > 256) __nanosleep(32);
     }
-    __threadfence();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
