@@ -13,7 +13,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboptimization_b200.so")
+# OB200_LIB: developer override (profiling builds of the same library, tools/ only)
+LIB_PATH = os.environ.get("OB200_LIB") or os.path.join(_HERE, "liboptimization_b200.so")
 
 OK, INVALID_ARGUMENT, CUDA_ERROR, UNSUPPORTED, NUMERIC_RANGE, ABORTED = range(6)
 EXIT_RESIDUAL, EXIT_MAX_ITERATIONS, EXIT_KERNEL, EXIT_BOUNDARY = range(4)

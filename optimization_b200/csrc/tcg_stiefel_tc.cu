@@ -1,18 +1,19 @@
-// Persistent fused truncated-CG for the Stiefel trace-minimisation Hessian, v3:
+// Persistent fused truncated-CG for the Stiefel trace-minimisation Hessian, v4:
 // the block contraction A * p runs on the 5th-generation tensor cores (tcgen05,
-// accumulators in TMEM) through the exact bf16 digit-plane scheme of tc_common.cuh;
+// accumulators in TMEM) through the exact int8 digit-plane scheme of tc_common.cuh;
 // the small fp64 x fp64 products (p S, the projection Gram Y^T W, Y symG) stay on
 // the fp64 tensor cores.  Same iteration structure, reductions and scalar logic as
 // tcg_stiefel_kernel (see tcg_stiefel.cu / tcg.cuh for the reference line map).
 //
-// 17 warps.  Phase A roles per 128-row block:
-//   L (warps 0-7)  : stream r, p_old -> p (written back), block maximum, digit slicing of
-//                    p into shared memory (UMMA operand image), then Y -> shared memory
-//   X (warp 16)    : one thread: bulk-copies (TMA 1-D) the precomputed A digit planes and
-//                    issues the 112 tcgen05.mma of the block; double-buffered TMEM accumulators
-//   M (warps 8-15) : TMEM -> registers, fp64 recombination, W -= p S, W written back,
-//                    projection Gram, exact accumulation of all partial sums
-// hand-offs through mbarriers (TMA / UMMA completion) and named barriers.
+// 16 warps.  Phase A is a software pipeline over the CTA's 128-row blocks with two
+// balanced roles (about 5 us per block each, measured):
+//   L (warps 0-7)  : block u : stream r, p_old -> p (written back), block maximum, digit
+//                    slicing of p into the UMMA operand image; thread 0 bulk-copies (TMA 1-D)
+//                    the precomputed A digit planes and issues the 13 tcgen05.mma of the block;
+//                    block u-1 : TMEM -> registers, integer recombination, Z = A p -> Wsm[u-1 & 1]
+//   M (warps 8-15) : block u : W = Z - p S (fp64 MMA), W written back, <p,W>, <W,W>,
+//                    projection Gram Y^T W, exact accumulation of all partial sums
+// hand-offs through mbarriers only (TMA / UMMA completion, Z full, W buffer empty).
 #include "tcg.cuh"
 #include "stiefel_dev.cuh"
 #include "tc_common.cuh"
@@ -22,9 +23,10 @@ using namespace tc;
 
 constexpr int V3_THREADS = 512;
 constexpr size_t V3_A = 0;                                   // 48 KB int8 digit planes of A (1024-aligned)
-constexpr size_t V3_Q = V3_A + TC_ABLOCK;                    // 2 x 28 KB int8 digit images of p (double buffered)
-constexpr size_t V3_W = V3_Q + 2 * TC_QBYTES;                // 128 x 36 doubles
-constexpr size_t V3_Y = V3_W + sizeof(double) * ST_NB * WS;
+constexpr size_t V3_Q = V3_A + TC_ABLOCK;                    // 28 KB int8 digit image of p
+constexpr size_t V3_WBUF = sizeof(double) * ST_NB * WS;      // 128 x 36 doubles
+constexpr size_t V3_W = V3_Q + TC_QBYTES;                    // two W tiles (L fills one while M works on the other)
+constexpr size_t V3_Y = V3_W + 2 * V3_WBUF;
 constexpr size_t V3_S = V3_Y + sizeof(double) * ST_NB * WS;
 constexpr size_t V3_G = V3_S + sizeof(double) * ST_P * WS;
 constexpr size_t V3_ACC = V3_G + sizeof(double) * ST_P * WS;
@@ -32,8 +34,11 @@ constexpr size_t V3_BAR = V3_ACC + sizeof(u64) * ACC_NSCAL * KUL_STRIDE;
 constexpr size_t V3_TOTAL = V3_BAR + 256 + 1024;             // + alignment slack
 
 // mbarrier slots
-enum { MB_A_FULL = 0, MB_Q_FULL = 1, MB_MMA_DONE = 4 /*,5*/, MB_ACC_EMPTY = 6 /*,7*/ };
+enum { MB_A_FULL = 0, MB_Q_FULL = 1, MB_MMA_DONE = 2 /*,3*/, MB_Z_FULL = 4 /*,5*/, MB_W_EMPTY = 6 /*,7*/ };
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void *g, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Two 8x8 tiles (mt, nt0) and (mt, nt0 + 1) of Y^T W over one 64-row half block; the Y
@@ -57,6 +62,31 @@ __device__ __forceinline__ void gram_pair_half(const double *Yg /* row 0 of the 
       dmma884(g[1][0], g[1][1], av[q], Zsm[krow * WS + 8 * (nt0 + 1) + m]);
     }
   }
+}
+
+// Both tiles (mt, nt0), (mt, nt0 + 1) of Y^T W over one whole 128-row block: four independent
+// accumulator chains per tile over k (8 steps each; the fp64 MMA has a long dependent-issue latency),
+// added in a fixed order.  The block is the exact-reduction unit of the Gram.
+__device__ __forceinline__ void gram_pair_block(const double *Xsm, const double *Zsm, int mt, int nt0, int lane,
+                                                double &g00, double &g01, double &g10, double &g11) {
+  const int m = lane >> 2, j = lane & 3;
+  double a0[4][2], a1[4][2];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { a0[s][0] = a0[s][1] = a1[s][0] = a1[s][1] = 0.0; }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int krow = 4 * (8 * s + q) + j;
+      const double x = Xsm[krow * WS + 8 * mt + m];
+      dmma884(a0[s][0], a0[s][1], x, Zsm[krow * WS + 8 * nt0 + m]);
+      dmma884(a1[s][0], a1[s][1], x, Zsm[krow * WS + 8 * (nt0 + 1) + m]);
+    }
+  }
+  g00 = (a0[0][0] + a0[1][0]) + (a0[2][0] + a0[3][0]);
+  g01 = (a0[0][1] + a0[1][1]) + (a0[2][1] + a0[3][1]);
+  g10 = (a1[0][0] + a1[1][0]) + (a1[2][0] + a1[3][0]);
+  g11 = (a1[0][1] + a1[1][1]) + (a1[2][1] + a1[3][1]);
 }
 
 // Two 8-row strips (rows 8*mw.. and 64+8*mw.. of the block) of W = (A p) - p S on the fp64 tensor
@@ -123,6 +153,7 @@ __device__ __forceinline__ void ps_strips(const double (&pa0)[8], const double (
 // while the current one is being processed.
 constexpr uint32_t STRIP_TILE = 8 * ST_P * sizeof(double);   // 2 KB
 constexpr uint32_t STRIP_SLOT = 5 * STRIP_TILE;              // 10 KB per warp
+static_assert(16 * STRIP_SLOT + 8192 <= V3_S, "phase-B staging must not overlap S / G / the CTA accumulators");
 __device__ __forceinline__ void strip_fetch(unsigned char *slot, uint64_t *bar, int sidx, unsigned n_rows,
                                             const double *W, const double *S, const double *Pn, const double *R,
                                             const double *Y) {
@@ -156,7 +187,6 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   __shared__ double s_part[16];
   __shared__ double s_invq, s_q;
   __shared__ double s_lmax[16];
-  __shared__ int s_E[4];
   __shared__ int s_next_strip;
   __shared__ __align__(8) uint64_t s_bmb[16];   // phase B: one mbarrier per warp (strip staging)
   __shared__ int s_fe[5];      // fixacc exponents: <p,W>, <W,W>, <p,p>, <p,r>, <r,r>
@@ -199,8 +229,10 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     mbar_init(&mb[MB_Q_FULL], 256);
     mbar_init(&mb[MB_MMA_DONE], 1);
     mbar_init(&mb[MB_MMA_DONE + 1], 1);
-    mbar_init(&mb[MB_ACC_EMPTY], 256);
-    mbar_init(&mb[MB_ACC_EMPTY + 1], 256);
+    mbar_init(&mb[MB_Z_FULL], 256);
+    mbar_init(&mb[MB_Z_FULL + 1], 256);
+    mbar_init(&mb[MB_W_EMPTY], 256);
+    mbar_init(&mb[MB_W_EMPTY + 1], 256);
     for (int w = 0; w < 16; ++w) mbar_init(&s_bmb[w], 1);
     fence_mbar_init();
   }
@@ -210,16 +242,15 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  // ownership: 64-row half blocks [h0, h1)
+  // ownership: whole 128-row operator blocks [bfirst, bfirst + nb_local)
   // (32-bit row bookkeeping: local row counts stay below 2^31)
   const unsigned n_rows32 = (unsigned)st.n_rows;
-  const unsigned nhalf = (n_rows32 + 63u) / 64u;
-  const unsigned h0 = (unsigned)((unsigned long long)nhalf * blockIdx.x / gridDim.x);
-  const unsigned h1 = (unsigned)((unsigned long long)nhalf * (blockIdx.x + 1ull) / gridDim.x);
-  const unsigned row_lo = h0 * 64u;
-  const unsigned row_hi = (h1 * 64u < n_rows32) ? h1 * 64u : n_rows32;
-  const unsigned bfirst = h0 >> 1;
-  const int nb_local = (h1 > h0) ? (int)(((h1 - 1) >> 1) - bfirst + 1) : 0;
+  const unsigned nblk = (n_rows32 + ST_NB - 1u) / ST_NB;
+  const unsigned bfirst = (unsigned)((unsigned long long)nblk * blockIdx.x / gridDim.x);
+  const unsigned bend = (unsigned)((unsigned long long)nblk * (blockIdx.x + 1ull) / gridDim.x);
+  const int nb_local = (int)(bend - bfirst);
+  const unsigned row_lo = bfirst * ST_NB;
+  const unsigned row_hi = (bend * ST_NB < n_rows32) ? bend * ST_NB : n_rows32;
   // phase B has its own, finer partition: 8-row strips split evenly over the CTAs and handed to the warps
   // dynamically (results do not depend on who processes which strip: exact integer accumulation)
   const unsigned nstrips = (n_rows32 + 7u) >> 3;
@@ -254,30 +285,39 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     }
     unsigned ovf = 0;
     if (is_L) {
-      // ===== loader warps (thread 0 also drives the TMA copies and issues the MMAs) =====
+      // ===== L warps: block u -> p, digit image, MMAs ; block u-1 -> TMEM read-back =====
       const int cp = tid & 15, g = tid >> 4;           // columns 2cp, 2cp+1 ; rows 8g .. 8g+7 of the block
-      for (int i = 0; i < nb_local; ++i) {
+      const int q4 = warp & 3, chalf = warp >> 2;      // read-back: TMEM lane quarter, column half
+      int E_prev = 0;
+      for (int i = 0; i <= nb_local; ++i) {
         const unsigned u = use + i;
-        const unsigned b = bfirst + i, r0 = b * ST_NB;
-        TL(0);
-        if (i + 1 < nb_local) {   // next block's r, p_old, Y -> L2 (3 x 32 KB = 768 lines)
-          const size_t noff = (size_t)(r0 + ST_NB) * ST_P + 16 * (size_t)tid;
-          if (r0 + ST_NB + (tid >> 1) < n_rows32) {
-            prefetch_l2(a.r + noff);
-            prefetch_l2(st.Y + noff);
-            if (k) prefetch_l2(p_old + noff);
+        int E_cur = 0;
+        if (i < nb_local) {
+          const unsigned b = bfirst + i, r0 = b * ST_NB;
+          TL(0);
+#ifndef OB200_PFDIST
+#define OB200_PFDIST 1
+#endif
+          // the block OB200_PFDIST ahead: r, p_old, Y and the A digit planes -> L2 through the TMA unit (bulk
+          // prefetches are queued by the copy engine, not dropped under load like per-thread prefetch hints)
+          if (OB200_PFDIST > 0 && tid == 32 && i + OB200_PFDIST < nb_local) {
+            const unsigned rn = r0 + OB200_PFDIST * ST_NB;
+            const unsigned rows = n_rows32 - rn < ST_NB ? n_rows32 - rn : ST_NB;
+            const uint32_t bytes = rows * ST_P * (uint32_t)sizeof(double);
+            const size_t noff = (size_t)rn * ST_P;
+            bulk_prefetch_l2(a.r + noff, bytes);
+            if (k) bulk_prefetch_l2(p_old + noff, bytes);
+            bulk_prefetch_l2(planes + (size_t)(b + OB200_PFDIST) * TC_ABLOCK, TC_ABLOCK);
+            bulk_prefetch_l2(st.Y + noff, bytes);
           }
-        }
-        const unsigned hh = 2u * b + (g >> 3);      // this thread's half block
-        const bool own = hh >= h0 && hh < h1;
-        double p[8][2];
-        double pp = 0.0, pr = 0.0, mx = 0.0;
+          if (i == 0 && tid == 0) {   // every MMA of the previous phase has completed: the A image is free
+            mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
+            bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+          }
+          double2 rv[8], po[8];
 #pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-          double2 rv[4], po[4];
-#pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            const unsigned grow = r0 + 8 * g + 4 * hrow + ii;
+          for (int ii = 0; ii < 8; ++ii) {      // all 16 loads of this thread in flight at once
+            const unsigned grow = r0 + 8 * g + ii;
             rv[ii] = po[ii] = make_double2(0.0, 0.0);
             if (grow < n_rows32) {
               const size_t off = (size_t)grow * ST_P + 2 * cp;
@@ -285,9 +325,11 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
               if (k) po[ii] = ldcg2(p_old + off);
             }
           }
+          double p[8][2];
+          double pp = 0.0, pr = 0.0, mx = 0.0;
 #pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            const unsigned grow = r0 + 8 * g + 4 * hrow + ii;
+          for (int ii = 0; ii < 8; ++ii) {
+            const unsigned grow = r0 + 8 * g + ii;
             double2 pv;
             if (k) {
               pv.x = fma(beta, po[ii].x, -rv[ii].x);        // l.420
@@ -296,65 +338,84 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
               pv.x = -rv[ii].x;                             // l.256
               pv.y = -rv[ii].y;
             }
-            if (own && grow < n_rows32) {
+            if (grow < n_rows32) {
               stcg2(p_new + (size_t)grow * ST_P + 2 * cp, pv);
               pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
               pr = fma(pv.x, rv[ii].x, pr); pr = fma(pv.y, rv[ii].y, pr);
             }
-            p[4 * hrow + ii][0] = pv.x;
-            p[4 * hrow + ii][1] = pv.y;
+            p[ii][0] = pv.x;
+            p[ii][1] = pv.y;
             mx = fmax(mx, fmax(fabs(pv.x), fabs(pv.y)));
           }
-        }
-        TL(1);
-        // exact-reduction unit: this lane's 8 x 2 elements (all inside one half block)
-        if (own) {
+          TL(1);
+          // next block's r, p_old, Y and A digit planes -> L2, issued AFTER this block's demand loads have
+          // returned: the fetch then runs during the slicing / MMA / read-back instead of competing with them
+          // exact-reduction unit: this lane's 8 x 2 elements
           fixacc_add(fa0, pp, fq0, ovf);
           fixacc_add(fa1, pr, fq1, ovf);
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) s_lmax[(u & 1) * 8 + warp] = mx;
-        nbar_sync(NB_LSYNC, 256);
-        mx = s_lmax[(u & 1) * 8];
+          for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0) s_lmax[(u & 1) * 8 + warp] = mx;
+          nbar_sync(NB_LSYNC, 256);
+          mx = s_lmax[(u & 1) * 8];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) mx = fmax(mx, s_lmax[(u & 1) * 8 + w]);
-        // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
-        const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
-        TL(2);
-        if (u >= 2) mbar_wait(&mb[MB_MMA_DONE + (u & 1)], ((u - 2) >> 1) & 1);   // digit image (u & 1) free
-        TL(3);
-        if (tid == 0) {
-          s_E[u & 3] = E;
-          if (i == 0) {   // first block of the phase: every earlier MMA has completed; later blocks: see M
-            mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
-            bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+          for (int w = 1; w < 8; ++w) mx = fmax(mx, s_lmax[(u & 1) * 8 + w]);
+          // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
+          const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
+          E_cur = E;
+          TL(2);
+          if (i > 0) {   // MMAs of block u-1 complete: digit image and A image are free again
+            mbar_wait(&mb[MB_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);
+            if (tid == 0) {
+              mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
+              bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
+            }
           }
+          TL(3);
+          slice_tile_to_smem(p, scalbn(1.0, 54 - E), Qsm, tid);
+          fence_proxy_async_smem();
+          mbar_arrive(&mb[MB_Q_FULL]);
+          TL(4);
+          if (tid == 0) {
+            // every L thread has sliced block u -- and, earlier in program order, drained the TMEM
+            // accumulators (u & 1) of block u-2
+            mbar_wait(&mb[MB_Q_FULL], u & 1);
+            TL(6);
+            mbar_wait(&mb[MB_A_FULL], u & 1);
+            TL(7);
+            tc_fence_after();
+            issue_block_mmas(smem_u32(Asm), smem_u32(Qsm), tmem_base + (u & 1) * TC_TMEM_COLS);
+            umma_commit(&mb[MB_MMA_DONE + (u & 1)]);
+            TL(8);
+          }
+          __syncwarp();
         }
-        slice_tile_to_smem(p, scalbn(1.0, 54 - E), Qsm + (u & 1) * TC_QBYTES, tid);
-        fence_proxy_async_smem();
-        mbar_arrive(&mb[MB_Q_FULL]);
-        TL(4);
-        if (tid == 0) {
-          if (u >= 2) mbar_wait(&mb[MB_ACC_EMPTY + (u & 1)], ((u >> 1) - 1) & 1);         // accumulators drained
-          mbar_wait(&mb[MB_Q_FULL], u & 1);
-          TL(6);
-          mbar_wait(&mb[MB_A_FULL], u & 1);
-          TL(7);
+        if (i > 0) {
+          // read back block v = u-1: Z = A p -> Wsm[v & 1]
+          const unsigned v = u - 1;
+          if (i == nb_local) mbar_wait(&mb[MB_MMA_DONE + (v & 1)], (v >> 1) & 1);
           tc_fence_after();
-          issue_block_mmas(smem_u32(Asm), smem_u32(Qsm + (u & 1) * TC_QBYTES), tmem_base + (u & 1) * TC_TMEM_COLS);
-          umma_commit(&mb[MB_MMA_DONE + (u & 1)]);
-          TL(8);
+          if (v >= 2) mbar_wait(&mb[MB_W_EMPTY + (v & 1)], ((v >> 1) - 1) & 1);    // M is done with this tile
+          double out[16];
+          recombine_row16(tmem_base + (v & 1) * TC_TMEM_COLS + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
+          tc_fence_before();
+          const double sc = scalbn(1.0, __ldg(plane_exp + bfirst + i - 1) + E_prev + 10);
+          double *wrow = Wsm + (v & 1) * (ST_NB * WS) + (32 * q4 + lane) * WS + 16 * chalf;
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(wrow + c) = make_double2(out[c] * sc, out[c + 1] * sc);
+          mbar_arrive(&mb[MB_Z_FULL + (v & 1)]);
+          TL(5);
         }
-        __syncwarp();
+        E_prev = E_cur;
       }
     } else {
-      // ===== math warps =====
-      const int q4 = warp & 3, chalf = mw >> 2;
+      // ===== M warps =====
       i64 gfix[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
       for (int i = 0; i < nb_local; ++i) {
         const unsigned u = use + i;
         const unsigned b = bfirst + i, r0 = b * ST_NB;
+        double *Wb = Wsm + (u & 1) * (ST_NB * WS);
+        TL(9);
         {   // Y of this block -> shared memory (free since the Gram of the previous block: NB_MSYNC3)
           const int mt_ = tid - 256, cpy = mt_ & 15, gy = mt_ >> 4;
           double2 yv[8];
@@ -366,66 +427,36 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) *reinterpret_cast<double2 *>(Ysm + (8 * gy + ii) * WS + 2 * cpy) = yv[ii];
         }
-        TL(9);
-        mbar_wait(&mb[MB_MMA_DONE + (u & 1)], (u >> 1) & 1);
+        mbar_wait(&mb[MB_Z_FULL + (u & 1)], (u >> 1) & 1);
         TL(10);
-        if (tid == 256 && i + 1 < nb_local) {   // the A image is free again: fetch the next block's digit planes
-          mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
-          bulk_g2s(Asm, planes + (size_t)(b + 1) * TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
-        }
-        tc_fence_after();
-        const int E = *((volatile int *)&s_E[u & 3]);              // written by L before the digits of block u
-        // p rows of this warp's strips as DMMA A fragments (from L2; p_new of block u was written by L before
-        // its digits); half 0 is in flight during the TMEM read-back, half 1 during the first p S product
-        bool hown[2];
+        // p rows of this warp's strips as DMMA A fragments (from L2: every L thread stored p of block u
+        // before its Z_FULL arrival)
         double pa0[8], pa1[8];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const unsigned hh = 2u * b + half;
-          hown[half] = hh >= h0 && hh < h1;
-        }
         {
-          const unsigned grow = r0 + 8 * mw + m;
-          const bool ld = hown[0] && grow < n_rows32;
+          const unsigned g0 = r0 + 8 * mw + m, g1 = g0 + 64;
+          const bool l0 = g0 < n_rows32, l1 = g1 < n_rows32;
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq) pa0[qq] = ld ? __ldcg(p_new + (size_t)grow * ST_P + 4 * qq + j) : 0.0;
-        }
-        {
-          double out[16];
-          recombine_row16(tmem_base + (u & 1) * TC_TMEM_COLS + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
-          tc_fence_before();
-          mbar_arrive(&mb[MB_ACC_EMPTY + (u & 1)]);
-          const double sc = scalbn(1.0, __ldg(plane_exp + b) + E + 10);
-          double *wrow = Wsm + (32 * q4 + lane) * WS + 16 * chalf;
-#pragma unroll
-          for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(wrow + c) = make_double2(out[c] * sc, out[c + 1] * sc);
-        }
-        {
-          const unsigned grow = r0 + 8 * (8 + mw) + m;
-          const bool ld = hown[1] && grow < n_rows32;
-#pragma unroll
-          for (int qq = 0; qq < 8; ++qq) pa1[qq] = ld ? __ldcg(p_new + (size_t)grow * ST_P + 4 * qq + j) : 0.0;
-        }
-        nbar_sync(NB_MSYNC, 256);                                // A p complete in Wsm
-        TL(11);
-#ifdef OB200_TIMELINE_BUILD
-        ps_strips(pa0, pa1, hown[0], hown[1], mw, r0, Wsm, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf,
-                  (a.dbg && blockIdx.x == 0 && i == 2 && tid == 256) ? a.dbg + 4096 : nullptr);
-#else
-        ps_strips(pa0, pa1, hown[0], hown[1], mw, r0, Wsm, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf);
-#endif
-        nbar_sync(NB_MSYNC2, 256);                               // W complete in Wsm
-        TL(12);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (hown[half]) {
-            double g00, g01, g10, g11;
-            gram_pair_half_split(Ysm + half * 64 * WS, Wsm + half * 64 * WS, mw >> 1, 2 * (mw & 1), lane, g00, g01, g10, g11);
-            gram_accumulate(g00, g01, inv_q, gfix[0], &ovf);
-            gram_accumulate(g10, g11, inv_q, gfix[1], &ovf);
+          for (int qq = 0; qq < 8; ++qq) {
+            pa0[qq] = l0 ? __ldcg(p_new + (size_t)g0 * ST_P + 4 * qq + j) : 0.0;
+            pa1[qq] = l1 ? __ldcg(p_new + (size_t)g1 * ST_P + 4 * qq + j) : 0.0;
           }
         }
-        nbar_sync(NB_MSYNC3, 256);                               // Wsm free for the next block
+#ifdef OB200_TIMELINE_BUILD
+        ps_strips(pa0, pa1, true, true, mw, r0, Wb, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf,
+                  (a.dbg && blockIdx.x == 0 && i == 2 && tid == 256) ? a.dbg + 4096 : nullptr);
+#else
+        ps_strips(pa0, pa1, true, true, mw, r0, Wb, Ssm, a.Hp, n_rows32, lane, fa0, fa1, fq0, fq1, ovf);
+#endif
+        nbar_sync(NB_MSYNC2, 256);                               // W complete in Wb, Y complete in Ysm
+        TL(12);
+        {
+          double g00, g01, g10, g11;
+          gram_pair_block(Ysm, Wb, mw >> 1, 2 * (mw & 1), lane, g00, g01, g10, g11);
+          gram_accumulate(g00, g01, inv_q, gfix[0], &ovf);
+          gram_accumulate(g10, g11, inv_q, gfix[1], &ovf);
+        }
+        mbar_arrive(&mb[MB_W_EMPTY + (u & 1)]);                  // L may refill this W tile
+        nbar_sync(NB_MSYNC3, 256);                               // Ysm free for the next block
         TL(13);
       }
       gram_flush(set, 2 * mw, lane, gfix[0], ovf);
