@@ -88,8 +88,8 @@ int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A_bf
 #define OB200_OP_DIAG 1             /* H v = d .* v                                   */
 #define OB200_OP_STIEFEL_BLOCKDIAG 2 /* H V = P_Y(A V - V S), P_Y(Z) = Z - Y sym(Y^T Z),
                                         A block-diagonal dense (bf16 storage), p == 32  */
-#define OB200_OP_SPHERE_LOWRANK 3   /* H v = 2 P_x(A v) - 2 (x^T A x) v,
-                                        A = diag(d) + U diag(sigma) U^T               */
+#define OB200_OP_SPHERE_LOWRANK 3   /* H v = 2 P_x(A v) - 2 (x^T A x) v, P_x(z) = z - x (x^T z),
+                                        A = diag(d) + U diag(sigma) U^T, k <= 16, p == 1 */
 
 typedef struct {
   int kind;
@@ -103,11 +103,13 @@ typedef struct {
   const double *S_host;       /* p x p, sym(Y^T A Y) (host memory; see ob200_stiefel_model) */
   double op_norm_bound;       /* >= ||A||_2 + ||S||_2 (ob200_stiefel_model returns one) */
   /* OB200_OP_SPHERE_LOWRANK */
-  const double *x_dev;     /* n, unit vector */
-  const double *U_dev;     /* n x k row-major */
+  const double *x_dev;     /* n, unit vector (base point) */
+  const double *U_dev;     /* U TRANSPOSED: k rows of ldu doubles (row j = column j of U), 16-byte aligned */
   const double *sigma_host; /* k */
   uint64_t k;
-  double xAx;
+  double xAx;              /* x^T A x   (ob200_sphere_model returns it) */
+  const double *Ax_dev;    /* n, A x    (ob200_sphere_model fills it)   */
+  uint64_t ldu;            /* row stride of U_dev in doubles: even and >= n; 0 means n (n must then be even) */
 } ob200_operator;
 
 /* Replaces the optional preconditioner functor (reference
@@ -161,7 +163,9 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v_dev, 
 
 /* Algorithmic HBM bytes of ONE fused tCG step / one stand-alone HVP for this
  * operator (the roofline numerator; definition in DESIGN.md section 4):
- *   step = 10 N e + B_op (+ 2 N e with Jacobi),  hvp = 2 N e + B_op,  e = 8. */
+ *   step = 10 N e + B_op (+ 2 N e with Jacobi),  hvp = 2 N e + B_op,  e = 8;
+ *   B_op: DIAG N e; STIEFEL_BLOCKDIAG 2 N e (Y twice) + 2 bytes per stored entry of A;
+ *   SPHERE_LOWRANK (2k + 4) N e (U twice, d, x, A x, p re-read by the second pass). */
 uint64_t ob200_stpcg_step_bytes(const ob200_operator *H, const ob200_precon *P);
 uint64_t ob200_hvp_bytes(const ob200_operator *H);
 
@@ -194,6 +198,18 @@ int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16
 /* Cholesky-QR retraction  out = qf(Y + V) */
 int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y_dev,
                           const double *V_dev, double *out_dev);
+
+/* ---- Rayleigh quotient on the sphere, f(x) = x^T A x, A = diag(d) + U diag(sigma) U^T ----
+ * Replace the Objective / QuadraticModel / Retraction functors of the sphere model
+ * (reference call sites TNT.h:377,380,505,508,573; the model of BASELINE configs C1 / C2,
+ * shaped after examples/Riemannian_optimization_example.cpp).
+ * Ax_dev <- A x (n doubles, also the `Ax_dev` field of the Hessian descriptor), *xAx <- f(x),
+ * optional grad_dev <- 2 (A x - (x^T A x) x). */
+int ob200_sphere_model(ob200_context *ctx, uint64_t n, uint64_t k, const double *d_dev, const double *Ut_dev,
+                       uint64_t ldu, const double *sigma_host, const double *x_dev, double *Ax_dev, double *xAx,
+                       double *grad_dev);
+/* projection retraction  out = (x + v) / ||x + v||   (out may alias v) */
+int ob200_sphere_retract(ob200_context *ctx, uint64_t n, const double *x_dev, const double *v_dev, double *out_dev);
 
 /* ---- device memory helpers (so non-CUDA hosts can stage data) -------------- */
 int ob200_malloc(ob200_context *ctx, size_t bytes, void **ptr_dev);

@@ -38,6 +38,15 @@ size_t stiefel_planes_bytes(unsigned long long nblk);
 cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
                                   const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm);
+cudaError_t launch_tcg_sphere(const TcgCommon &a, const double *d, const double *Ut, unsigned long long ldu, const double *x,
+                              const double *w, const double *sigma_host, int k, double lambda, int grid, cudaStream_t st);
+cudaError_t launch_sphere_tdot(unsigned long long N, const double *Ut, unsigned long long ldu, const double *sigma_host, int k,
+                               const double *v, u64 *set, int sm_count, cudaStream_t st);
+cudaError_t launch_sphere_scale_t(const u64 *set, const double *sigma_host, int k, double *st_dev, cudaStream_t st);
+cudaError_t launch_sphere_apply(unsigned long long N, const double *d, const double *Ut, unsigned long long ldu, int k,
+                                const double *st_dev, const double *v, double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_sphere_combine(unsigned long long N, const double *Av, const double *x, const double *v, double c,
+                                  double lambda, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_dots(unsigned long long N, int count, const double *const *a, const double *const *b,
                         u64 *set, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st);
@@ -413,6 +422,40 @@ static int check_params(ob200_context *ctx, const ob200_stpcg_params *p) {
   return OB200_OK;
 }
 
+static int check_ldu(ob200_context *ctx, uint64_t n, uint64_t k, uint64_t ldu, const double *Ut) {
+  const uint64_t ld = ldu ? ldu : n;
+  if (k > 1 && (ld < n || (ld & 1))) return fail(ctx, OB200_INVALID_ARGUMENT, "U^T row stride (ldu) must be even and >= n");
+  if (k && (reinterpret_cast<uintptr_t>(Ut) & 15)) return fail(ctx, OB200_INVALID_ARGUMENT, "U^T must be 16-byte aligned");
+  return OB200_OK;
+}
+static int check_sphere(ob200_context *ctx, const ob200_operator *H) {
+  if (H->p != 1) return fail(ctx, OB200_INVALID_ARGUMENT, "sphere operator acts on vectors (p == 1)");
+  if (H->k > 16) return fail(ctx, OB200_UNSUPPORTED, "sphere low-rank operator supports k <= 16");
+  if (!H->diag_dev || !H->x_dev || !H->Ax_dev || (H->k && (!H->U_dev || !H->sigma_host)))
+    return fail(ctx, OB200_INVALID_ARGUMENT, "incomplete sphere operator");
+  return check_ldu(ctx, H->n, H->k, H->ldu, H->U_dev);
+}
+
+// out = A v for A = diag(d) + U diag(sigma) U^T: low-rank sums (exact reduction), then one streaming pass
+static int sphere_Av(ob200_context *ctx, uint64_t n, uint64_t k, const double *d, const double *Ut, uint64_t ldu,
+                     const double *sigma_host, const double *v, double *out) {
+  if (!ldu) ldu = n;
+  cudaStream_t st = ctx->stream;
+  double *st_dev = ctx->dmat;   // k doubles
+  if (k) {
+    CK(cudaMemsetAsync(ctx->acc + ACC_GRAM_OFF, 0, sizeof(u64) * 16 * KUL_STRIDE, st));
+    CK(launch_sphere_tdot(n, Ut, ldu, sigma_host, (int)k, v, ctx->acc, ctx->sm_count, st));
+    ctx->launches += 1;
+    int rc = exchange(ctx, ctx->acc, ACC_GRAM_OFF, (int)k * KUL_STRIDE);
+    if (rc) return rc;
+    CK(launch_sphere_scale_t(ctx->acc, sigma_host, (int)k, st_dev, st));
+    ctx->launches += 1;
+  }
+  CK(launch_sphere_apply(n, d, Ut, ldu, (int)k, st_dev, v, out, ctx->sm_count, st));
+  ctx->launches += 1;
+  return OB200_OK;
+}
+
 static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
                         const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
   int rc = check_params(ctx, prm);
@@ -434,6 +477,8 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     if (!(H->op_norm_bound > 0)) return fail(ctx, OB200_INVALID_ARGUMENT, "op_norm_bound must be positive");
   } else if (H->kind == OB200_OP_DIAG) {
     if (!H->diag_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "diag operator without diagonal");
+  } else if (H->kind == OB200_OP_SPHERE_LOWRANK) {
+    if ((rc = check_sphere(ctx, H))) return rc;
   } else {
     return fail(ctx, OB200_UNSUPPORTED, "operator kind not supported by the fused tCG path");
   }
@@ -489,6 +534,9 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   CK(cudaEventRecord(ctx->ev0, st));
   if (H->kind == OB200_OP_DIAG) {
     CK(launch_tcg_diag(a, H->diag_dev, ctx->sm_count, st));
+  } else if (H->kind == OB200_OP_SPHERE_LOWRANK) {
+    CK(launch_tcg_sphere(a, H->diag_dev, H->U_dev, H->ldu ? H->ldu : H->n, H->x_dev, H->Ax_dev, H->sigma_host,
+                         (int)H->k, H->xAx, ctx->sm_count, st));
   } else {
     const unsigned long long nblk = (H->n + 127) / 128;
     int grid = ctx->sm_count;
@@ -548,7 +596,7 @@ static uint64_t op_bytes(const ob200_operator *H) {
     case OB200_OP_DIAG: return 8 * N;                                   // d read once
     case OB200_OP_STIEFEL_BLOCKDIAG:                                    // A (bf16) + Y read twice
       return ((H->n + 127) / 128) * 128 * 128 * 2 + 2 * 8 * N;
-    case OB200_OP_SPHERE_LOWRANK: return 8 * H->n * (2 + H->k);         // d, x, U
+    case OB200_OP_SPHERE_LOWRANK: return 8 * H->n * (4 + 2 * H->k);     // U twice, d, x, w = A x, p re-read
     default: return 0;
   }
 }
@@ -670,6 +718,20 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
     ctx->launches += 1;
     return OB200_OK;
   }
+  if (H->kind == OB200_OP_SPHERE_LOWRANK) {
+    int rc = check_sphere(ctx, H);
+    if (rc) return rc;
+    if ((rc = ensure_vectors(ctx, N))) return rc;
+    double *Av = ctx->Hp;
+    if ((rc = sphere_Av(ctx, H->n, H->k, H->diag_dev, H->U_dev, H->ldu, H->sigma_host, v, Av))) return rc;
+    double xAv = 0.0;                                       // x^T A v
+    const double *aa[1] = {H->x_dev}, *bb[1] = {Av};
+    if ((rc = dots_sync(ctx, N, 1, aa, bb, &xAv))) return rc;
+    CK(launch_sphere_combine(N, Av, H->x_dev, v, xAv, H->xAx, out, ctx->sm_count, st));
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(st));
+    return OB200_OK;
+  }
   if (H->kind != OB200_OP_STIEFEL_BLOCKDIAG || H->p != 32) return fail(ctx, OB200_UNSUPPORTED, "operator kind");
   int rc = ensure_vectors(ctx, N);
   if (rc) return rc;
@@ -693,6 +755,40 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
   CK(launch_stiefel_rowgemm(H->n, ctx->Hp, 1.0, H->Y_dev, ctx->dmat + 1024, out, grid, st));
   ctx->launches += 1;
   CK(cudaStreamSynchronize(st));
+  return OB200_OK;
+}
+
+int ob200_sphere_model(ob200_context *ctx, uint64_t n, uint64_t k, const double *d, const double *Ut, uint64_t ldu,
+                       const double *sigma_host, const double *x, double *Ax_dev, double *xAx, double *grad_dev) {
+  if (!ctx || !d || !x || !Ax_dev || !xAx || (k && (!Ut || !sigma_host))) return OB200_INVALID_ARGUMENT;
+  if (k > 16) return fail(ctx, OB200_UNSUPPORTED, "sphere low-rank operator supports k <= 16");
+  CK(cudaSetDevice(ctx->device));
+  int rc = check_ldu(ctx, n, k, ldu, Ut);
+  if (rc) return rc;
+  if ((rc = sphere_Av(ctx, n, k, d, Ut, ldu, sigma_host, x, Ax_dev))) return rc;
+  const double *aa[1] = {x}, *bb[1] = {Ax_dev};
+  if ((rc = dots_sync(ctx, n, 1, aa, bb, xAx))) return rc;     // f(x) = x^T A x
+  if (grad_dev) {                                               // grad f(x) = 2 (A x - (x^T A x) x)
+    CK(launch_sphere_combine(n, Ax_dev, x, nullptr, *xAx, 0.0, grad_dev, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return OB200_OK;
+}
+
+int ob200_sphere_retract(ob200_context *ctx, uint64_t n, const double *x, const double *v, double *out) {
+  if (!ctx || !x || !v || !out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_axpby(n, 1.0, x, 1.0, v, out, ctx->sm_count, ctx->stream));       // z = x + v
+  ctx->launches += 1;
+  double zz = 0.0;
+  const double *aa[1] = {out}, *bb[1] = {out};
+  int rc = dots_sync(ctx, n, 1, aa, bb, &zz);
+  if (rc) return rc;
+  if (!(zz > 0)) return fail(ctx, OB200_NUMERIC_RANGE, "retraction: x + v is zero or not finite");
+  const double inv = 1.0 / std::sqrt(zz);
+  CK(launch_axpby(n, inv, out, 0.0, nullptr, out, ctx->sm_count, ctx->stream));  // z / ||z||
+  ctx->launches += 1;
   return OB200_OK;
 }
 

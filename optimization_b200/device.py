@@ -149,6 +149,50 @@ class Context:
         h.S, h.f = S, f.value
         return h
 
+    def sphere_operator(self, d: torch.Tensor, U: torch.Tensor, sigma: np.ndarray, x: torch.Tensor,
+                        Ut: torch.Tensor | None = None) -> "OperatorHandle":
+        """Hess f(x)[v] = 2 P_x(A v) - 2 (x^T A x) v for f(x) = x^T A x on the sphere,
+        A = diag(d) + U diag(sigma) U^T (U: n x k).  The device keeps U transposed (k x n)."""
+        n = d.numel()
+        k = int(sigma.size)
+        if Ut is None:                       # k rows of ldu = n rounded up to even (16-byte aligned rows)
+            Ut = torch.zeros((k, n + (n & 1)), dtype=torch.float64, device=d.device)
+            if k:
+                Ut[:, :n] = U.t()
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+        Ax, f, _ = self.sphere_model(d, Ut, sigma, x, want_grad=False)
+        op = capi.Operator()
+        op.kind = capi.OP_SPHERE_LOWRANK
+        op.n, op.p, op.k = n, 1, k
+        op.diag_dev = d.data_ptr()
+        op.U_dev = Ut.data_ptr() if k else None
+        op.sigma_host = sigma.ctypes.data if k else None
+        op.ldu = Ut.shape[1] if k else 0
+        op.x_dev = x.data_ptr()
+        op.Ax_dev = Ax.data_ptr()
+        op.xAx = f
+        h = OperatorHandle(self, op, [d, Ut, sigma, x, Ax])
+        h.f, h.Ut, h.Ax = f, Ut, Ax
+        return h
+
+    def sphere_model(self, d, Ut, sigma, x, want_grad=True):
+        """(A x, f = x^T A x, grad = 2 (A x - f x)) on the device."""
+        n = d.numel()
+        k = int(sigma.size)
+        Ax = torch.empty_like(x)
+        grad = torch.empty_like(x) if want_grad else None
+        f = C.c_double(0)
+        self._check(self.lib.ob200_sphere_model(self.h, n, k, _ptr(d), _ptr(Ut) if k else None,
+                                                Ut.shape[1] if k else 0, _ptr(sigma) if k else None,
+                                                _ptr(x), _ptr(Ax), C.byref(f), _ptr(grad)))
+        return Ax, f.value, grad
+
+    def sphere_retract(self, x, v, out=None):
+        if out is None:
+            out = torch.empty_like(x)
+        self._check(self.lib.ob200_sphere_retract(self.h, x.numel(), _ptr(x), _ptr(v), _ptr(out)))
+        return out
+
     def jacobi(self, minv: torch.Tensor | None):
         pc = capi.Precon()
         if minv is None:

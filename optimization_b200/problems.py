@@ -198,6 +198,78 @@ def make_sphere(n: int, k: int = 16, seed: int = 11) -> SphereProblem:
     return SphereProblem(n, k, d, np.ascontiguousarray(U), sigma, x0, g)
 
 
+def make_sphere_critical(n: int, k: int = 16, seed: int = 11, x_noise: float = 0.02) -> SphereProblem:
+    """Same family with a known minimiser: d_0 = 0.25, d_i in [1.5, 2.5] otherwise, row 0 of U zero and
+    |sigma| <= 0.5, so e_0 is the eigenvector of the smallest eigenvalue (0.25) and the Riemannian
+    Hessian 2 (A - lambda I) is positive definite on the tangent space (spectrum within about
+    [1.4, 5.6]): tCG runs its natural course to the residual target instead of leaving through the
+    boundary at once.  x0 = normalised e_0 + noise of norm about x_noise; g = a tangent vector at x0."""
+    d = 1.5 + uniform01(seed, 0, n)
+    d[0] = 0.25
+    U = gaussish(seed + 1, 0, n * k).reshape(n, k) / np.sqrt(n) if k else np.zeros((n, 0))
+    if k:
+        U[0, :] = 0.0
+    sigma = uniform01(seed + 2, 0, k) - 0.5
+    x0 = (x_noise / np.sqrt(n)) * gaussish(seed + 3, 0, n)
+    x0[0] = 1.0
+    x0 /= np.linalg.norm(x0)
+    z = gaussish(seed + 4, 0, n)
+    g = z - x0 * float(x0 @ z)
+    return SphereProblem(n, k, d, np.ascontiguousarray(U), sigma, x0, g)
+
+
+def _torch_uniform01(seed: int, start: int, count: int, device):
+    """uniform01 on the device, bit-identical to the numpy version (int64 arithmetic wraps like uint64;
+    logical right shifts are emulated with a mask)."""
+    import torch
+
+    def c(v):  # uint64 constant as a wrapped python int for int64 tensors
+        v &= 0xFFFFFFFFFFFFFFFF
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def shr(z, sh):
+        return (z >> sh) & ((1 << (64 - sh)) - 1)
+
+    idx = torch.arange(start, start + count, dtype=torch.int64, device=device)
+    z = idx + c(seed * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)
+    z = (z ^ shr(z, 30)) * c(0xBF58476D1CE4E5B9)
+    z = (z ^ shr(z, 27)) * c(0x94D049BB133111EB)
+    z = z ^ shr(z, 31)
+    return shr(z, 11).to(torch.float64) * (1.0 / (1 << 53))
+
+
+def _torch_gaussish(seed: int, start: int, count: int, device):
+    import torch
+    acc = torch.zeros(count, dtype=torch.float64, device=device)
+    for k in range(4):
+        acc += _torch_uniform01(seed * 4 + k + 1000003, start, count, device)
+    return (acc - 2.0) * float(np.sqrt(3.0))
+
+
+def make_sphere_critical_device(n: int, k: int = 16, seed: int = 11, x_noise: float = 0.02, device="cuda:0"):
+    """make_sphere_critical generated directly in device memory (full-size config C2: U alone is
+    2 GB at n = 2^24).  Returns torch tensors (d, Ut [k x n], sigma (numpy), x0, g); d and U are
+    bit-identical to the host generator, x0 / g agree up to the rounding of the normalisation."""
+    import torch
+    d = 1.5 + _torch_uniform01(seed, 0, n, device)
+    d[0] = 0.25
+    Ut = torch.empty((k, n), dtype=torch.float64, device=device)
+    rows = max(1, (1 << 22) // max(k, 1))
+    for r0 in range(0, n, rows):                  # U[r, j] = sample r * k + j
+        r1 = min(n, r0 + rows)
+        blk = _torch_gaussish(seed + 1, r0 * k, (r1 - r0) * k, device).view(r1 - r0, k)
+        Ut[:, r0:r1] = (blk / float(np.sqrt(n))).t()
+    if k:
+        Ut[:, 0] = 0.0
+    sigma = uniform01(seed + 2, 0, k) - 0.5
+    x0 = float(x_noise / np.sqrt(n)) * _torch_gaussish(seed + 3, 0, n, device)
+    x0[0] = 1.0
+    x0 /= torch.linalg.norm(x0)
+    z = _torch_gaussish(seed + 4, 0, n, device)
+    g = z - x0 * torch.dot(x0, z)
+    return d, Ut, sigma, x0, g
+
+
 @dataclasses.dataclass
 class DiagProblem:
     """Diagonal SPD Hessian with optional Jacobi preconditioner (the shape of the

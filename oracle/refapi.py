@@ -252,6 +252,12 @@ class PortOracle:
                                          C.c_double, C.c_uint64, C.c_double, C.c_double,
                                          C.c_double, _dp, _dp, _u64p]
         L.port_stiefel_S.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, _dp, _dp, _dp]
+        L.port_stpcg_sphere.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp,
+                                        C.c_double, C.c_uint64, C.c_double, C.c_double,
+                                        C.c_double, _dp, _dp, _u64p]
+        L.port_sphere_model.restype = C.c_double
+        L.port_sphere_model.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.port_sphere_hess.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp]
 
     def dot(self, x, y):
         return float(self.lib.port_dot(_d(x), _d(y), x.size))
@@ -266,6 +272,31 @@ class PortOracle:
         if rc < 0:
             raise ValueError("invalid argument")
         return s, float(mn.value), int(it.value), self.EXIT[rc]
+
+    def stpcg_sphere(self, prob, x, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1,
+                     theta=0.5, epsilon=1e-8):
+        s = np.zeros(prob.n)
+        mn = C.c_double(0)
+        it = C.c_uint64(0)
+        rc = self.lib.port_stpcg_sphere(prob.n, prob.k, _d(prob.d), _d(prob.U), _d(prob.sigma), _d(x),
+                                        _d(g), _d(minv), Delta, max_iterations, kappa_fgr, theta,
+                                        epsilon, _d(s), C.byref(mn), C.byref(it))
+        if rc < 0:
+            raise ValueError("invalid argument")
+        return s, float(mn.value), int(it.value), self.EXIT[rc]
+
+    def sphere_model(self, prob, x):
+        Ax = np.zeros(prob.n)
+        grad = np.zeros(prob.n)
+        f = self.lib.port_sphere_model(prob.n, prob.k, _d(prob.d), _d(prob.U), _d(prob.sigma), _d(x),
+                                       _d(Ax), _d(grad))
+        return float(f), Ax, grad
+
+    def sphere_hess(self, prob, x, v):
+        out = np.zeros(prob.n)
+        self.lib.port_sphere_hess(prob.n, prob.k, _d(prob.d), _d(prob.U), _d(prob.sigma), _d(x), _d(v),
+                                  _d(out))
+        return out
 
     def stpcg_stiefel(self, prob, Y, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1,
                       theta=0.5, epsilon=1e-8):

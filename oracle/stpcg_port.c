@@ -144,6 +144,76 @@ int port_stpcg_diag(uint64_t n, const double *g, const double *hdiag, const doub
                     kappa_fgr, theta, epsilon, s, mnorm, iters);
 }
 
+/* Rayleigh-quotient Hessian on the sphere (config C2; the model of the reference's
+ * examples/Riemannian_optimization_example.cpp with a structured A):
+ *   f(x) = x^T A x,  A = diag(d) + U diag(sigma) U^T  (U: n x k row-major),
+ *   Hess f(x)[v] = 2 (A v - (x^T A v) x) - 2 (x^T A x) v.
+ * Same statement order as oracle/ref_driver.cpp (SphereOp::apply, single-thread path, and
+ * ref_sphere_stpcg), so both oracles round identically. */
+typedef struct {
+  uint64_t n, k;
+  const double *d, *U, *sigma, *x;
+  double xAx;
+  double *Av; /* scratch, n */
+} port_sphere;
+static void sphere_A(const port_sphere *P, const double *v, double *out) {
+  double t[64];
+  for (size_t j = 0; j < P->k; ++j) t[j] = 0.0;
+  for (size_t r = 0; r < P->n; ++r) {            /* t = U^T v, row order, fma */
+    const double vr = v[r];
+    const double *u = P->U + r * P->k;
+    for (size_t j = 0; j < P->k; ++j) t[j] = fma(u[j], vr, t[j]);
+  }
+  for (size_t j = 0; j < P->k; ++j) t[j] = t[j] * P->sigma[j];
+  for (size_t r = 0; r < P->n; ++r) {            /* out = d .* v + U t */
+    double acc = P->d[r] * v[r];
+    const double *u = P->U + r * P->k;
+    for (size_t j = 0; j < P->k; ++j) acc = fma(u[j], t[j], acc);
+    out[r] = acc;
+  }
+}
+static void sphere_hess(void *c, const double *v, double *out) {
+  port_sphere *P = (port_sphere *)c;
+  sphere_A(P, v, P->Av);
+  const double xAv = dot8(P->x, P->Av, P->n);
+  for (size_t i = 0; i < P->n; ++i)
+    out[i] = 2.0 * (P->Av[i] - xAv * P->x[i]) - 2.0 * P->xAx * v[i];
+}
+/* f = x^T A x, optional Ax (n), optional grad = 2 (A x - f x) */
+double port_sphere_model(uint64_t n, uint64_t k, const double *d, const double *U, const double *sigma,
+                         const double *x, double *Ax_out, double *grad_out) {
+  if (k > 64) return NAN;
+  double *Ax = (double *)malloc(n * sizeof(double));
+  port_sphere P = {n, k, d, U, sigma, x, 0.0, NULL};
+  sphere_A(&P, x, Ax);
+  const double f = dot8(x, Ax, n);
+  if (grad_out)
+    for (size_t i = 0; i < n; ++i) grad_out[i] = 2.0 * (Ax[i] - f * x[i]);
+  if (Ax_out) memcpy(Ax_out, Ax, n * sizeof(double));
+  free(Ax);
+  return f;
+}
+void port_sphere_hess(uint64_t n, uint64_t k, const double *d, const double *U, const double *sigma,
+                      const double *x, const double *v, double *out) {
+  port_sphere P = {n, k, d, U, sigma, x, 0.0, (double *)malloc(n * sizeof(double))};
+  P.xAx = port_sphere_model(n, k, d, U, sigma, x, NULL, NULL);
+  sphere_hess(&P, v, out);
+  free(P.Av);
+}
+int port_stpcg_sphere(uint64_t n, uint64_t k, const double *d, const double *U, const double *sigma,
+                      const double *x, const double *g, const double *minv, double Delta,
+                      uint64_t max_iterations, double kappa_fgr, double theta, double epsilon, double *s,
+                      double *mnorm, uint64_t *iters) {
+  if (k > 64) return PORT_EXIT_BADARG;
+  port_sphere P = {n, k, d, U, sigma, x, 0.0, (double *)malloc(n * sizeof(double))};
+  P.xAx = port_sphere_model(n, k, d, U, sigma, x, NULL, NULL);
+  port_diag Pd = {n, minv};
+  const int rc = port_stpcg(n, g, sphere_hess, &P, minv ? diag_apply : NULL, &Pd, Delta, max_iterations,
+                            kappa_fgr, theta, epsilon, s, mnorm, iters);
+  free(P.Av);
+  return rc;
+}
+
 /* Stiefel trace-min Hessian  Hess f(Y)[V] = P_Y(A V - V S),  S = sym(Y^T A Y),
  * A block-diagonal (double copy of the bf16 blocks).  Same loop order as
  * oracle/ref_driver.cpp so both oracles round identically. */

@@ -92,6 +92,23 @@ def main():
             out[f"stiefelcrit{n}_{name}"] = dict(update_step_M_norm=mn, num_iterations=it, args=kw,
                                                  problem=f"make_stiefel_critical({n}, 32)")
             arrays[f"stiefelcrit{n}_{name}_s"] = s
+    # --- sphere Rayleigh quotient, diag + low-rank A (configs C1 / C2 shape) ------------
+    for (n, k) in ((1000, 16), (4099, 5)):
+        prob = P.make_sphere_critical(n, k)
+        gn = float(np.linalg.norm(prob.g))
+        tag = f"spherecrit{n}_k{k}"
+        for name, kw in (("tight", dict(Delta=1e6, max_iterations=200, kappa_fgr=1e-9, theta=0.0)),
+                         ("default", dict(Delta=10.0 * gn, max_iterations=1000, kappa_fgr=.1, theta=.5)),
+                         ("boundary", dict(Delta=0.2 * gn, max_iterations=1000, kappa_fgr=1e-6, theta=.5))):
+            s, mn, it = R.sphere_stpcg(prob, prob.x0, prob.g, **kw)
+            out[f"{tag}_{name}"] = dict(update_step_M_norm=mn, num_iterations=it, args=kw,
+                                        problem=f"make_sphere_critical({n}, {k})")
+            arrays[f"{tag}_{name}_s"] = s
+    prob = P.make_sphere(100, 16)          # C1: n = 100, random start, default TNTParams
+    r = R.sphere_tnt(prob, prob.x0, default_tnt_params())
+    arrays["sphere100_tnt_x"] = r.pop("x")
+    r["params"] = default_tnt_params()
+    out["sphere100_tnt"] = r
     with open(os.path.join(HERE, "golden.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "golden_arrays.npz"), **arrays)

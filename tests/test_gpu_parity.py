@@ -228,3 +228,93 @@ def test_stiefel_full_size_properties(ctx):
     # host-buffer entry gives the same result as the device entry
     oh = ctx.stpcg(prob.g, H, host=True, **kw)
     assert oh.num_iterations == o1.num_iterations and np.array_equal(oh.s, s1.cpu().numpy())
+
+
+# ---- sphere Rayleigh-quotient Hessian, A = diag + low rank (configs C1 / C2) ------------------
+def sphere_setup(ctx, prob):
+    d, U, x = ctx.to_device(prob.d), ctx.to_device(prob.U), ctx.to_device(prob.x0)
+    return ctx.sphere_operator(d, U, prob.sigma, x)
+
+
+@pytest.mark.parametrize("n,k", [(1000, 16), (4099, 5)])
+def test_sphere_stpcg_golden(ctx, golden, n, k):
+    rec, arr = golden
+    prob = P.make_sphere_critical(n, k)
+    H = sphere_setup(ctx, prob)
+    for name in ("tight", "default", "boundary"):
+        r = rec[f"spherecrit{n}_k{k}_{name}"]
+        out = ctx.stpcg(ctx.to_device(prob.g), H, **r["args"])
+        assert out.num_iterations == r["num_iterations"], name
+        assert rel(out.s.cpu().numpy(), arr[f"spherecrit{n}_k{k}_{name}_s"]) < RTOL, name
+        assert abs(out.update_step_M_norm - r["update_step_M_norm"]) <= RTOL * r["update_step_M_norm"], name
+
+
+@pytest.mark.parametrize("n,k", [(1, 0), (2, 1), (255, 16), (256, 16), (257, 3), (4099, 16), (100003, 16),
+                                 (1 << 20, 16), (70000, 0)])
+@pytest.mark.parametrize("precon", [False, True])
+def test_sphere_stpcg_vs_oracle_ragged(ctx, port, n, k, precon):
+    prob = P.make_sphere_critical(n, k) if n > 2 else P.make_sphere(n, k)
+    H = sphere_setup(ctx, prob)
+    minv = 1.0 / (1.0 + P.uniform01(77, 0, n)) if precon else None
+    gn = float(np.linalg.norm(prob.g)) or 1.0
+    for kw in (dict(Delta=1e6 * gn, max_iterations=40, kappa_fgr=1e-10, theta=0.),
+               dict(Delta=.2 * gn, max_iterations=40, kappa_fgr=.1, theta=.5),
+               dict(Delta=1e6 * gn, max_iterations=3, kappa_fgr=1e-10, theta=0.)):
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_sphere(prob, prob.x0, prob.g, minv, **kw)
+        out = ctx.stpcg(ctx.to_device(prob.g), H, minv=None if minv is None else ctx.to_device(minv), **kw)
+        assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+
+
+def test_sphere_indefinite_exits_like_oracle(ctx, port):
+    # random base point: the Rayleigh Hessian is indefinite, tCG leaves through the boundary (l.347-361)
+    prob = P.make_sphere(20000, 16)
+    H = sphere_setup(ctx, prob)
+    for Delta in (0.5, 50.0, 1e4):
+        kw = dict(Delta=Delta, max_iterations=100, kappa_fgr=1e-8, theta=0.)
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_sphere(prob, prob.x0, prob.g, **kw)
+        out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+        assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL and out.update_step_M_norm == mn_ref
+
+
+def test_sphere_model_hvp_retract(ctx, port):
+    prob = P.make_sphere(30011, 16)
+    H = sphere_setup(ctx, prob)
+    f_ref, Ax_ref, grad_ref = port.sphere_model(prob, prob.x0)
+    Ax, f, grad = ctx.sphere_model(ctx.to_device(prob.d), H.Ut, prob.sigma, ctx.to_device(prob.x0))
+    assert abs(f - f_ref) <= RTOL * abs(f_ref)
+    assert rel(Ax.cpu().numpy(), Ax_ref) < RTOL and rel(grad.cpu().numpy(), grad_ref) < RTOL
+    hv = ctx.hvp(H, ctx.to_device(prob.g)).cpu().numpy()
+    assert rel(hv, port.sphere_hess(prob, prob.x0, prob.g)) < RTOL
+    # projection retraction (reference example: (x + v) / |x + v|)
+    v = 0.01 * prob.g
+    q = ctx.sphere_retract(ctx.to_device(prob.x0), ctx.to_device(v)).cpu().numpy()
+    z = prob.x0 + v
+    assert rel(q, z / np.linalg.norm(z)) < 1e-14 and abs(np.linalg.norm(q) - 1.0) < 1e-14
+
+
+def test_sphere_full_size_properties(ctx):
+    # config C2: n = 2^24, k = 16 (U alone is 2 GB), generated on the device
+    import torch
+    n, k = 1 << 24, 16
+    d, Ut, sigma, x0, g = P.make_sphere_critical_device(n, k, device="cuda:0")
+    H = ctx.sphere_operator(d, None, sigma, x0, Ut=Ut)
+    gn = math.sqrt(ctx.dot(g, g))
+    kw = dict(Delta=1e6 * gn, max_iterations=200, kappa_fgr=1e-9, theta=0.)
+    o1 = ctx.stpcg(g, H, **kw)
+    s1 = o1.s.clone()
+    o2 = ctx.stpcg(g, H, **kw)
+    assert o1.exit_reason == "residual" and 5 < o1.num_iterations < 100
+    assert o1.num_iterations == o2.num_iterations and o1.update_step_M_norm == o2.update_step_M_norm
+    assert torch.equal(s1, o2.s)                               # bitwise run-to-run determinism
+    r = g + ctx.hvp(H, s1)                                     # residual reduction (:254-275)
+    assert math.sqrt(ctx.dot(r, r)) <= 1.0001 * 1e-9 * gn
+    assert abs(o1.update_step_M_norm - math.sqrt(ctx.dot(s1, s1))) <= 1e-9 * o1.update_step_M_norm
+    assert abs(ctx.dot(x0, s1)) <= 1e-9 * o1.update_step_M_norm    # s is tangent at x
+    v = torch.roll(g, 12345)
+    v = v - x0 * ctx.dot(x0, v)
+    lhs = ctx.hvp(H, ctx.axpby(2.0, g, -3.0, v)).cpu().numpy()
+    rhs = 2.0 * ctx.hvp(H, g).cpu().numpy() - 3.0 * ctx.hvp(H, v).cpu().numpy()
+    assert rel(lhs, rhs) < 1e-12                               # linearity of the HVP

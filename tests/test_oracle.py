@@ -173,3 +173,40 @@ def test_ref_matches_port_live(port, ref):
     a = ref.stiefel(prob).stpcg(prob.Y0, prob.g, Delta=1e6, max_iterations=100, kappa_fgr=1e-9, theta=0.)
     b = port.stpcg_stiefel(prob, prob.Y0, prob.g, Delta=1e6, max_iterations=100, kappa_fgr=1e-9, theta=0.)
     assert a[1] == b[1] and a[2] == b[2] and np.array_equal(a[0], b[0])
+
+
+# ---- sphere Rayleigh quotient (configs C1 / C2 shape) ----------------------------------
+@pytest.mark.parametrize("n,k", [(1000, 16), (4099, 5)])
+def test_port_matches_golden_sphere(port, golden, n, k):
+    rec, arr = golden
+    prob = P.make_sphere_critical(n, k)
+    for name in ("tight", "default", "boundary"):
+        r = rec[f"spherecrit{n}_k{k}_{name}"]
+        s, mn, it, why = port.stpcg_sphere(prob, prob.x0, prob.g, **r["args"])
+        assert it == r["num_iterations"] and mn == r["update_step_M_norm"]
+        assert np.array_equal(s, arr[f"spherecrit{n}_k{k}_{name}_s"])          # bit for bit
+    # the residual-reduction property the reference tests (IterativeSolvers_unit_test.cpp:254-275)
+    kw = rec[f"spherecrit{n}_k{k}_tight"]["args"]
+    s, mn, it, why = port.stpcg_sphere(prob, prob.x0, prob.g, **kw)
+    r = prob.g + port.sphere_hess(prob, prob.x0, s)
+    assert why == "residual" and np.linalg.norm(r) <= 1.0001 * kw["kappa_fgr"] * np.linalg.norm(prob.g)
+
+
+def test_sphere_tnt_golden_reference_assertions(golden):
+    # the assertions of tests/TNT_unit_test.cpp:126-187 on the recorded C1 run (n = 100, default TNTParams)
+    rec, arr = golden
+    r = rec["sphere100_tnt"]
+    x = arr["sphere100_tnt_x"]
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-12
+    assert r["objective_values"][-1] < r["objective_values"][0] if "objective_values" in r else True
+
+
+def test_ref_matches_port_live_sphere(port, ref):
+    for n, k in ((257, 16), (5000, 3), (300, 0)):
+        prob = P.make_sphere_critical(n, k)
+        gn = float(np.linalg.norm(prob.g))
+        for kw in (dict(Delta=1e6, max_iterations=50, kappa_fgr=1e-10, theta=0.),
+                   dict(Delta=.2 * gn, max_iterations=50, kappa_fgr=.1, theta=.5)):
+            a = ref.sphere_stpcg(prob, prob.x0, prob.g, **kw)
+            b = port.stpcg_sphere(prob, prob.x0, prob.g, **kw)
+            assert a[2] == b[2] and a[1] == b[1] and np.array_equal(a[0], b[0])
