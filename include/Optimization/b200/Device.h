@@ -142,7 +142,8 @@ struct OperatorState {
   ob200_context *ctx = nullptr;
   ob200_operator op{};
   std::vector<double> S;        // host copy of sym(Y^T A Y) (op.S_host points here)
-  DeviceMatrix Y;               // base point the descriptor refers to (op.Y_dev points here)
+  DeviceMatrix Y;               // base point the descriptor refers to (op.Y_dev / op.x_dev point here)
+  DeviceMatrix Ax;              // sphere model: A x at the base point (op.Ax_dev points here)
 };
 
 // Hessian with the point already bound: SymmetricLinearOperator<DeviceMatrix, Args...>.
@@ -243,6 +244,71 @@ class StiefelTraceMin {
   ob200_context *ctx_;
   size_t n_, p_;
   uint16_t *A_ = nullptr;
+};
+
+// ---- Rayleigh quotient on the sphere  f(x) = x^T A x,  A = diag(d) + U diag(sigma) U^T ------------------
+// (the model of the reference's examples/Riemannian_optimization_example.cpp with a structured A; BASELINE
+// configs C1 / C2).  Functor set for TNT<DeviceMatrix, DeviceMatrix, double>(f, QM, metric, retract, x0, ...).
+class SphereRayleigh {
+ public:
+  // d: n, U: n x k row-major, sigma: k  (host arrays); the device keeps U transposed, rows padded to even length
+  SphereRayleigh(ob200_context *ctx, size_t n, size_t k, const double *d, const double *U, const double *sigma)
+      : ctx_(ctx), n_(n), k_(k), ldu_(n + (n & 1)), sigma_(sigma, sigma + k), d_(ctx, n, 1, d) {
+    if (k_) {
+      std::vector<double> Ut(k_ * ldu_, 0.0);
+      for (size_t r = 0; r < n_; ++r)
+        for (size_t j = 0; j < k_; ++j) Ut[j * ldu_ + r] = U[r * k_ + j];
+      Ut_ = DeviceMatrix(ctx_, k_, ldu_, Ut.data());
+    }
+  }
+  Objective<DeviceMatrix, double> objective() const {
+    return [this](const DeviceMatrix &x) {
+      DeviceMatrix Ax = x.like();
+      double f = 0;
+      check(ctx_, ob200_sphere_model(ctx_, n_, k_, d_.data(), Ut_.data(), ldu_, sigma_.data(), x.data(), Ax.data(), &f,
+                                     nullptr));
+      return f;
+    };
+  }
+  Riemannian::QuadraticModel<DeviceMatrix, DeviceMatrix> quadratic_model() const {
+    return [this](const DeviceMatrix &x, DeviceMatrix &grad,
+                  Riemannian::LinearOperator<DeviceMatrix, DeviceMatrix> &Hess) {
+      auto st = std::make_shared<OperatorState>();
+      st->ctx = ctx_;
+      st->Y = x;
+      st->Ax = x.like();
+      grad = x.like();
+      double f = 0;
+      check(ctx_, ob200_sphere_model(ctx_, n_, k_, d_.data(), Ut_.data(), ldu_, sigma_.data(), st->Y.data(),
+                                     st->Ax.data(), &f, grad.data()));
+      st->op.kind = OB200_OP_SPHERE_LOWRANK;
+      st->op.n = n_;
+      st->op.p = 1;
+      st->op.k = k_;
+      st->op.ldu = ldu_;
+      st->op.diag_dev = d_.data();
+      st->op.U_dev = Ut_.data();
+      st->op.sigma_host = sigma_.data();
+      st->op.x_dev = st->Y.data();
+      st->op.Ax_dev = st->Ax.data();
+      st->op.xAx = f;
+      Hess = FusedHessian{st};
+    };
+  }
+  Riemannian::RiemannianMetric<DeviceMatrix, DeviceMatrix, double> metric() const { return FrobeniusMetric{}; }
+  Riemannian::Retraction<DeviceMatrix, DeviceMatrix> retraction() const {
+    return [this](const DeviceMatrix &x, const DeviceMatrix &v) {
+      DeviceMatrix out = x.like();
+      check(ctx_, ob200_sphere_retract(ctx_, n_, x.data(), v.data(), out.data()));
+      return out;
+    };
+  }
+
+ private:
+  ob200_context *ctx_;
+  size_t n_, k_, ldu_;
+  std::vector<double> sigma_;
+  DeviceMatrix d_, Ut_;
 };
 
 }  // namespace b200

@@ -99,3 +99,29 @@ def test_device_tnt_matches_reference_golden(golden, tmp_path):
     s_ref = arr["stiefel512_yn1_tight_s"]
     if np.all(np.isfinite(s_ref)):
         assert np.linalg.norm(s_dev - s_ref) / np.linalg.norm(s_ref) < 1e-10
+
+
+@pytest.mark.gpu
+def test_device_sphere_tnt_matches_reference_golden(golden, tmp_path):
+    """Config C1 (sphere, n = 100, default TNTParams) through TNT<DeviceMatrix, DeviceMatrix, double> with the
+    SphereRayleigh functor set: fused device tCG inside, model / retraction on the device."""
+    rec, arr = golden
+    exe = _compile("tnt_sphere_check", link=True)
+    prob = P.make_sphere(100, 16)
+    f = tmp_path / "sphere.bin"
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<QQ", prob.n, prob.k))
+        for a in (prob.d, prob.U, prob.sigma, prob.x0):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    xo = tmp_path / "x.bin"
+    out = subprocess.run([exe, str(f), str(xo)], check=True, capture_output=True, text=True).stdout
+    g = _lines(out)["sphere_tnt"]
+    r = rec["sphere100_tnt"]
+    assert g["status_code"] == r["status_code"]                          # bit-exact termination status
+    assert g["inner_iterations"] == r["inner_iterations"]                # bit-exact iteration counts
+    assert np.allclose(g["trust_region_radius"], r["trust_region_radius"], rtol=1e-10, atol=0)
+    assert np.allclose(g["objective_values"], r["objective_values"], rtol=1e-10, atol=1e-13)
+    assert np.allclose(g["gain_ratios"], r["gain_ratios"], rtol=1e-6, atol=0)
+    x = np.fromfile(xo)
+    x_ref = arr["sphere100_tnt_x"]
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-10     # final iterate
