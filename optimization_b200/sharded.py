@@ -35,7 +35,22 @@ class SingleStiefel:
         return self.H.step_bytes()
 
     def ncu_traffic_per_launch(self, iters_per_launch):
-        return None
+        """DRAM bytes per launch of the persistent kernel from the committed `ncu --set full` capture
+        (profiles/traffic.json), scaled to this run's iteration count; None if no capture matches."""
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+        try:
+            with open(path) as fh:
+                rec = json.load(fh)["tcg_stiefel_tc_kernel"]
+        except Exception:
+            return None
+        if rec.get("n") != self.prob.n or getattr(self, "world", 1) != 1:
+            return None
+        return rec["dram_bytes_per_launch"] / rec["cg_iterations_per_launch"] * iters_per_launch
+
+    def hvp_device(self):
+        return self.ctx.hvp(self.H, self.g)
 
 
 def row_partition(n: int, world: int, nb: int = 128):
@@ -72,3 +87,30 @@ class ShardedStiefel(SingleStiefel):
         # whole-problem algorithmic bytes of one CG step = sum over ranks
         n, p = self.prob.n, self.prob.p
         return 12 * 8 * n * p + self.prob.nblk * self.prob.nb * self.prob.nb * 2
+
+
+class SingleSphere:
+    """Sphere Rayleigh-quotient tCG problem (config C1 / C2 family) resident on one GPU."""
+
+    def __init__(self, ctx, prob, lo=0, hi=None):
+        hi = prob.n if hi is None else hi
+        self.ctx, self.prob, self.lo, self.hi = ctx, prob, lo, hi
+        self.d = ctx.to_device(prob.d[lo:hi])
+        self.U = ctx.to_device(np.ascontiguousarray(prob.U[lo:hi]))
+        self.x = ctx.to_device(prob.x0[lo:hi])
+        self.g = ctx.to_device(prob.g[lo:hi])
+        self.H = ctx.sphere_operator(self.d, self.U, prob.sigma, self.x)      # A x, x^T A x: global (exchanged)
+
+    def solve_device(self, **kw):
+        return self.ctx.stpcg(self.g, self.H, **kw)
+
+
+class ShardedSphere(SingleSphere):
+    """The same problem row-sharded over the ranks (shard boundaries at multiples of 256 elements, the unit
+    of the exact reduction, so N-GPU runs are bit-identical to 1-GPU runs)."""
+
+    def __init__(self, ctx, prob, rank, world):
+        if getattr(ctx, "world", 1) != world:
+            ctx.connect(rank, world)
+        lo, hi = row_partition(prob.n, world, 256)
+        super().__init__(ctx, prob, lo[rank], hi[rank])

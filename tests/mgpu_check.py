@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from optimization_b200 import problems as P  # noqa: E402
 from optimization_b200.device import Context  # noqa: E402
-from optimization_b200.sharded import ShardedStiefel, SingleStiefel  # noqa: E402
+from optimization_b200.sharded import ShardedSphere, ShardedStiefel, SingleSphere, SingleStiefel  # noqa: E402
 
 
 def main():
@@ -46,6 +46,29 @@ def main():
                 same = (o1.num_iterations == out.num_iterations and o1.exit_reason == out.exit_reason
                         and o1.update_step_M_norm == out.update_step_M_norm and np.array_equal(s1, s_full))
                 print(f"n={n} world={world} iters={out.num_iterations}/{o1.num_iterations} exit={out.exit_reason} "
+                      f"bit-identical={same} maxdiff={np.abs(s1 - s_full).max():.3e}", flush=True)
+                ok = ok and same
+                c1.close()
+            dist.barrier()
+    # sphere Rayleigh Hessian (three exact reductions per CG step, 16 low-rank sums in the first one)
+    for n in [4096, 100003, 1 << 20]:
+        prob = P.make_sphere_critical(n, 16)
+        gn = float(np.linalg.norm(prob.g))
+        for kw in (dict(Delta=1e6 * gn, max_iterations=60, kappa_fgr=1e-10, theta=0.0),
+                   dict(Delta=0.3 * gn, max_iterations=60, kappa_fgr=1e-3, theta=.5)):
+            sh = ShardedSphere(ctx, prob, rank, world)
+            out = sh.solve_device(**kw)
+            parts = [None] * world
+            dist.all_gather_object(parts, (sh.lo, out.s.cpu().numpy(), out.num_iterations, out.exit_reason,
+                                           out.update_step_M_norm))
+            if rank == 0:
+                s_full = np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])])
+                c1 = Context(local)
+                o1 = SingleSphere(c1, prob).solve_device(**kw)
+                s1 = o1.s.cpu().numpy()
+                same = (o1.num_iterations == out.num_iterations and o1.exit_reason == out.exit_reason
+                        and o1.update_step_M_norm == out.update_step_M_norm and np.array_equal(s1, s_full))
+                print(f"sphere n={n} world={world} iters={out.num_iterations}/{o1.num_iterations} exit={out.exit_reason} "
                       f"bit-identical={same} maxdiff={np.abs(s1 - s_full).max():.3e}", flush=True)
                 ok = ok and same
                 c1.close()
