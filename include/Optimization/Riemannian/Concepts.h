@@ -57,16 +57,28 @@ struct SmoothOptimizerResult : public OptimizerResult<Variable, Scalar> {
   std::vector<Scalar> update_step_norms;
 };
 
-// Euclidean specialisations
-template <typename Vector, typename Scalar = double, typename... Args>
-using EuclideanInnerProduct = std::function<Scalar(const Vector &V1, const Vector &V2, Args &...args)>;
+// Euclidean specialisations (reference Riemannian/Concepts.h:162-190): one type `Vector` for points and tangent
+// vectors; `Vector` provides `double dot(const Vector &) const`.
+template <typename Vector, typename... Args>
+using EuclideanVectorField = VectorField<Vector, Vector, Args...>;
+
+template <typename Vector, typename... Args>
+using EuclideanLinearOperator = LinearOperator<Vector, Vector, Args...>;
+
+template <typename Vector, typename... Args>
+using EuclideanLinearOperatorConstructor = LinearOperatorConstructor<Vector, Vector, Args...>;
+
+template <typename Vector, typename... Args>
+using EuclideanQuadraticModel = QuadraticModel<Vector, Vector, Args...>;
 
 template <typename Vector, typename Scalar = double, typename... Args>
-RiemannianMetric<Vector, Vector, Scalar, Args...>
-EuclideanMetric(const EuclideanInnerProduct<Vector, Scalar, Args...> &inner_product) {
-  return [inner_product](const Vector &, const Vector &V1, const Vector &V2, Args &...args) {
-    return inner_product(V1, V2, args...);
-  };
+Scalar EuclideanInnerProduct(const Vector &V1, const Vector &V2, Args &...) {
+  return V1.dot(V2);
+}
+
+template <typename Vector, typename Scalar = double, typename... Args>
+Scalar EuclideanMetric(const Vector &, const Vector &V1, const Vector &V2, Args &...args) {
+  return EuclideanInnerProduct<Vector, Scalar, Args...>(V1, V2, args...);
 }
 
 template <typename Vector, typename... Args>

@@ -273,40 +273,37 @@ TNT(const Objective<Variable, Scalar, Args...> &f, const VectorField<Variable, T
   return TNT<Variable, Tangent, Scalar, Args...>(f, QM, metric, retract, x0, args..., precon, params, user_function);
 }
 
-// Euclidean conveniences (reference TNT.h:757-805).
+// Euclidean conveniences (reference TNT.h:753-805): standard inner product (`Vector::dot`), retraction X + V.
 template <typename Vector, typename Scalar = double, typename... Args>
 using EuclideanTNTUserFunction = TNTUserFunction<Vector, Vector, Scalar, Args...>;
 
 template <typename Vector, typename Scalar = double, typename... Args>
-using EuclideanQuadraticModel = QuadraticModel<Vector, Vector, Args...>;
-
-template <typename Vector, typename Scalar = double, typename... Args>
-using EuclideanLinearOperator = LinearOperator<Vector, Vector, Args...>;
-
-template <typename Vector, typename Scalar = double, typename... Args>
 TNTResult<Vector, Scalar>
-EuclideanTNT(const Objective<Vector, Scalar, Args...> &f, const EuclideanQuadraticModel<Vector, Scalar, Args...> &QM,
-             const EuclideanInnerProduct<Vector, Scalar, Args...> &inner_product, const Vector &x0, Args &...args,
-             const std::optional<EuclideanLinearOperator<Vector, Scalar, Args...>> &precon = std::nullopt,
+EuclideanTNT(const Objective<Vector, Scalar, Args...> &f, const EuclideanQuadraticModel<Vector, Args...> &QM,
+             const Vector &x0, Args &...args,
+             const std::optional<EuclideanLinearOperator<Vector, Args...>> &precon = std::nullopt,
              const TNTParams<Scalar> &params = TNTParams<Scalar>(),
              const std::optional<EuclideanTNTUserFunction<Vector, Scalar, Args...>> &user_function = std::nullopt) {
-  RiemannianMetric<Vector, Vector, Scalar, Args...> metric = EuclideanMetric<Vector, Scalar, Args...>(inner_product);
-  Retraction<Vector, Vector, Args...> retract = [](const Vector &X, const Vector &V, Args &...) { return X + V; };
-  return TNT<Vector, Vector, Scalar, Args...>(f, QM, metric, retract, x0, args..., precon, params, user_function);
+  return TNT<Vector, Vector, Scalar, Args...>(f, QM, EuclideanMetric<Vector, Scalar, Args...>,
+                                              EuclideanRetraction<Vector, Args...>, x0, args..., precon, params,
+                                              user_function);
 }
 
+// gradient + Hessian-constructor form
 template <typename Vector, typename Scalar = double, typename... Args>
 TNTResult<Vector, Scalar>
-EuclideanTNT(const Objective<Vector, Scalar, Args...> &f, const VectorField<Vector, Vector, Args...> &grad_f,
-             const LinearOperatorConstructor<Vector, Vector, Args...> &HC,
-             const EuclideanInnerProduct<Vector, Scalar, Args...> &inner_product, const Vector &x0, Args &...args,
-             const std::optional<EuclideanLinearOperator<Vector, Scalar, Args...>> &precon = std::nullopt,
+EuclideanTNT(const Objective<Vector, Scalar, Args...> &f, const EuclideanVectorField<Vector, Args...> &nabla_f,
+             const EuclideanLinearOperatorConstructor<Vector, Args...> &HessianConstructor, const Vector &x0,
+             Args &...args, const std::optional<EuclideanLinearOperator<Vector, Args...>> &precon = std::nullopt,
              const TNTParams<Scalar> &params = TNTParams<Scalar>(),
              const std::optional<EuclideanTNTUserFunction<Vector, Scalar, Args...>> &user_function = std::nullopt) {
-  RiemannianMetric<Vector, Vector, Scalar, Args...> metric = EuclideanMetric<Vector, Scalar, Args...>(inner_product);
-  Retraction<Vector, Vector, Args...> retract = [](const Vector &X, const Vector &V, Args &...) { return X + V; };
-  return TNT<Vector, Vector, Scalar, Args...>(f, grad_f, HC, metric, retract, x0, args..., precon, params,
-                                              user_function);
+  EuclideanQuadraticModel<Vector, Args...> QM = [&nabla_f, &HessianConstructor](
+                                                    const Vector &X, Vector &grad,
+                                                    EuclideanLinearOperator<Vector, Args...> &Hess, Args &...a) {
+    grad = nabla_f(X, a...);
+    Hess = HessianConstructor(X, a...);
+  };
+  return EuclideanTNT<Vector, Scalar, Args...>(f, QM, x0, args..., precon, params, user_function);
 }
 
 }  // namespace Riemannian

@@ -12,6 +12,7 @@
 
 #include "Optimization/LinearAlgebra/IterativeSolvers.h"
 #include "Optimization/Riemannian/Concepts.h"
+#include "Optimization/Riemannian/GradientDescent.h"
 #include "Optimization/Riemannian/TNT.h"
 #include "optimization_b200.h"
 
@@ -81,6 +82,12 @@ class DeviceMatrix {
     return h;
   }
   DeviceMatrix like() const { return DeviceMatrix(ctx_, n_, p_); }
+  // Frobenius inner product with the exact device reduction (what the Euclidean helpers of the header layer call)
+  double dot(const DeviceMatrix &o) const {
+    double r = 0;
+    check(ctx_, ob200_dot(ctx_, size(), d_, o.d_, &r));
+    return r;
+  }
 
   // out = a * x + b * y  (device level-1 kernel)
   static DeviceMatrix axpby(double a, const DeviceMatrix &x, double b, const DeviceMatrix *y) {
@@ -270,6 +277,16 @@ class SphereRayleigh {
       return f;
     };
   }
+  // grad f(x) = 2 (A x - (x^T A x) x): the VectorField GradientDescent takes
+  Riemannian::VectorField<DeviceMatrix, DeviceMatrix> gradient() const {
+    return [this](const DeviceMatrix &x) {
+      DeviceMatrix Ax = x.like(), grad = x.like();
+      double f = 0;
+      check(ctx_, ob200_sphere_model(ctx_, n_, k_, d_.data(), Ut_.data(), ldu_, sigma_.data(), x.data(), Ax.data(), &f,
+                                     grad.data()));
+      return grad;
+    };
+  }
   Riemannian::QuadraticModel<DeviceMatrix, DeviceMatrix> quadratic_model() const {
     return [this](const DeviceMatrix &x, DeviceMatrix &grad,
                   Riemannian::LinearOperator<DeviceMatrix, DeviceMatrix> &Hess) {
@@ -327,6 +344,9 @@ struct InnerViews<b200::DeviceMatrix, b200::DeviceMatrix, double, Args...> {
   static LinearAlgebra::InnerProduct<M, double, Args...>
   inner_product(const M &x, const RiemannianMetric<M, M, double, Args...> &metric) {
     if (metric.template target<b200::FrobeniusMetric>()) return b200::FrobeniusProduct{};
+    using EuclideanFn = double (*)(const M &, const M &, const M &, Args &...);      // EuclideanTNT's metric
+    if (const EuclideanFn *fn = metric.template target<EuclideanFn>())
+      if (*fn == &EuclideanMetric<M, double, Args...>) return b200::FrobeniusProduct{};
     return [&x, &metric](const M &a1, const M &a2, Args &...a) -> double { return metric(x, a1, a2, a...); };
   }
 };

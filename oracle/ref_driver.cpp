@@ -760,4 +760,58 @@ int ref_s2_gd(const double *x0, const double *Ppt, uint64_t max_iterations,
   return 0;
 }
 
+// Reference GradientDescent on the sphere Rayleigh-quotient model (same functors as ref_sphere_tnt).
+int ref_sphere_gd(uint64_t n, uint64_t k, const double *d, const double *U,
+                  const double *sigma, const double *x0, uint64_t max_iterations,
+                  double gradient_tolerance, double *x_out, int *status,
+                  uint64_t *n_iter, uint64_t *ls_total, double *f_out,
+                  double *gradnorm_out) {
+  using V = HostMat;
+  SphereOp op{n, k, d, U, sigma};
+  Objective<V, double> f = [&](const V &x) {
+    V Ax(n);
+    op.apply(x.data(), Ax.data());
+    return oracle::dot(x, Ax);
+  };
+  Riemannian::VectorField<V, V> grad = [&](const V &x) {
+    V Ax(n);
+    op.apply(x.data(), Ax.data());
+    const double xAx = oracle::dot(x, Ax);
+    V g(n);
+    double *gd = g.data();
+    const double *ax = Ax.data(), *xd = x.data();
+    for (size_t i = 0; i < n; ++i) gd[i] = 2.0 * (ax[i] - xAx * xd[i]);
+    return g;
+  };
+  Riemannian::RiemannianMetric<V, V, double> metric =
+      [](const V &, const V &a, const V &b) { return oracle::dot(a, b); };
+  Riemannian::Retraction<V, V> retract = [n](const V &x, const V &v) {
+    V z(n);
+    double *zd = z.data();
+    const double *xd = x.data(), *vd = v.data();
+    for (size_t i = 0; i < n; ++i) zd[i] = xd[i] + vd[i];
+    const double inv = 1.0 / std::sqrt(oracle::dot(z, z));
+    for (size_t i = 0; i < n; ++i) zd[i] *= inv;
+    return z;
+  };
+  Riemannian::GradientDescentParams<double> params;
+  params.max_iterations = size_t(max_iterations);
+  params.gradient_tolerance = gradient_tolerance;
+  try {
+    V X0(x0, n);
+    auto res = Riemannian::GradientDescent<V, V, double>(f, grad, metric, retract, X0, params);
+    std::memcpy(x_out, res.x.data(), n * sizeof(double));
+    *status = int(res.status);
+    *n_iter = res.gradient_norms.size();
+    uint64_t ls = 0;
+    for (size_t v : res.linesearch_iterations) ls += v;
+    *ls_total = ls;
+    *f_out = res.f;
+    *gradnorm_out = res.gradfx_norm;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+
 } // extern "C"

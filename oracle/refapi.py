@@ -181,6 +181,22 @@ class RefOracle:
                     gradfx_norm=gn.value)
 
 
+    def sphere_gd(self, prob, x0, max_iterations=100, gradient_tolerance=1e-6):
+        x = np.zeros(prob.n)
+        st, it, ls = C.c_int(-1), C.c_uint64(0), C.c_uint64(0)
+        f, gn = C.c_double(0), C.c_double(0)
+        self.lib.ref_sphere_gd.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, C.c_uint64, C.c_double,
+                                           _dp, C.POINTER(C.c_int), _u64p, _u64p, C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double)]
+        rc = self.lib.ref_sphere_gd(prob.n, prob.k, _d(prob.d), _d(prob.U), _d(prob.sigma), _d(x0),
+                                    max_iterations, gradient_tolerance, _d(x), C.byref(st), C.byref(it),
+                                    C.byref(ls), C.byref(f), C.byref(gn))
+        if rc:
+            raise ValueError("std::invalid_argument from reference GradientDescent")
+        return dict(x=x, status_code=st.value, iterations=int(it.value), linesearch_total=int(ls.value),
+                    f=f.value, gradfx_norm=gn.value)
+
+
 class RefStiefel:
     def __init__(self, ora, prob):
         self.ora, self.prob = ora, prob

@@ -109,6 +109,13 @@ def main():
     arrays["sphere100_tnt_x"] = r.pop("x")
     r["params"] = default_tnt_params()
     out["sphere100_tnt"] = r
+    # --- GradientDescent (reference GradientDescent.h; tests/GradientDescent_unit_test.cpp shape) ----------
+    r = R.s2_gd(x0, Ppt, max_iterations=1000, gradient_tolerance=1e-6)
+    r["x"] = r["x"].tolist()
+    out["s2_gd"] = r
+    r = R.sphere_gd(prob, prob.x0, max_iterations=60, gradient_tolerance=1e-6)      # prob = make_sphere(100, 16)
+    arrays["sphere100_gd_x"] = r.pop("x")
+    out["sphere100_gd"] = r
     with open(os.path.join(HERE, "golden.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "golden_arrays.npz"), **arrays)

@@ -45,5 +45,23 @@ int main(int argc, char **argv) {
   FILE *o = fopen(argv[2], "wb");
   fwrite(x.data(), 8, x.size(), o);
   fclose(o);
+
+  // ---- GradientDescent<DeviceMatrix, DeviceMatrix, double> on the same model (level-1 kernels + model / retraction
+  //      entry points; reference GradientDescent.h:124-398), same parameters as the golden run ----
+  if (argc > 3) {
+    Riemannian::GradientDescentParams<double> gp;
+    gp.max_iterations = 60;
+    gp.gradient_tolerance = 1e-6;
+    auto gd = Riemannian::GradientDescent<DeviceMatrix, DeviceMatrix, double>(prob.objective(), prob.gradient(),
+                                                                             prob.metric(), prob.retraction(), X, gp);
+    size_t ls = 0;
+    for (size_t v : gd.linesearch_iterations) ls += v;
+    printf("{\"case\": \"sphere_gd\", \"status_code\": %d, \"iterations\": %zu, \"linesearch_total\": %zu, \"f\": %.17g, "
+           "\"gradfx_norm\": %.17g}\n", int(gd.status), gd.gradient_norms.size(), ls, gd.f, gd.gradfx_norm);
+    const std::vector<double> xg = gd.x.to_host();
+    FILE *og = fopen(argv[3], "wb");
+    fwrite(xg.data(), 8, xg.size(), og);
+    fclose(og);
+  }
   return 0;
 }

@@ -55,9 +55,23 @@ def test_host_headers_match_reference_golden(golden):
     assert got["invalid_argument"]["thrown"] == 1
 
 
+def test_gradient_descent_header_matches_reference_golden(golden):
+    """OUR Riemannian/GradientDescent.h (+ EuclideanGradientDescent / EuclideanTNT with the reference's signatures)."""
+    rec, _ = golden
+    exe = _compile("gd_host_check", link=False)
+    got = _lines(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+    g, r = got["s2_gd"], rec["s2_gd"]
+    assert g["status_code"] == r["status_code"] == 0 and g["iterations"] == r["iterations"]
+    assert g["f"] == r["f"] and g["gradfx_norm"] == r["gradfx_norm"] and g["x"] == r["x"]      # bit for bit
+    assert g["hook_calls"] == g["accepted"] == r["iterations"] - 1        # user function: once per accepted step
+    assert got["gd_invalid_argument"]["thrown"] == 4                      # GradientDescent.h:141-161
+    e = got["euclidean"]
+    assert e["tnt_status"] == 0 and e["tnt_err"] < 1e-12 and e["gd_err"] < 1e-6
+
+
 def test_header_layer_has_reference_layout():
     for rel in ("Optimization/Base/Concepts.h", "Optimization/Riemannian/Concepts.h",
-                "Optimization/Riemannian/TNT.h", "Optimization/LinearAlgebra/Concepts.h",
+                "Optimization/Riemannian/TNT.h", "Optimization/Riemannian/GradientDescent.h", "Optimization/LinearAlgebra/Concepts.h",
                 "Optimization/LinearAlgebra/IterativeSolvers.h", "Optimization/Util/Stopwatch.h",
                 "Optimization/b200/Device.h", "optimization_b200.h"):
         assert os.path.exists(os.path.join(ROOT, "include", rel)), rel
@@ -113,8 +127,15 @@ def test_device_sphere_tnt_matches_reference_golden(golden, tmp_path):
         fh.write(struct.pack("<QQ", prob.n, prob.k))
         for a in (prob.d, prob.U, prob.sigma, prob.x0):
             fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
-    xo = tmp_path / "x.bin"
-    out = subprocess.run([exe, str(f), str(xo)], check=True, capture_output=True, text=True).stdout
+    xo, xg = tmp_path / "x.bin", tmp_path / "xgd.bin"
+    out = subprocess.run([exe, str(f), str(xo), str(xg)], check=True, capture_output=True, text=True).stdout
+    gd, rgd = _lines(out)["sphere_gd"], rec["sphere100_gd"]
+    # GradientDescent<DeviceMatrix>: same status, iteration count and line-search trial count as the reference run
+    assert (gd["status_code"], gd["iterations"], gd["linesearch_total"]) == \
+        (rgd["status_code"], rgd["iterations"], rgd["linesearch_total"])
+    assert abs(gd["f"] - rgd["f"]) <= 1e-12 * abs(rgd["f"])
+    xgd = np.fromfile(xg)
+    assert np.linalg.norm(xgd - arr["sphere100_gd_x"]) / np.linalg.norm(arr["sphere100_gd_x"]) < 1e-10
     g = _lines(out)["sphere_tnt"]
     r = rec["sphere100_tnt"]
     assert g["status_code"] == r["status_code"]                          # bit-exact termination status
