@@ -270,6 +270,16 @@ def make_sphere_critical_device(n: int, k: int = 16, seed: int = 11, x_noise: fl
     return d, Ut, sigma, x0, g
 
 
+def make_projected(n: int = 50, mc: int = 3, seed: int = 61):
+    """Equality-constrained quadratic model for the constraint-preconditioned STPCG tests (the shape of the
+    reference's tests/IterativeSolvers_unit_test.cpp:316-496): H = diag(h) SPD, M = diag(m) SPD, A: mc x n, g."""
+    h = 1000.0 + 2000.0 * uniform01(seed, 0, n)
+    m = 1000.0 + 2000.0 * uniform01(seed + 1, 0, n)
+    A = 1000.0 * (2.0 * uniform01(seed + 2, 0, mc * n) - 1.0).reshape(mc, n)
+    g = 2.0 * uniform01(seed + 3, 0, n) - 1.0
+    return h, m, np.ascontiguousarray(A), g
+
+
 @dataclasses.dataclass
 class DiagProblem:
     """Diagonal SPD Hessian with optional Jacobi preconditioner (the shape of the

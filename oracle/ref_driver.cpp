@@ -18,6 +18,7 @@
 #include "Optimization/Riemannian/TNT.h"
 
 #include "hostmat.hpp"
+#include "dense_lu.hpp"
 
 #include <cmath>
 #include <cstdint>
@@ -808,6 +809,58 @@ int ref_sphere_gd(uint64_t n, uint64_t k, const double *d, const double *U,
     *ls_total = ls;
     *f_out = res.f;
     *gradnorm_out = res.gradfx_norm;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+
+// Constraint-preconditioned (projected) STPCG, the shape of the reference's tests
+// tests/IterativeSolvers_unit_test.cpp:316-496: H = diag(h), M = diag(m), constraint A s = 0
+// (A: mc x n row-major), preconditioner = KKT solve [M A^T; A 0][v; lambda] = [r; 0] (dense LU stand-in
+// for UmfPackLU), At(lambda) = A^T lambda.
+int ref_stpcg_projected(uint64_t n, uint64_t mc, const double *hdiag, const double *mdiag,
+                        const double *A, const double *g, double Delta,
+                        uint64_t max_iterations, double kappa_fgr, double theta,
+                        double *s_out, double *update_step_M_norm, uint64_t *num_iterations) {
+  using V = HostMat;
+  oracle::DenseLU lu;
+  if (!lu.factor(oracle::kkt_matrix(mdiag, A, n, mc), n + mc)) return 2;
+  LinearAlgebra::SymmetricLinearOperator<V> H = [&](const V &v) {
+    V out(n);
+    for (size_t i = 0; i < n; ++i) out.d[i] = hdiag[i] * v.d[i];
+    return out;
+  };
+  LinearAlgebra::InnerProduct<V> ip = [](const V &a, const V &b) { return oracle::dot(a, b); };
+  LinearAlgebra::STPCGPreconditioner<V, V> P = [&](const V &r) {
+    std::vector<double> w(n + mc, 0.0);
+    for (size_t i = 0; i < n; ++i) w[i] = r.d[i];
+    const std::vector<double> z = lu.solve(w);
+    V x(n), l(mc);
+    for (size_t i = 0; i < n; ++i) x.d[i] = z[i];
+    for (size_t c = 0; c < mc; ++c) l.d[c] = z[n + c];
+    return std::make_pair(x, l);
+  };
+  LinearAlgebra::LinearOperator<V, V> At = [&](const V &l) {
+    V out(n);
+    for (size_t i = 0; i < n; ++i) {
+      double acc = 0;
+      for (size_t c = 0; c < mc; ++c) acc += A[c * n + i] * l.d[c];
+      out.d[i] = acc;
+    }
+    return out;
+  };
+  try {
+    V G(g, n);
+    size_t iters = 0;
+    double mnorm = 0;
+    std::optional<LinearAlgebra::STPCGPreconditioner<V, V>> Pop(P);
+    std::optional<LinearAlgebra::LinearOperator<V, V>> Atop(At);
+    V s = LinearAlgebra::STPCG<V, V>(G, H, ip, mnorm, iters, Delta, size_t(max_iterations),
+                                     kappa_fgr, theta, Pop, Atop);
+    std::memcpy(s_out, s.data(), n * sizeof(double));
+    *update_step_M_norm = mnorm;
+    *num_iterations = iters;
   } catch (const std::invalid_argument &) {
     return 1;
   }

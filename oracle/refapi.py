@@ -181,6 +181,19 @@ class RefOracle:
                     gradfx_norm=gn.value)
 
 
+    def stpcg_projected(self, h, m, A, g, Delta, max_iterations, kappa_fgr, theta):
+        """Reference STPCG with constraint preconditioning (P = KKT solve, At = A^T); A: mc x n."""
+        mc, n = A.shape
+        s = np.zeros(n)
+        mn, it = C.c_double(0), C.c_uint64(0)
+        self.lib.ref_stpcg_projected.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, C.c_double, C.c_uint64,
+                                                 C.c_double, C.c_double, _dp, C.POINTER(C.c_double), _u64p]
+        rc = self.lib.ref_stpcg_projected(n, mc, _d(h), _d(m), _d(np.ascontiguousarray(A)), _d(g), Delta,
+                                          max_iterations, kappa_fgr, theta, _d(s), C.byref(mn), C.byref(it))
+        if rc:
+            raise ValueError("reference projected STPCG failed")
+        return s, float(mn.value), int(it.value)
+
     def sphere_gd(self, prob, x0, max_iterations=100, gradient_tolerance=1e-6):
         x = np.zeros(prob.n)
         st, it, ls = C.c_int(-1), C.c_uint64(0), C.c_uint64(0)

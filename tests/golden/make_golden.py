@@ -109,6 +109,13 @@ def main():
     arrays["sphere100_tnt_x"] = r.pop("x")
     r["params"] = default_tnt_params()
     out["sphere100_tnt"] = r
+    # --- constraint-preconditioned (projected) STPCG (tests/IterativeSolvers_unit_test.cpp:316-496 shape) ----
+    h, m, A, g = P.make_projected(50, 3)
+    for name, kw in (("projected_exact", dict(Delta=DBL_MAX, max_iterations=250, kappa_fgr=1e-8, theta=.7)),
+                     ("projected_trunc", dict(Delta=1e-4, max_iterations=250, kappa_fgr=.1, theta=.7))):
+        s, mn, it = R.stpcg_projected(h, m, A, g, **kw)
+        out[name] = dict(update_step_M_norm=mn, num_iterations=it, args=kw, problem="make_projected(50, 3)")
+        arrays[name + "_s"] = s
     # --- GradientDescent (reference GradientDescent.h; tests/GradientDescent_unit_test.cpp shape) ----------
     r = R.s2_gd(x0, Ppt, max_iterations=1000, gradient_tolerance=1e-6)
     r["x"] = r["x"].tolist()

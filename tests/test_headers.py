@@ -69,6 +69,37 @@ def test_gradient_descent_header_matches_reference_golden(golden):
     assert e["tnt_status"] == 0 and e["tnt_err"] < 1e-12 and e["gd_err"] < 1e-6
 
 
+def test_projected_stpcg_matches_reference_golden(golden, tmp_path):
+    """Constraint-preconditioned (projected) path of OUR IterativeSolvers.h (P + At, Multiplier type) and the
+    per-iteration user hook; assertions of the reference's tests/IterativeSolvers_unit_test.cpp:316-496."""
+    rec, arr = golden
+    exe = _compile("projected_host_check", link=False)
+    h, m, A, g = P.make_projected(50, 3)
+    f = tmp_path / "proj.bin"
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<QQ", 50, 3))
+        for a in (h, m, A, g):
+            fh.write(np.ascontiguousarray(a).tobytes())
+    got = _lines(subprocess.run([exe, str(f)], check=True, capture_output=True, text=True).stdout)
+    for name in ("projected_exact", "projected_trunc"):
+        gt, r = got[name], rec[name]
+        assert gt["num_iterations"] == r["num_iterations"] and gt["update_step_M_norm"] == r["update_step_M_norm"]
+        assert np.array_equal(np.array(gt["s"]), arr[name + "_s"])                      # bit for bit
+        assert gt["As_norm"] < 1e-9                                                     # s in ker(A)  (:400)
+        assert abs(gt["s_M_norm"] - gt["update_step_M_norm"]) <= 1e-6 * gt["s_M_norm"]  # M-norm recurrence (:408)
+    # exact solve == primal part of the KKT solution [H A^T; A 0][s; l] = [-g; 0]  (:326-404)
+    n, mc = 50, 3
+    K = np.zeros((n + mc, n + mc))
+    K[:n, :n] = np.diag(h)
+    K[:n, n:] = A.T
+    K[n:, :n] = A
+    s_gt = np.linalg.solve(K, np.concatenate([-g, np.zeros(mc)]))[:n]
+    s = np.array(got["projected_exact"]["s"])
+    assert np.linalg.norm(s - s_gt) / np.linalg.norm(s_gt) < 1e-6
+    assert got["projected_trunc"]["update_step_M_norm"] == 1e-4                         # truncated at the boundary
+    assert got["user_hook"] == {"case": "user_hook", "calls": 3, "num_iterations": 2}  # hook stops the loop (l.365-369)
+
+
 def test_header_layer_has_reference_layout():
     for rel in ("Optimization/Base/Concepts.h", "Optimization/Riemannian/Concepts.h",
                 "Optimization/Riemannian/TNT.h", "Optimization/Riemannian/GradientDescent.h", "Optimization/LinearAlgebra/Concepts.h",
