@@ -280,6 +280,33 @@ def make_projected(n: int = 50, mc: int = 3, seed: int = 61):
     return h, m, np.ascontiguousarray(A), g
 
 
+LSQR_A43 = np.array([[10., 5., 10.], [2., 9., 8.], [10., 2., 10.], [10., 5., 7.]])   # the 4 x 3 system of the
+LSQR_B4 = np.array([1., 9., 10., 2.])                                                # reference's LSQR tests
+
+
+def lsqr_cases():
+    """LSQR problems: the five cases of the reference's tests/IterativeSolvers_unit_test.cpp:517-700 and a larger
+    seeded 60 x 40 system (plain, Tikhonov, trust-region).  name -> (A, b, kwargs of LSQR)."""
+    A0 = np.zeros((3, 2))
+    A0[1:, :] = np.eye(2)
+    xls = np.linalg.lstsq(LSQR_A43, LSQR_B4, rcond=None)[0]
+    m, n = 60, 40
+    Abig = (2.0 * uniform01(71, 0, m * n) - 1.0).reshape(m, n)
+    bbig = 2.0 * uniform01(72, 0, m) - 1.0
+    big = float(np.sqrt(np.finfo(np.float64).max))
+    return {
+        "lsqr_trivial": (A0, np.array([1., 0., 0.]), dict()),
+        "lsqr_consistent": (LSQR_A43, LSQR_A43 @ np.array([1., 2., 3.]), dict(max_iterations=1000, lam=0.0, btol=1e-6)),
+        "lsqr_inconsistent": (LSQR_A43, LSQR_B4, dict(max_iterations=1000, lam=0.0, btol=0.0, Atol=1e-6)),
+        "lsqr_trust_region": (LSQR_A43, LSQR_B4, dict(max_iterations=1000, lam=0.0, btol=0.0, Atol=0.0, cond_limit=1e12,
+                                                      Delta=float(np.linalg.norm(xls)) / 2)),
+        "lsqr_tikhonov": (LSQR_A43, LSQR_B4, dict(max_iterations=1000, lam=1.0, btol=0.0, Atol=1e-6)),
+        "lsqr_big": (Abig, bbig, dict(max_iterations=500, lam=0.0, btol=1e-10, Atol=1e-10, cond_limit=1e12, Delta=big)),
+        "lsqr_big_tikhonov_tr": (Abig, bbig, dict(max_iterations=500, lam=0.5, btol=1e-10, Atol=1e-10, cond_limit=1e12,
+                                                  Delta=0.3)),
+    }
+
+
 @dataclasses.dataclass
 class DiagProblem:
     """Diagonal SPD Hessian with optional Jacobi preconditioner (the shape of the

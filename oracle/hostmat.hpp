@@ -64,12 +64,17 @@ struct HostMat {
   HostMat &operator+=(const HostMat &o);
   HostMat &operator-=(const HostMat &o);
   HostMat &operator*=(int a);
+  HostMat &operator/=(double a) {
+    for (auto &v : d) v /= a;
+    return *this;
+  }
 };
 
 inline Scaled operator*(double a, const HostMat &v) { return Scaled{a, &v}; }
 inline Scaled operator*(int a, const HostMat &v) { return Scaled{double(a), &v}; }
 inline Scaled operator-(const HostMat &v) { return Scaled{-1.0, &v}; }
 inline Sum operator+(const HostMat &x, const Scaled &s) { return Sum{&x, s.a, s.v}; }
+inline Sum operator-(const HostMat &x, const Scaled &s) { return Sum{&x, -s.a, s.v}; }   // x - a y == x + (-a) y, bit for bit
 inline Sum2 operator+(const Scaled &s1, const Scaled &s2) {
   return Sum2{s1.a, s1.v, s2.a, s2.v};
 }

@@ -867,4 +867,45 @@ int ref_stpcg_projected(uint64_t n, uint64_t mc, const double *hdiag, const doub
   return 0;
 }
 
+// Reference LSQR (IterativeSolvers.h:552-855) on a dense m x n matrix (row-major), the shape of the
+// reference's tests/IterativeSolvers_unit_test.cpp:498-700.
+int ref_lsqr(uint64_t m, uint64_t n, const double *A, const double *b, uint64_t max_iterations,
+             double lambda, double btol, double Atol, double cond_limit, double Delta,
+             double *x_out, double *xnorm_out, uint64_t *num_iterations) {
+  using V = HostMat;
+  LinearAlgebra::LinearOperator<V, V> Aop = [&](const V &x) {
+    V out(m);
+    for (size_t i = 0; i < m; ++i) {
+      double acc = 0;
+      for (size_t j = 0; j < n; ++j) acc += A[i * n + j] * x.d[j];
+      out.d[i] = acc;
+    }
+    return out;
+  };
+  LinearAlgebra::LinearOperator<V, V> Atop = [&](const V &y) {
+    V out(n);
+    for (size_t j = 0; j < n; ++j) {
+      double acc = 0;
+      for (size_t i = 0; i < m; ++i) acc += A[i * n + j] * y.d[i];
+      out.d[j] = acc;
+    }
+    return out;
+  };
+  LinearAlgebra::InnerProduct<V> ip = [](const V &a, const V &c) { return oracle::dot(a, c); };
+  try {
+    V B(b, m);
+    double xnorm = 0;
+    size_t iters = 0;
+    V x = LinearAlgebra::LSQR<V>(Aop, Atop, B, ip, xnorm, iters, size_t(max_iterations), lambda, btol,
+                                 Atol, cond_limit, Delta);
+    if (x.size() == n) std::memcpy(x_out, x.data(), n * sizeof(double));
+    else std::memset(x_out, 0, n * sizeof(double));
+    *xnorm_out = xnorm;
+    *num_iterations = iters;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+
 } // extern "C"

@@ -194,6 +194,21 @@ class RefOracle:
             raise ValueError("reference projected STPCG failed")
         return s, float(mn.value), int(it.value)
 
+    def lsqr(self, A, b, max_iterations=1000, lam=0.0, btol=1e-6, Atol=1e-6, cond_limit=1e8, Delta=None):
+        """Reference LSQR on a dense matrix."""
+        m, n = A.shape
+        if Delta is None:
+            Delta = float(np.sqrt(np.finfo(np.float64).max))
+        x = np.zeros(n)
+        xn, it = C.c_double(0), C.c_uint64(0)
+        self.lib.ref_lsqr.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, C.c_uint64, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, _dp, C.POINTER(C.c_double), _u64p]
+        rc = self.lib.ref_lsqr(m, n, _d(np.ascontiguousarray(A, dtype=np.float64)), _d(b), max_iterations, lam, btol,
+                               Atol, cond_limit, Delta, _d(x), C.byref(xn), C.byref(it))
+        if rc:
+            raise ValueError("std::invalid_argument from reference LSQR")
+        return x, float(xn.value), int(it.value)
+
     def sphere_gd(self, prob, x0, max_iterations=100, gradient_tolerance=1e-6):
         x = np.zeros(prob.n)
         st, it, ls = C.c_int(-1), C.c_uint64(0), C.c_uint64(0)

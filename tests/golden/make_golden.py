@@ -116,6 +116,10 @@ def main():
         s, mn, it = R.stpcg_projected(h, m, A, g, **kw)
         out[name] = dict(update_step_M_norm=mn, num_iterations=it, args=kw, problem="make_projected(50, 3)")
         arrays[name + "_s"] = s
+    # --- LSQR (reference IterativeSolvers.h:552-855; tests/IterativeSolvers_unit_test.cpp:517-700 cases) -------
+    for name, (Am, bv, kw) in P.lsqr_cases().items():
+        x, xn, it = R.lsqr(Am, bv, **kw)
+        out[name] = dict(xnorm=xn, num_iterations=it, args=kw, x=x.tolist())
     # --- GradientDescent (reference GradientDescent.h; tests/GradientDescent_unit_test.cpp shape) ----------
     r = R.s2_gd(x0, Ppt, max_iterations=1000, gradient_tolerance=1e-6)
     r["x"] = r["x"].tolist()

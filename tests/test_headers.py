@@ -100,6 +100,55 @@ def test_projected_stpcg_matches_reference_golden(golden, tmp_path):
     assert got["user_hook"] == {"case": "user_hook", "calls": 3, "num_iterations": 2}  # hook stops the loop (l.365-369)
 
 
+def test_lsqr_header_matches_reference_golden(golden, tmp_path):
+    """OUR LSQR (LinearAlgebra/IterativeSolvers.h) on the five cases of the reference's LSQR unit tests
+    (tests/IterativeSolvers_unit_test.cpp:517-700) + a seeded 60 x 40 system: bit for bit against the reference
+    header, plus that test file's own assertions."""
+    rec, _ = golden
+    exe = _compile("lsqr_host_check", link=False)
+    cases = P.lsqr_cases()
+    big = float(np.sqrt(np.finfo(np.float64).max))
+    f = tmp_path / "lsqr.bin"
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<Q", len(cases)))
+        for name, (A, b, kw) in cases.items():
+            m, n = A.shape
+            fh.write(struct.pack("<QQ", m, n))
+            fh.write(np.ascontiguousarray(A).tobytes())
+            fh.write(np.ascontiguousarray(b).tobytes())
+            fh.write(struct.pack("<Q5d", kw.get("max_iterations", 1000), kw.get("lam", 0.0), kw.get("btol", 1e-6),
+                                 kw.get("Atol", 1e-6), kw.get("cond_limit", 1e8), kw.get("Delta", big)))
+    out = subprocess.run([exe, str(f)], check=True, capture_output=True, text=True).stdout
+    lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    got = {name: d for name, d in zip(cases, lines)}
+    for name in cases:
+        assert got[name]["num_iterations"] == rec[name]["num_iterations"], name
+        assert got[name]["xnorm"] == rec[name]["xnorm"] and got[name]["x"] == rec[name]["x"], name     # bit for bit
+    A, b = P.LSQR_A43, P.LSQR_B4
+    # :517-557 x = 0 is stationary: immediate return
+    assert got["lsqr_trivial"]["num_iterations"] == 0 and got["lsqr_trivial"]["xnorm"] == 0
+    # :560-597 consistent system: relative residual, reported norm, iteration count
+    x = np.array(got["lsqr_consistent"]["x"])
+    bc = A @ np.array([1., 2., 3.])
+    assert np.linalg.norm(A @ x - bc) < 1e-6 * np.linalg.norm(bc)
+    assert abs(got["lsqr_consistent"]["xnorm"] - np.linalg.norm(x)) < 1e-6 * np.linalg.norm(x)
+    assert got["lsqr_consistent"]["num_iterations"] < 12
+    # :600-633 inconsistent system: least-squares solution
+    xls = np.linalg.lstsq(A, b, rcond=None)[0]
+    x = np.array(got["lsqr_inconsistent"]["x"])
+    assert np.linalg.norm(x - xls) < 1e-5 * np.linalg.norm(xls)
+    # :637-690 trust region binding: terminates on the boundary and still reduces the residual
+    x = np.array(got["lsqr_trust_region"]["x"])
+    Delta = np.linalg.norm(xls) / 2
+    assert abs(got["lsqr_trust_region"]["xnorm"] - Delta) < 1e-9 and abs(np.linalg.norm(x) - Delta) < 1e-9
+    assert np.linalg.norm(A @ x - b) < np.linalg.norm(b)
+    # :693-735 Tikhonov: normal equations (A^T A + lambda I) x = A^T b
+    x = np.array(got["lsqr_tikhonov"]["x"])
+    xt = np.linalg.solve(A.T @ A + np.eye(3), A.T @ b)
+    assert np.linalg.norm(x - xt) < 1e-5 * np.linalg.norm(xt)
+    assert lines[-1] == {"case": "lsqr_invalid_argument", "thrown": 5}                  # IterativeSolvers.h:568-587
+
+
 def test_header_layer_has_reference_layout():
     for rel in ("Optimization/Base/Concepts.h", "Optimization/Riemannian/Concepts.h",
                 "Optimization/Riemannian/TNT.h", "Optimization/Riemannian/GradientDescent.h", "Optimization/LinearAlgebra/Concepts.h",
