@@ -307,6 +307,21 @@ def lsqr_cases():
     }
 
 
+def tnls_sine_cases(m: int = 100):
+    """Curve-fitting problem of the reference's tests/TNLS_unit_test.cpp: y = sin(omega t + phi) on t = linspace(-pi, pi, m),
+    omega = pi/2, phi = pi/4, start (1, 1); noiseless root finding, noisy least squares, noisy + preconditioner.
+    name -> (t, y, kwargs)."""
+    t = np.linspace(-np.pi, np.pi, m)
+    y = np.sin(0.5 * np.pi * t + 0.25 * np.pi)
+    z = 0.1 * (2.0 * uniform01(81, 0, m) - 1.0)
+    fit = dict(rel_tol=0.0, grad_tol=1e-6, step_tol=0.0, Delta_tol=1e-10, root_tol=1e-6)
+    return {
+        "tnls_root": (t, y, dict(rel_tol=0.0, grad_tol=0.0, step_tol=0.0, Delta_tol=0.0, root_tol=1e-6)),
+        "tnls_fit": (t, y + z, dict(fit)),
+        "tnls_fit_precon": (t, y + z, dict(fit, use_precon=True)),
+    }
+
+
 @dataclasses.dataclass
 class DiagProblem:
     """Diagonal SPD Hessian with optional Jacobi preconditioner (the shape of the

@@ -53,6 +53,8 @@ struct HostMat {
   explicit HostMat(size_t n) : d(n, 0.0) {}
   HostMat(const double *src, size_t n) : d(src, src + n) {}
   HostMat(const Scaled &s);
+  HostMat(const Sum &s);
+  double dot(const HostMat &o) const;   // Euclidean helpers of the reference call V1.dot(V2)
   size_t size() const { return d.size(); }
   double *data() { return d.data(); }
   const double *data() const { return d.data(); }
@@ -75,11 +77,18 @@ inline Scaled operator*(int a, const HostMat &v) { return Scaled{double(a), &v};
 inline Scaled operator-(const HostMat &v) { return Scaled{-1.0, &v}; }
 inline Sum operator+(const HostMat &x, const Scaled &s) { return Sum{&x, s.a, s.v}; }
 inline Sum operator-(const HostMat &x, const Scaled &s) { return Sum{&x, -s.a, s.v}; }   // x - a y == x + (-a) y, bit for bit
+inline Sum operator+(const HostMat &x, const HostMat &y) { return Sum{&x, 1.0, &y}; }    // 1.0 * y is exact
 inline Sum2 operator+(const Scaled &s1, const Scaled &s2) {
   return Sum2{s1.a, s1.v, s2.a, s2.v};
 }
 
 inline HostMat::HostMat(const Scaled &s) : d(s.v->size()) { *this = s; }
+inline HostMat::HostMat(const Sum &s) : d(s.x->size()) { *this = s; }
+inline HostMat operator/(const HostMat &v, double a) {
+  HostMat o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o.d[i] = v.d[i] / a;
+  return o;
+}
 
 inline HostMat &HostMat::operator=(const Scaled &s) {
   if (d.size() != s.v->size()) d.resize(s.v->size());
@@ -180,5 +189,6 @@ inline double dot(const double *x, const double *y, size_t n) {
 inline double dot(const HostMat &x, const HostMat &y) {
   return dot(x.data(), y.data(), x.size());
 }
+inline double HostMat::dot(const HostMat &o) const { return oracle::dot(*this, o); }
 
 } // namespace oracle

@@ -15,6 +15,7 @@
 // oracle/_ref/ only.  Exposed as a plain C ABI for ctypes.
 #include "Optimization/LinearAlgebra/IterativeSolvers.h"
 #include "Optimization/Riemannian/GradientDescent.h"
+#include "Optimization/Riemannian/TNLS.h"
 #include "Optimization/Riemannian/TNT.h"
 
 #include "hostmat.hpp"
@@ -902,6 +903,85 @@ int ref_lsqr(uint64_t m, uint64_t n, const double *A, const double *b, uint64_t 
     else std::memset(x_out, 0, n * sizeof(double));
     *xnorm_out = xnorm;
     *num_iterations = iters;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+
+// Reference TNLS (Riemannian/TNLS.h:265-729) on the curve-fitting problem of the reference's
+// tests/TNLS_unit_test.cpp:  F(beta)_i = y_i - sin(beta_0 t_i + beta_1),  t = linspace(-pi, pi, m),
+// optional right preconditioner M = diag(1 / |J column|) (diagonal stand-in for the test's R^{-1}).
+int ref_tnls_sine(uint64_t m, const double *t, const double *y, const double *beta0, int use_precon,
+                  uint64_t max_iterations, double root_tol, double grad_tol, double rel_tol,
+                  double step_tol, double Delta_tol, double *beta_out, int *status,
+                  uint64_t *n_outer, uint64_t cap, uint64_t *inner_iterations, double *rho_out,
+                  double *radius_out, double *fvals_out, double *f_out, double *gradnorm_out) {
+  using V = HostMat;
+  std::vector<double> Jm(2 * m, 0.0), scale(2, 1.0);    // Jacobian columns, preconditioner diagonal
+  Riemannian::Mapping<V, V> F = [&](const V &b) {
+    V out(m);
+    for (size_t i = 0; i < m; ++i) out.d[i] = y[i] - std::sin(b.d[0] * t[i] + b.d[1]);
+    return out;
+  };
+  Riemannian::JacobianPairFunction<V, V, V> JF = [&](const V &b) {
+    for (size_t i = 0; i < m; ++i) {
+      Jm[m + i] = -std::cos(b.d[0] * t[i] + b.d[1]);
+      Jm[i] = Jm[m + i] * t[i];
+    }
+    for (int c = 0; c < 2; ++c) {
+      double s2 = 0;
+      for (size_t i = 0; i < m; ++i) s2 += Jm[c * m + i] * Jm[c * m + i];
+      scale[c] = 1.0 / std::sqrt(s2);
+    }
+    Riemannian::Jacobian<V, V, V> DF = [&](const V &, const V &v) {
+      V out(m);
+      for (size_t i = 0; i < m; ++i) out.d[i] = Jm[i] * v.d[0] + Jm[m + i] * v.d[1];
+      return out;
+    };
+    Riemannian::JacobianAdjoint<V, V, V> DFt = [&](const V &, const V &w) {
+      V out(2);
+      for (int c = 0; c < 2; ++c) {
+        double acc = 0;
+        for (size_t i = 0; i < m; ++i) acc += Jm[c * m + i] * w.d[i];
+        out.d[c] = acc;
+      }
+      return out;
+    };
+    return std::make_pair(DF, DFt);
+  };
+  Riemannian::LinearOperator<V, V> M = [&](const V &, const V &v) {
+    V out(2);
+    out.d[0] = scale[0] * v.d[0];
+    out.d[1] = scale[1] * v.d[1];
+    return out;
+  };
+  std::optional<Riemannian::TNLSPreconditioner<V, V>> precon;
+  if (use_precon) precon = std::make_pair(M, M);
+  Riemannian::TNLSParams<double> params;
+  params.max_iterations = size_t(max_iterations);
+  params.root_tolerance = root_tol;
+  params.gradient_tolerance = grad_tol;
+  params.relative_decrease_tolerance = rel_tol;
+  params.stepsize_tolerance = step_tol;
+  params.Delta_tolerance = Delta_tol;
+  try {
+    V B0(beta0, 2);
+    auto res = Riemannian::EuclideanTNLS<V>(F, JF, B0, precon, params);
+    beta_out[0] = res.x.d[0];
+    beta_out[1] = res.x.d[1];
+    *status = int(res.status);
+    *n_outer = res.inner_iterations.size();
+    for (size_t i = 0; i < res.inner_iterations.size() && i < cap; ++i) {
+      inner_iterations[i] = res.inner_iterations[i];
+      rho_out[i] = res.rho[i];
+    }
+    for (size_t i = 0; i < res.trust_region_radius.size() && i < cap; ++i) {
+      radius_out[i] = res.trust_region_radius[i];
+      fvals_out[i] = res.objective_values[i];
+    }
+    *f_out = res.f;
+    *gradnorm_out = res.gradfx_norm;
   } catch (const std::invalid_argument &) {
     return 1;
   }

@@ -209,6 +209,30 @@ class RefOracle:
             raise ValueError("std::invalid_argument from reference LSQR")
         return x, float(xn.value), int(it.value)
 
+    def tnls_sine(self, t, y, beta0, use_precon=False, max_iterations=100, root_tol=1e-6, grad_tol=1e-6, rel_tol=1e-6,
+                  step_tol=1e-6, Delta_tol=1e-6, cap=256):
+        """Reference EuclideanTNLS on the sine-fit problem of tests/TNLS_unit_test.cpp."""
+        beta = np.zeros(2)
+        st, n = C.c_int(-1), C.c_uint64(0)
+        inner = np.zeros(cap, dtype=np.uint64)
+        rho, rad, fv = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        f, gn = C.c_double(0), C.c_double(0)
+        dd = C.c_double
+        self.lib.ref_tnls_sine.argtypes = [C.c_uint64, _dp, _dp, _dp, C.c_int, C.c_uint64, dd, dd, dd, dd, dd, _dp,
+                                           C.POINTER(C.c_int), _u64p, C.c_uint64, _u64p, _dp, _dp, _dp,
+                                           C.POINTER(dd), C.POINTER(dd)]
+        rc = self.lib.ref_tnls_sine(t.size, _d(t), _d(y), _d(np.ascontiguousarray(beta0, dtype=np.float64)),
+                                    1 if use_precon else 0, max_iterations, root_tol, grad_tol, rel_tol, step_tol,
+                                    Delta_tol, _d(beta), C.byref(st), C.byref(n), cap, inner.ctypes.data_as(_u64p),
+                                    _d(rho), _d(rad), _d(fv), C.byref(f), C.byref(gn))
+        if rc:
+            raise ValueError("std::invalid_argument from reference TNLS")
+        k = int(n.value)
+        nrec = min(cap, k + 1)
+        return dict(x=beta.tolist(), status_code=st.value, inner_iterations=inner[:k].astype(int).tolist(),
+                    rho=rho[:k].tolist(), trust_region_radius=rad[:nrec].tolist(), objective_values=fv[:nrec].tolist(),
+                    f=f.value, gradfx_norm=gn.value)
+
     def sphere_gd(self, prob, x0, max_iterations=100, gradient_tolerance=1e-6):
         x = np.zeros(prob.n)
         st, it, ls = C.c_int(-1), C.c_uint64(0), C.c_uint64(0)

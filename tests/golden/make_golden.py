@@ -120,6 +120,9 @@ def main():
     for name, (Am, bv, kw) in P.lsqr_cases().items():
         x, xn, it = R.lsqr(Am, bv, **kw)
         out[name] = dict(xnorm=xn, num_iterations=it, args=kw, x=x.tolist())
+    # --- TNLS (reference Riemannian/TNLS.h; tests/TNLS_unit_test.cpp problem) ---------------------------------
+    for name, (tt, yy, kw) in P.tnls_sine_cases().items():
+        out[name] = dict(R.tnls_sine(tt, yy, [1.0, 1.0], **kw), args=kw)
     # --- GradientDescent (reference GradientDescent.h; tests/GradientDescent_unit_test.cpp shape) ----------
     r = R.s2_gd(x0, Ppt, max_iterations=1000, gradient_tolerance=1e-6)
     r["x"] = r["x"].tolist()

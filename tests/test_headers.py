@@ -149,9 +149,46 @@ def test_lsqr_header_matches_reference_golden(golden, tmp_path):
     assert lines[-1] == {"case": "lsqr_invalid_argument", "thrown": 5}                  # IterativeSolvers.h:568-587
 
 
+def test_tnls_header_matches_reference_golden(golden, tmp_path):
+    """OUR Riemannian/TNLS.h (EuclideanTNLS -> TNLS -> LSQR) on the curve-fitting problem of the reference's
+    tests/TNLS_unit_test.cpp (root finding, noisy fit, noisy fit with a right preconditioner)."""
+    rec, _ = golden
+    exe = _compile("tnls_host_check", link=False)
+    cases = P.tnls_sine_cases()
+    f = tmp_path / "tnls.bin"
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<Q", len(cases)))
+        for name, (t, y, kw) in cases.items():
+            fh.write(struct.pack("<Q", t.size))
+            fh.write(np.ascontiguousarray(t).tobytes())
+            fh.write(np.ascontiguousarray(y).tobytes())
+            fh.write(struct.pack("<QQ5d", 1 if kw.get("use_precon") else 0, 100, kw["root_tol"], kw["grad_tol"],
+                                 kw["rel_tol"], kw["step_tol"], kw["Delta_tol"]))
+    out = subprocess.run([exe, str(f)], check=True, capture_output=True, text=True).stdout
+    lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    for (name, (t, y, kw)), g in zip(cases.items(), lines):
+        r = rec[name]
+        assert g["status_code"] == r["status_code"] and g["inner_iterations"] == r["inner_iterations"], name
+        # floating-point traces: identical arithmetic up to libm's sin / cos (same image => bit for bit in practice)
+        for key in ("rho", "trust_region_radius", "objective_values", "x"):
+            assert np.allclose(g[key], r[key], rtol=1e-11, atol=1e-13), (name, key)
+        assert abs(g["f"] - r["f"]) <= 1e-11 * abs(r["f"]) + 1e-15
+    # assertions of the reference's tests (TNLS_unit_test.cpp:118-205)
+    root, fit, fitp = lines
+    t, y, _ = cases["tnls_root"]
+    assert root["status_code"] == 0                                                    # TNLSStatus::Root
+    assert np.linalg.norm(y - np.sin(root["x"][0] * t + root["x"][1])) < 1e-6
+    t, yn, _ = cases["tnls_fit"]
+    noise = np.linalg.norm(yn - y)
+    for g in (fit, fitp):
+        assert g["status_code"] == 1 and g["gradfx_norm"] < 1e-6                       # TNLSStatus::Gradient
+        assert np.linalg.norm(yn - np.sin(g["x"][0] * t + g["x"][1])) < noise          # better than the planted signal
+
+
 def test_header_layer_has_reference_layout():
     for rel in ("Optimization/Base/Concepts.h", "Optimization/Riemannian/Concepts.h",
-                "Optimization/Riemannian/TNT.h", "Optimization/Riemannian/GradientDescent.h", "Optimization/LinearAlgebra/Concepts.h",
+                "Optimization/Riemannian/TNT.h", "Optimization/Riemannian/GradientDescent.h",
+                "Optimization/Riemannian/TNLS.h", "Optimization/LinearAlgebra/Concepts.h",
                 "Optimization/LinearAlgebra/IterativeSolvers.h", "Optimization/Util/Stopwatch.h",
                 "Optimization/b200/Device.h", "optimization_b200.h"):
         assert os.path.exists(os.path.join(ROOT, "include", rel)), rel
