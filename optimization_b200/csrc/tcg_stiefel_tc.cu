@@ -485,19 +485,22 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
       const u64 flag = rvw.load(ACC_FLAG_OFF);
       double c = 0.0;
       {
-        // G (fixed point) -> shared memory with one 16-byte load per entry, then sym(G) from shared memory
+        // G (fixed point) -> shared memory with one 16-byte load per entry (warps 4-15) while warps 0-3 finalize the
+        // four exact scalars (both are latency chains on L2); then sym(G) from shared memory
         double *Graw = reinterpret_cast<double *>(base + 16 * STRIP_SLOT);   // 8 KB of scratch behind the strip slots
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int e = tid + 512 * h;
-          u64 hi, lo;
-          if (rvw.world == 1) {
-            const ulonglong2 w = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + ACC_GRAM_OFF + 2 * e));
-            hi = w.x; lo = w.y;
-          } else {
-            hi = rvw.load(ACC_GRAM_OFF + 2 * e); lo = rvw.load(ACC_GRAM_OFF + 2 * e + 1);
+        if (warp >= 4) {
+          for (int e = tid - 128; e < ST_P * ST_P; e += 384) {
+            u64 hi, lo;
+            if (rvw.world == 1) {
+              const ulonglong2 w = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + ACC_GRAM_OFF + 2 * e));
+              hi = w.x; lo = w.y;
+            } else {
+              hi = rvw.load(ACC_GRAM_OFF + 2 * e); lo = rvw.load(ACC_GRAM_OFF + 2 * e + 1);
+            }
+            Graw[e] = fix2_to_double((i64)hi, (i64)lo, q);
           }
-          Graw[e] = fix2_to_double((i64)hi, (i64)lo, q);
+        } else {
+          finalize_scalars(rvw, sh, 0, 4);
         }
         __syncthreads();
 #pragma unroll
@@ -510,7 +513,6 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
         }
       }
       TLB(10);
-      finalize_scalars(rvw, sh, 0, 4);
       TLB(11);
       c = warp_sum(c);
       if (lane == 0) s_part[warp] = c;
