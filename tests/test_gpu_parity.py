@@ -318,3 +318,44 @@ def test_sphere_full_size_properties(ctx):
     lhs = ctx.hvp(H, ctx.axpby(2.0, g, -3.0, v)).cpu().numpy()
     rhs = 2.0 * ctx.hvp(H, g).cpu().numpy() - 3.0 * ctx.hvp(H, v).cpu().numpy()
     assert rel(lhs, rhs) < 1e-12                               # linearity of the HVP
+
+
+# ---- the fp64 tensor-core fallback of the Stiefel kernel ------------------------------------------
+@pytest.mark.parametrize("n", [300, 4096])
+def test_stiefel_fp64_mma_path_vs_oracle(ctx, port, n):
+    """ob200_set_option("tcgen05", 0): tcg_stiefel_kernel (A p on the fp64 tensor cores) against the oracle and
+    against the tcgen05 digit-plane kernel."""
+    prob = P.make_stiefel_critical(n, 32)
+    A, Y, H = stiefel_setup(ctx, prob)
+    kw = dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.)
+    s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
+    o_tc = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+    assert ctx.last_path == "tcgen05"
+    ctx.set_option("tcgen05", 0)
+    try:
+        o_mm = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+        assert ctx.last_path == "dmma"
+    finally:
+        ctx.set_option("tcgen05", 1)
+    for o in (o_tc, o_mm):
+        assert (o.num_iterations, o.exit_reason) == (it_ref, why_ref)
+        assert rel(o.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(o.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+    assert rel(o_tc.s.cpu().numpy(), o_mm.s.cpu().numpy()) < RTOL
+
+
+def test_stiefel_wide_range_A_takes_fallback(ctx, port):
+    """A block whose entries span more than 22 bits is not block-fixed-point: the library must notice and run the
+    fp64 tensor-core kernel by itself (no option set), still matching the oracle."""
+    import dataclasses
+    prob = P.make_stiefel_critical(1024, 32)
+    Ad = P.from_bf16_bits(prob.A_bf16).copy()          # (nblk, 128, 128) doubles on the bf16 grid
+    Ad[0, 5, 9] = Ad[0, 9, 5] = 2.0 ** -40             # exact in bf16, 2^-40 relative to the block's O(1) entries
+    prob2 = dataclasses.replace(prob, A_bf16=P.to_bf16_bits(Ad))
+    A, Y, H = stiefel_setup(ctx, prob2)
+    kw = dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.)
+    s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob2, prob2.Y0, prob2.g, **kw)
+    out = ctx.stpcg(ctx.to_device(prob2.g), H, **kw)
+    assert ctx.last_path == "dmma"
+    assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+    assert rel(out.s.cpu().numpy(), s_ref) < RTOL
