@@ -49,6 +49,11 @@ def test_byte_model():
     assert lib.ob200_stpcg_step_bytes(C.byref(op), C.byref(pc)) == 11 * 8 * 1000
     pc.kind = capi.PRECON_JACOBI
     assert lib.ob200_stpcg_step_bytes(C.byref(op), C.byref(pc)) == 13 * 8 * 1000
+    # sphere, k = 16: (14 + 2k) n e per step, (6 + 2k) n e per stand-alone HVP
+    pc.kind = capi.PRECON_NONE
+    op.kind, op.n, op.p, op.k = capi.OP_SPHERE_LOWRANK, 1 << 24, 1, 16
+    assert lib.ob200_stpcg_step_bytes(C.byref(op), C.byref(pc)) == 46 * 8 * (1 << 24)
+    assert lib.ob200_hvp_bytes(C.byref(op)) == 38 * 8 * (1 << 24)
 
 
 def test_product_never_imports_oracle():

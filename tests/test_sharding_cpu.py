@@ -77,6 +77,12 @@ def test_row_partition_covers_and_aligns():
                 assert lo[r] <= hi[r] and lo[r] % 128 == 0
                 if r + 1 < world:
                     assert hi[r] == lo[r + 1]
+    # sphere shards: boundaries at multiples of the 256-element reduction unit
+    for n in (1, 255, 257, 100003, 1 << 20):
+        for world in (1, 2, 8):
+            lo, hi = row_partition(n, world, 256)
+            assert lo[0] == 0 and hi[-1] == n and all(l % 256 == 0 for l in lo)
+            assert all(hi[r] == lo[r + 1] for r in range(world - 1))
     lo, hi = row_partition(100000, 8, 128)
     assert max(h - l for l, h in zip(lo, hi)) - min(h - l for l, h in zip(lo, hi)) <= 128 + 96
 
