@@ -211,6 +211,32 @@ int ob200_sphere_model(ob200_context *ctx, uint64_t n, uint64_t k, const double 
 /* projection retraction  out = (x + v) / ||x + v||   (out may alias v) */
 int ob200_sphere_retract(ob200_context *ctx, uint64_t n, const double *x_dev, const double *v_dev, double *out_dev);
 
+/* ---- LOBPCG: smallest eigenpairs of A x = lambda B x  (reference LinearAlgebra/LOBPCG.h:131-337) -------------
+ * Replaces  LOBPCG<Vector, Matrix>(A, B, T, X0, nev, max_iters, num_iters, nc, tau)  for block operators the library
+ * knows (the `SymmetricLinearOperator<Matrix>` functors A, B, T of LOBPCG.h:131-140 become descriptors), with the
+ * reference's iteration: basis S = [X, T R, P] with soft locking of the nc converged columns (l.207-221),
+ * Rayleigh-Ritz on (S^T A S, S^T B S) with diagonal equilibration (l.53-62; the dense generalised eigensolve runs in
+ * cuSOLVER, LIBRARY code: it stands for Eigen's GeneralizedSelfAdjointEigenSolver), X = S C, P = S_{W,P} C_{W,P},
+ * R = A X - B X Theta, convergence test |r_i| <= tau (|A| + |B| |theta_i|) |x_i| on the first nev columns (l.254-269).
+ * Block vectors are row-major m x k; X_dev: m x nx (in: X0, out: eigenvector estimates, first nev columns meaningful).
+ * Omega_dev: m x nx probe block for the operator norm estimates of l.172-181 (NULL: X0 is used). */
+#define OB200_BLK_DIAG 1     /* (A X)[r, :] = diag_dev[r] * X[r, :]                                      */
+#define OB200_BLK_STENCIL7 2 /* 7-point Laplacian, Dirichlet boundary, grid gx x gy x gz (x fastest), m = gx gy gz */
+#define OB200_BLK_SCALAR 3   /* A X = alpha X  (e.g. the Jacobi preconditioner 1/6 of the Laplacian)     */
+typedef struct {
+  int kind;
+  const double *diag_dev; /* OB200_BLK_DIAG: m doubles */
+  double alpha;           /* OB200_BLK_SCALAR */
+  uint32_t gx, gy, gz;    /* OB200_BLK_STENCIL7 */
+} ob200_block_operator;
+int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, const ob200_block_operator *B /* NULL: identity */,
+                 const ob200_block_operator *T /* NULL: none */, uint64_t m, uint64_t nx, double *X_dev, uint64_t nev,
+                 uint64_t max_iters, double tau, const double *Omega_dev, double *theta_host /* nev */,
+                 uint64_t *num_iters, uint64_t *num_converged);
+/* out = Op(in) for a block operator (m x k row-major blocks with leading dimensions) */
+int ob200_block_apply(ob200_context *ctx, const ob200_block_operator *Op, uint64_t m, uint64_t k, const double *in_dev,
+                      uint64_t ldi, double *out_dev, uint64_t ldo);
+
 /* ---- device memory helpers (so non-CUDA hosts can stage data) -------------- */
 int ob200_malloc(ob200_context *ctx, size_t bytes, void **ptr_dev);
 int ob200_free(ob200_context *ctx, void *ptr_dev);

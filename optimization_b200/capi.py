@@ -27,7 +27,7 @@ EXPORTS = [
     "ob200_create", "ob200_destroy", "ob200_last_error", "ob200_version", "ob200_sm_count",
     "ob200_synchronize", "ob200_kernel_launches", "ob200_stpcg", "ob200_stpcg_host", "ob200_hvp",
     "ob200_dot", "ob200_dots", "ob200_axpby", "ob200_hadamard", "ob200_stiefel_model",
-    "ob200_stiefel_retract", "ob200_sphere_model", "ob200_sphere_retract", "ob200_malloc",
+    "ob200_stiefel_retract", "ob200_sphere_model", "ob200_sphere_retract", "ob200_lobpcg", "ob200_block_apply", "ob200_malloc",
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
@@ -41,6 +41,14 @@ class Operator(C.Structure):
                 ("S_host", C.c_void_p), ("op_norm_bound", C.c_double), ("x_dev", C.c_void_p),
                 ("U_dev", C.c_void_p), ("sigma_host", C.c_void_p), ("k", C.c_uint64),
                 ("xAx", C.c_double), ("Ax_dev", C.c_void_p), ("ldu", C.c_uint64)]
+
+
+class BlockOperator(C.Structure):
+    _fields_ = [("kind", C.c_int), ("diag_dev", C.c_void_p), ("alpha", C.c_double), ("gx", C.c_uint32),
+                ("gy", C.c_uint32), ("gz", C.c_uint32)]
+
+
+BLK_DIAG, BLK_STENCIL7, BLK_SCALAR = 1, 2, 3
 
 
 class Precon(C.Structure):
@@ -113,6 +121,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_stiefel_retract.argtypes = [vp, u64, u64, vp, vp, vp]
     lib.ob200_sphere_model.argtypes = [vp, u64, u64, vp, vp, u64, vp, vp, vp, C.POINTER(dbl), vp]
     lib.ob200_sphere_retract.argtypes = [vp, u64, vp, vp, vp]
+    bo = C.POINTER(BlockOperator)
+    lib.ob200_lobpcg.argtypes = [vp, bo, bo, bo, u64, u64, vp, u64, u64, dbl, vp, C.POINTER(dbl), C.POINTER(u64),
+                                 C.POINTER(u64)]
+    lib.ob200_block_apply.argtypes = [vp, bo, u64, u64, vp, u64, vp, u64]
     lib.ob200_malloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.ob200_free.argtypes = [vp, vp]
     lib.ob200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]

@@ -5,6 +5,9 @@
 #include "../../include/optimization_b200.h"
 #include "tcg.cuh"
 
+#include <cusolverDn.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -47,6 +50,20 @@ cudaError_t launch_sphere_apply(unsigned long long N, const double *d, const dou
                                 const double *st_dev, const double *v, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_sphere_combine(unsigned long long N, const double *Av, const double *x, const double *v, double c,
                                   double lambda, double *out, int sm_count, cudaStream_t st);
+cudaError_t launch_blk_diag(unsigned long long m, int k, const double *d, double alpha, const double *in, int ldi, double *out,
+                            int ldo, int sm_count, cudaStream_t st);
+cudaError_t launch_blk_stencil7(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
+                                int sm_count, cudaStream_t st);
+cudaError_t launch_blk_gram(unsigned long long m, const double *A, int lda, int k1, const double *B, int ldb, int k2,
+                            double *partial, int nb, double *G, cudaStream_t st);
+cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int k, const double *C, int ldc, int n2, double *out,
+                            int ldo, int nb, cudaStream_t st);
+cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, const double *X,
+                                const double *theta, double *R, double *partial, int nb, double *norms2, cudaStream_t st);
+cudaError_t launch_blk_sumsq(unsigned long long total, const double *V, double *partial, int nb, double *out, cudaStream_t st);
+cudaError_t launch_rr_equilibrate(int ns, const double *GA, const double *GB, double *EA, double *EB, double *D,
+                                  cudaStream_t st);
+cudaError_t launch_rr_scale_transpose(int ns, const double *Z, const double *D, double *C, cudaStream_t st);
 cudaError_t launch_dots(unsigned long long N, int count, const double *const *a, const double *const *b,
                         u64 *set, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st);
@@ -65,6 +82,7 @@ struct ob200_context {
   bool own_stream = false;
   std::string err;
   uint64_t launches = 0;
+  cusolverDnHandle_t solver = nullptr;   // LOBPCG: dense generalised eigensolve of the Rayleigh-Ritz pencil (library)
   // workspace
   size_t vec_capacity = 0;        // doubles per work vector
   double *r = nullptr, *p0 = nullptr, *p1 = nullptr, *Hp = nullptr, *gs = nullptr; // gs: staging for g/s (host entry)
@@ -176,6 +194,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaFree(ctx->dbg);
   cudaFree(ctx->planes);
   cudaFree(ctx->plane_exp);
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OB200_OK;
@@ -849,3 +868,196 @@ int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const doub
 }
 
 }  // extern "C"
+
+// ---- LOBPCG ------------------------------------------------------------------------------------------------
+static int block_apply(ob200_context *ctx, const ob200_block_operator *Op, uint64_t m, int k, const double *in, int ldi,
+                       double *out, int ldo) {
+  cudaStream_t st = ctx->stream;
+  switch (Op->kind) {
+    case OB200_BLK_DIAG:
+      if (!Op->diag_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "diagonal block operator without diagonal");
+      CK(launch_blk_diag(m, k, Op->diag_dev, 0.0, in, ldi, out, ldo, ctx->sm_count, st));
+      break;
+    case OB200_BLK_SCALAR:
+      CK(launch_blk_diag(m, k, nullptr, Op->alpha, in, ldi, out, ldo, ctx->sm_count, st));
+      break;
+    case OB200_BLK_STENCIL7:
+      if ((uint64_t)Op->gx * Op->gy * Op->gz != m) return fail(ctx, OB200_INVALID_ARGUMENT, "stencil grid does not match m");
+      CK(launch_blk_stencil7(Op->gx, Op->gy, Op->gz, k, in, ldi, out, ldo, ctx->sm_count, st));
+      break;
+    default:
+      return fail(ctx, OB200_UNSUPPORTED, "unknown block operator kind");
+  }
+  ctx->launches += 1;
+  return OB200_OK;
+}
+
+namespace {
+struct DevBuf {   // RAII for the call-local device buffers
+  std::vector<void *> ptrs;
+  ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
+  template <class T> cudaError_t get(T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+    if (e == cudaSuccess) { ptrs.push_back(q); *p = static_cast<T *>(q); }
+    return e;
+  }
+};
+}  // namespace
+
+// Rayleigh-Ritz (LOBPCG.h:53-62) on the device: GA, GB (ns x ns) -> theta (ascending), C (row-major, C^T GB C = I)
+static int rayleigh_ritz(ob200_context *ctx, int ns, const double *GA, const double *GB, double *EA, double *EB, double *D,
+                         double *theta, double *C, double *work, int lwork, int *info_dev) {
+  cudaStream_t st = ctx->stream;
+  CK(launch_rr_equilibrate(ns, GA, GB, EA, EB, D, st));
+  if (cusolverDnDsygvd(ctx->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ns, EA, ns, EB, ns,
+                       theta, work, lwork, info_dev) != CUSOLVER_STATUS_SUCCESS)
+    return fail(ctx, OB200_CUDA_ERROR, "cusolverDnDsygvd failed");
+  CK(launch_rr_scale_transpose(ns, EA, D, C, st));
+  ctx->launches += 2;
+  int info = 0;
+  CK(cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (info != 0) return fail(ctx, OB200_NUMERIC_RANGE, "Rayleigh-Ritz pencil is not positive definite (S^T B S singular)");
+  return OB200_OK;
+}
+
+extern "C" int ob200_block_apply(ob200_context *ctx, const ob200_block_operator *Op, uint64_t m, uint64_t k,
+                                 const double *in, uint64_t ldi, double *out, uint64_t ldo) {
+  if (!ctx || !Op || !in || !out || k == 0 || ldi < k || ldo < k) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  return block_apply(ctx, Op, m, (int)k, in, (int)ldi, out, (int)ldo);
+}
+
+extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, const ob200_block_operator *B,
+                            const ob200_block_operator *T, uint64_t m, uint64_t nx64, double *X, uint64_t nev,
+                            uint64_t max_iters, double tau, const double *Omega, double *theta_host, uint64_t *num_iters,
+                            uint64_t *num_converged) {
+  if (!ctx || !A || !X || !theta_host || !num_iters || !num_converged) return OB200_INVALID_ARGUMENT;
+  // reference LOBPCG.h:148-155
+  if (nev > nx64) return fail(ctx, OB200_INVALID_ARGUMENT, "Block size nx must be greater than or equal to the number nev of desired eigenpairs");
+  if (nx64 > m) return fail(ctx, OB200_INVALID_ARGUMENT, "Block size nx must be less than or equal to the dimension m of the problem");
+  if (nx64 == 0 || nx64 > 64) return fail(ctx, OB200_UNSUPPORTED, "block size nx must be in 1..64");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (!ctx->solver) {
+    if (cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ctx, OB200_CUDA_ERROR, "cusolverDnCreate failed");
+  }
+  cusolverDnSetStream(ctx->solver, st);
+  const int nx = (int)nx64, nsmax = 3 * nx, nb = ctx->sm_count;
+  const size_t mnx = (size_t)m * nx;
+  int rc;
+
+  DevBuf mem;
+  double *S, *AS, *BS = nullptr, *AX, *BX = nullptr, *R, *W = nullptr, *P, *Xn, *tmp;
+  double *GA, *GB, *EA, *EB, *D, *theta, *C, *partial, *norms2, *work;
+  int *info_dev;
+  CK(mem.get(&S, (size_t)m * nsmax));
+  CK(mem.get(&AS, (size_t)m * nsmax));
+  if (B) CK(mem.get(&BS, (size_t)m * nsmax));
+  CK(mem.get(&AX, mnx));
+  if (B) CK(mem.get(&BX, mnx));
+  CK(mem.get(&R, mnx));
+  if (T) CK(mem.get(&W, mnx));
+  CK(mem.get(&P, mnx));
+  CK(mem.get(&Xn, mnx));
+  CK(mem.get(&tmp, mnx));
+  const size_t nn = (size_t)nsmax * nsmax;
+  CK(mem.get(&GA, nn)); CK(mem.get(&GB, nn)); CK(mem.get(&EA, nn)); CK(mem.get(&EB, nn)); CK(mem.get(&C, nn));
+  CK(mem.get(&D, nsmax)); CK(mem.get(&theta, nsmax));
+  CK(mem.get(&partial, (size_t)nb * nn));
+  CK(mem.get(&norms2, 2 * nx + 8));
+  CK(mem.get(&info_dev, 1));
+  int lwork = 0;
+  if (cusolverDnDsygvd_bufferSize(ctx->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nsmax, EA,
+                                  nsmax, EB, nsmax, theta, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    return fail(ctx, OB200_CUDA_ERROR, "cusolverDnDsygvd_bufferSize failed");
+  CK(mem.get(&work, (size_t)lwork));
+
+  std::vector<double> h(2 * nx + 8), th(nsmax);
+  auto frob = [&](const double *V, double *out) -> int {   // ||V||_F of an m x nx block
+    CK(launch_blk_sumsq(mnx, V, partial, nb, norms2, st));
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(h.data(), norms2, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out = std::sqrt(h[0]);
+    return OB200_OK;
+  };
+
+  // operator norm estimates (l.172-181) from the probe block
+  const double *Om = Omega ? Omega : X;
+  double nOm = 0, nA = 0, nB = 0;
+  if ((rc = frob(Om, &nOm))) return rc;
+  if ((rc = block_apply(ctx, A, m, nx, Om, nx, tmp, nx))) return rc;
+  if ((rc = frob(tmp, &nA))) return rc;
+  const double A2normest = nA / nOm;
+  double B2normest = 1.0;
+  if (B) {
+    if ((rc = block_apply(ctx, B, m, nx, Om, nx, tmp, nx))) return rc;
+    if ((rc = frob(tmp, &nB))) return rc;
+    B2normest = nB / nOm;
+  }
+
+  // initial Rayleigh-Ritz on span(X0) (l.186-198)
+  if ((rc = block_apply(ctx, A, m, nx, X, nx, AX, nx))) return rc;
+  const double *BXp = X;
+  if (B) { if ((rc = block_apply(ctx, B, m, nx, X, nx, BX, nx))) return rc; BXp = BX; }
+  CK(launch_blk_gram(m, X, nx, nx, AX, nx, nx, partial, nb, GA, st));
+  CK(launch_blk_gram(m, X, nx, nx, BXp, nx, nx, partial, nb, GB, st));
+  ctx->launches += 4;
+  if ((rc = rayleigh_ritz(ctx, nx, GA, GB, EA, EB, D, theta, C, work, lwork, info_dev))) return rc;
+  CK(launch_blk_gemm(m, AX, nx, nx, C, nx, nx, tmp, nx, nb, st));           // AX <- AX C
+  CK(cudaMemcpyAsync(AX, tmp, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st));
+  CK(launch_blk_gemm(m, BXp, nx, nx, C, nx, nx, tmp, nx, nb, st));          // BX <- BX C  (B absent: X C, kept in tmp)
+  ctx->launches += 2;
+  const double *BXc = tmp;
+  if (B) { CK(cudaMemcpyAsync(BX, tmp, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st)); BXc = BX; }
+  CK(launch_blk_residual(m, nx, AX, BXc, X, theta, R, partial, nb, norms2, st));
+  ctx->launches += 2;
+
+  uint64_t nc = 0, it = 1;
+  const size_t rowX = sizeof(double) * nx, rowS = sizeof(double) * nsmax;
+  for (it = 1; it < max_iters; ++it) {
+    const double *Wp = R;
+    if (T) { if ((rc = block_apply(ctx, T, m, nx, R, nx, W, nx))) return rc; Wp = W; }       // l.207
+    const int act = nx - (int)nc;                                                           // soft locking
+    CK(cudaMemcpy2DAsync(S, rowS, X, rowX, rowX, m, cudaMemcpyDeviceToDevice, st));          // l.210
+    CK(cudaMemcpy2DAsync(S + nx, rowS, Wp + nc, rowX, sizeof(double) * act, m, cudaMemcpyDeviceToDevice, st));   // l.213
+    int ns = 2 * nx - (int)nc;
+    if (it > 1) {
+      CK(cudaMemcpy2DAsync(S + ns, rowS, P + nc, rowX, sizeof(double) * act, m, cudaMemcpyDeviceToDevice, st));  // l.217
+      ns = 3 * nx - 2 * (int)nc;
+    }
+    if ((rc = block_apply(ctx, A, m, ns, S, nsmax, AS, nsmax))) return rc;                  // l.225
+    const double *BSp = S;
+    if (B) { if ((rc = block_apply(ctx, B, m, ns, S, nsmax, BS, nsmax))) return rc; BSp = BS; }   // l.226
+    CK(launch_blk_gram(m, S, nsmax, ns, AS, nsmax, ns, partial, nb, GA, st));               // l.229
+    CK(launch_blk_gram(m, S, nsmax, ns, BSp, nsmax, ns, partial, nb, GB, st));              // l.230
+    ctx->launches += 4;
+    if ((rc = rayleigh_ritz(ctx, ns, GA, GB, EA, EB, D, theta, C, work, lwork, info_dev))) return rc;   // l.233
+    CK(launch_blk_gemm(m, S, nsmax, ns, C, ns, nx, Xn, nx, nb, st));                        // l.239  X = S C(:, 1:nx)
+    CK(launch_blk_gemm(m, S + nx, nsmax, ns - nx, C + (size_t)nx * ns, ns, nx, P, nx, nb, st));   // l.249  P = S_{W,P} C_{W,P}
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(X, Xn, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st));
+    if ((rc = block_apply(ctx, A, m, nx, X, nx, AX, nx))) return rc;                        // l.242
+    const double *BXq = X;
+    if (B) { if ((rc = block_apply(ctx, B, m, nx, X, nx, BX, nx))) return rc; BXq = BX; }   // l.243
+    CK(launch_blk_residual(m, nx, AX, BXq, X, theta, R, partial, nb, norms2, st));          // l.246, 254
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(h.data(), norms2, sizeof(double) * 2 * nx, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(th.data(), theta, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (nc = 0; nc < nev; ++nc) {                                                          // l.257-269
+      const double r = std::sqrt(h[nc]), xn = std::sqrt(h[nx + nc]);
+      const double tol = tau * (A2normest + B2normest * std::fabs(th[nc])) * xn;
+      if (!(r <= tol)) break;
+    }
+    if (nc == nev) break;                                                                   // l.277
+  }
+  CK(cudaMemcpyAsync(th.data(), theta, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (uint64_t i = 0; i < nev; ++i) theta_host[i] = th[i];
+  *num_iters = it;
+  *num_converged = nc;
+  return OB200_OK;
+}

@@ -1,0 +1,282 @@
+// Block kernels of the LOBPCG path (reference include/Optimization/LinearAlgebra/LOBPCG.h:131-337, BASELINE config C4):
+// block operator apply (diagonal, 7-point 3-D Laplacian), tall-skinny Gram S^T Z, block update S C, residual
+// R = AX - BX diag(theta) with column norms, and the small glue kernels around the Rayleigh-Ritz pencil.
+// Block vectors are row-major m x k with a leading dimension (k contiguous doubles per row): every kernel streams
+// whole rows, coalesced.  All cross-CTA sums go through per-CTA partial buffers reduced in a fixed order
+// (deterministic: the grid is fixed by the SM count, the row partition is static).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ob200 {
+
+constexpr int LB_THREADS = 256;
+constexpr int LB_KMAX = 192;      // 3 * nx, nx <= 64
+
+// ---- operator apply --------------------------------------------------------------------------------
+// out[r, c] = d[r] * in[r, c]   (d == nullptr: scalar `alpha`)
+__global__ void __launch_bounds__(LB_THREADS) blk_diag_kernel(unsigned long long m, int k, const double *d, double alpha,
+                                                              const double *in, int ldi, double *out, int ldo) {
+  const unsigned long long total = m * (unsigned long long)k;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long r = e / k;
+    const int c = (int)(e - r * k);
+    out[r * ldo + c] = (d ? d[r] : alpha) * in[r * ldi + c];
+  }
+}
+// 7-point Laplacian, Dirichlet boundary, grid gx x gy x gz (x fastest): out = 6 in - sum of existing neighbours
+__global__ void __launch_bounds__(LB_THREADS) blk_stencil7_kernel(unsigned gx, unsigned gy, unsigned gz, int k, const double *in,
+                                                                  int ldi, double *out, int ldo) {
+  const unsigned long long m = (unsigned long long)gx * gy * gz, total = m * (unsigned long long)k;
+  const unsigned long long sx = 1, sy = gx, sz = (unsigned long long)gx * gy;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long r = e / k;
+    const int c = (int)(e - r * k);
+    const unsigned x = (unsigned)(r % gx), y = (unsigned)((r / gx) % gy), z = (unsigned)(r / sz);
+    const double *p = in + r * ldi + c;
+    double v = 6.0 * p[0];
+    if (x > 0) v -= p[-(long long)(sx * ldi)];
+    if (x + 1 < gx) v -= p[sx * ldi];
+    if (y > 0) v -= p[-(long long)(sy * ldi)];
+    if (y + 1 < gy) v -= p[sy * ldi];
+    if (z > 0) v -= p[-(long long)(sz * ldi)];
+    if (z + 1 < gz) v -= p[sz * ldi];
+    out[r * ldo + c] = v;
+  }
+}
+
+// ---- Gram: partial[bx][i][j] = sum over the CTA's rows of A[r, i] * B[r, 64 by + j]  (i < k1, j < min(64, k2 - 64 by)) ----
+constexpr int GR_TR = 16;          // rows per shared-memory tile
+__global__ void __launch_bounds__(LB_THREADS) blk_gram_kernel(unsigned long long m, const double *A, int lda, int k1,
+                                                              const double *B, int ldb, int k2, double *partial) {
+  __shared__ double As[GR_TR][LB_KMAX];
+  __shared__ double Bs[GR_TR][64];
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+  const int j0 = 64 * blockIdx.y;
+  const int kb = min(64, k2 - j0);
+  const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
+  double acc[12][4];
+#pragma unroll
+  for (int u = 0; u < 12; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+  for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GR_TR) {
+    const int rows = (int)min((unsigned long long)GR_TR, r_hi - r0);
+    __syncthreads();
+    for (int e = tid; e < GR_TR * k1; e += LB_THREADS) {
+      const int rr = e / k1, c = e - rr * k1;
+      As[rr][c] = rr < rows ? A[(r0 + rr) * lda + c] : 0.0;
+    }
+    for (int e = tid; e < GR_TR * 64; e += LB_THREADS) {
+      const int rr = e >> 6, c = e & 63;
+      Bs[rr][c] = (rr < rows && c < kb) ? B[(r0 + rr) * ldb + j0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < GR_TR; ++rr) {
+      double b[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) b[v] = Bs[rr][tj + 16 * v];
+#pragma unroll
+      for (int u = 0; u < 12; ++u) {
+        const double a = (ti + 16 * u < k1) ? As[rr][ti + 16 * u] : 0.0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a, b[v], acc[u][v]);
+      }
+    }
+  }
+  double *out = partial + (size_t)blockIdx.x * k1 * k2;
+#pragma unroll
+  for (int u = 0; u < 12; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = ti + 16 * u, j = tj + 16 * v;
+      if (i < k1 && j < kb) out[(size_t)i * k2 + j0 + j] = acc[u][v];
+    }
+}
+// G[e] = sum_b partial[b][e], fixed order
+__global__ void blk_reduce_kernel(const double *partial, int nb, int count, double *G) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += partial[(size_t)b * count + e];
+    G[e] = s;
+  }
+}
+
+// ---- block update: out[m x n2] = S[m x k] * C[k x n2]   (C row-major, ldc) ---------------------------------
+constexpr int GM_TR = 64;
+__global__ void __launch_bounds__(LB_THREADS) blk_gemm_kernel(unsigned long long m, const double *S, int lds, int k,
+                                                              const double *C, int ldc, int n2, double *out, int ldo) {
+  extern __shared__ double sm[];
+  double *Cs = sm;                         // [k][64]
+  double *Ss = sm + (size_t)LB_KMAX * 64;  // [GM_TR][LB_KMAX]
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+  for (int e = tid; e < k * 64; e += LB_THREADS) {
+    const int kk = e >> 6, c = e & 63;
+    Cs[kk * 64 + c] = c < n2 ? C[(size_t)kk * ldc + c] : 0.0;
+  }
+  const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
+  for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GM_TR) {
+    const int rows = (int)min((unsigned long long)GM_TR, r_hi - r0);
+    __syncthreads();
+    for (int e = tid; e < GM_TR * k; e += LB_THREADS) {
+      const int rr = e / k, c = e - rr * k;
+      Ss[rr * LB_KMAX + c] = rr < rows ? S[(r0 + rr) * lds + c] : 0.0;
+    }
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < k; ++kk) {
+      double a[4], c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = Ss[(ti + 16 * u) * LB_KMAX + kk];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) c[v] = Cs[kk * 64 + tj + 16 * v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], c[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = ti + 16 * u;
+      if (rr < rows)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int c = tj + 16 * v;
+          if (c < n2) out[(r0 + rr) * ldo + c] = acc[u][v];
+        }
+    }
+  }
+}
+
+// ---- R = AX - BX diag(theta); per-CTA partial column sums of R^2 and X^2 -----------------------------------------
+__global__ void __launch_bounds__(LB_THREADS) blk_residual_kernel(unsigned long long m, int nx, const double *AX, const double *BX,
+                                                                  const double *X, const double *theta, double *R,
+                                                                  double *partial /* [grid][2 nx] */) {
+  __shared__ double s_r[4][64], s_x[4][64];
+  const int tid = threadIdx.x, c = tid & 63, g = tid >> 6;     // 4 row groups x 64 columns
+  const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
+  double rr = 0.0, xx = 0.0;
+  if (c < nx) {
+    const double th = theta[c];
+    for (unsigned long long r = r_lo + g; r < r_hi; r += 4) {
+      const double x = X[r * nx + c];
+      const double v = AX[r * nx + c] - BX[r * nx + c] * th;
+      R[r * nx + c] = v;
+      rr = fma(v, v, rr);
+      xx = fma(x, x, xx);
+    }
+  }
+  s_r[g][c] = rr;
+  s_x[g][c] = xx;
+  __syncthreads();
+  if (tid < 64 && tid < nx) {
+    partial[(size_t)blockIdx.x * 2 * nx + tid] = (s_r[0][tid] + s_r[1][tid]) + (s_r[2][tid] + s_r[3][tid]);
+    partial[(size_t)blockIdx.x * 2 * nx + nx + tid] = (s_x[0][tid] + s_x[1][tid]) + (s_x[2][tid] + s_x[3][tid]);
+  }
+}
+// sum of squares of a block (Frobenius norm^2), per-CTA partials
+__global__ void __launch_bounds__(LB_THREADS) blk_sumsq_kernel(unsigned long long total, const double *V, double *partial) {
+  __shared__ double s[LB_THREADS];
+  double a = 0.0;
+  const unsigned long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1ull) / gridDim.x;
+  for (unsigned long long e = lo + threadIdx.x; e < hi; e += LB_THREADS) a = fma(V[e], V[e], a);
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = LB_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+// ---- Rayleigh-Ritz glue (ns x ns, one CTA) ---------------------------------------------------------------------
+// equilibration (LOBPCG.h:56-59): D = 1/sqrt(diag(GB)); EA = sym(D GA D), EB = sym(D GB D)   (symmetric: row-major ==
+// column-major); out of place
+__global__ void rr_equilibrate_kernel(int ns, const double *GA, const double *GB, double *EA, double *EB, double *D) {
+  __shared__ double sD[LB_KMAX];
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    sD[i] = 1.0 / sqrt(GB[i * ns + i]);
+    D[i] = sD[i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ns * ns; e += blockDim.x) {
+    const int i = e / ns, j = e - i * ns;
+    const double w = sD[i] * sD[j];
+    EA[e] = 0.5 * (GA[i * ns + j] + GA[j * ns + i]) * w;
+    EB[e] = 0.5 * (GB[i * ns + j] + GB[j * ns + i]) * w;
+  }
+}
+// C[k][j] (row-major, ld ns) = D[k] * Z(k, j), Z column-major eigenvectors from the solver (LOBPCG.h:61)
+__global__ void rr_scale_transpose_kernel(int ns, const double *Z, const double *D, double *C) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ns * ns; e += gridDim.x * blockDim.x) {
+    const int k = e / ns, j = e - k * ns;
+    C[e] = D[k] * Z[k + (size_t)j * ns];
+  }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------
+static int lb_grid(unsigned long long total, int sm_count) {
+  unsigned long long g = (total + LB_THREADS - 1) / LB_THREADS;
+  const unsigned long long cap = (unsigned long long)sm_count * 8ull;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+cudaError_t launch_blk_diag(unsigned long long m, int k, const double *d, double alpha, const double *in, int ldi, double *out,
+                            int ldo, int sm_count, cudaStream_t st) {
+  blk_diag_kernel<<<lb_grid(m * k, sm_count), LB_THREADS, 0, st>>>(m, k, d, alpha, in, ldi, out, ldo);
+  return cudaGetLastError();
+}
+cudaError_t launch_blk_stencil7(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
+                                int sm_count, cudaStream_t st) {
+  blk_stencil7_kernel<<<lb_grid((unsigned long long)gx * gy * gz * k, sm_count), LB_THREADS, 0, st>>>(gx, gy, gz, k, in, ldi, out, ldo);
+  return cudaGetLastError();
+}
+// G (k1 x k2, row-major) = A^T B ; partial: scratch of nb * k1 * k2 doubles
+cudaError_t launch_blk_gram(unsigned long long m, const double *A, int lda, int k1, const double *B, int ldb, int k2,
+                            double *partial, int nb, double *G, cudaStream_t st) {
+  dim3 grid(nb, (k2 + 63) / 64);
+  blk_gram_kernel<<<grid, LB_THREADS, 0, st>>>(m, A, lda, k1, B, ldb, k2, partial);
+  blk_reduce_kernel<<<(k1 * k2 + 255) / 256, 256, 0, st>>>(partial, nb, k1 * k2, G);
+  return cudaGetLastError();
+}
+cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int k, const double *C, int ldc, int n2, double *out,
+                            int ldo, int nb, cudaStream_t st) {
+  static bool attr = false;
+  const size_t smem = sizeof(double) * ((size_t)LB_KMAX * 64 + (size_t)GM_TR * LB_KMAX);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(blk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    attr = true;
+  }
+  blk_gemm_kernel<<<nb, LB_THREADS, smem, st>>>(m, S, lds, k, C, ldc, n2, out, ldo);
+  return cudaGetLastError();
+}
+// R, and norms2[0:nx] = column sums of R^2, norms2[nx:2nx] = column sums of X^2
+cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, const double *X,
+                                const double *theta, double *R, double *partial, int nb, double *norms2, cudaStream_t st) {
+  blk_residual_kernel<<<nb, LB_THREADS, 0, st>>>(m, nx, AX, BX, X, theta, R, partial);
+  blk_reduce_kernel<<<1, 256, 0, st>>>(partial, nb, 2 * nx, norms2);
+  return cudaGetLastError();
+}
+cudaError_t launch_blk_sumsq(unsigned long long total, const double *V, double *partial, int nb, double *out, cudaStream_t st) {
+  blk_sumsq_kernel<<<nb, LB_THREADS, 0, st>>>(total, V, partial);
+  blk_reduce_kernel<<<1, 32, 0, st>>>(partial, nb, 1, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_rr_equilibrate(int ns, const double *GA, const double *GB, double *EA, double *EB, double *D,
+                                  cudaStream_t st) {
+  rr_equilibrate_kernel<<<1, 256, 0, st>>>(ns, GA, GB, EA, EB, D);
+  return cudaGetLastError();
+}
+cudaError_t launch_rr_scale_transpose(int ns, const double *Z, const double *D, double *C, cudaStream_t st) {
+  rr_scale_transpose_kernel<<<(ns * ns + 255) / 256, 256, 0, st>>>(ns, Z, D, C);
+  return cudaGetLastError();
+}
+
+}  // namespace ob200

@@ -193,6 +193,46 @@ class Context:
         self._check(self.lib.ob200_sphere_retract(self.h, x.numel(), _ptr(x), _ptr(v), _ptr(out)))
         return out
 
+    # -- LOBPCG (reference LinearAlgebra/LOBPCG.h:131-337) -----------------------------------------
+    @staticmethod
+    def block_diag(d: torch.Tensor):
+        op = capi.BlockOperator()
+        op.kind, op.diag_dev = capi.BLK_DIAG, d.data_ptr()
+        op._keep = d
+        return op
+
+    @staticmethod
+    def block_scalar(alpha: float):
+        op = capi.BlockOperator()
+        op.kind, op.alpha = capi.BLK_SCALAR, float(alpha)
+        return op
+
+    @staticmethod
+    def block_laplacian3d(gx: int, gy: int, gz: int):
+        op = capi.BlockOperator()
+        op.kind, op.gx, op.gy, op.gz = capi.BLK_STENCIL7, gx, gy, gz
+        return op
+
+    def block_apply(self, op, X: torch.Tensor):
+        out = torch.empty_like(X)
+        m, k = X.shape
+        self._check(self.lib.ob200_block_apply(self.h, C.byref(op), m, k, _ptr(X), k, _ptr(out), k))
+        return out
+
+    def lobpcg(self, A, B, T, X0: torch.Tensor, nev: int, max_iters: int, tau: float = 1e-6, Omega=None):
+        """Smallest nev eigenpairs of A x = lambda B x.  A, B, T: block operator descriptors (B, T may be None);
+        X0: m x nx.  Returns (theta[nev], X[m x nev], num_iters, num_converged); ValueError where the reference
+        throws std::invalid_argument (LOBPCG.h:148-155)."""
+        X = X0.clone().contiguous()
+        m, nx = X.shape
+        theta = np.zeros(nev)
+        it, nc = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.ob200_lobpcg(self.h, C.byref(A), C.byref(B) if B is not None else None,
+                                   C.byref(T) if T is not None else None, m, nx, _ptr(X), nev, max_iters, float(tau),
+                                   _ptr(Omega), theta.ctypes.data_as(C.POINTER(C.c_double)), C.byref(it), C.byref(nc))
+        self._check(rc)
+        return theta, X[:, :nev], int(it.value), int(nc.value)
+
     def jacobi(self, minv: torch.Tensor | None):
         pc = capi.Precon()
         if minv is None:

@@ -322,6 +322,21 @@ def tnls_sine_cases(m: int = 100):
     }
 
 
+def laplacian3d_apply(X: np.ndarray, gx: int, gy: int, gz: int) -> np.ndarray:
+    """7-point Laplacian with Dirichlet boundary on a gx x gy x gz grid (x fastest), applied to the rows of the
+    block vector X (m x k, m = gx gy gz): (A X)[i] = 6 X[i] - sum of the existing neighbours (config C4 operator)."""
+    k = X.shape[1]
+    V = X.reshape(gz, gy, gx, k)
+    out = 6.0 * V
+    out[:, :, 1:] -= V[:, :, :-1]
+    out[:, :, :-1] -= V[:, :, 1:]
+    out[:, 1:] -= V[:, :-1]
+    out[:, :-1] -= V[:, 1:]
+    out[1:] -= V[:-1]
+    out[:-1] -= V[1:]
+    return out.reshape(X.shape)
+
+
 @dataclasses.dataclass
 class DiagProblem:
     """Diagonal SPD Hessian with optional Jacobi preconditioner (the shape of the

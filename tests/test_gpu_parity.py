@@ -359,3 +359,67 @@ def test_stiefel_wide_range_A_takes_fallback(ctx, port):
     assert ctx.last_path == "dmma"
     assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
     assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+
+
+# ---- LOBPCG (reference LinearAlgebra/LOBPCG.h; BASELINE config C4) ------------------------------------------
+LOB_N, LOB_M, LOB_NEV, LOB_TAU = 1000, 10, 5, 1e-8
+
+
+def _lob_x0(m, nx, seed=91):
+    return (2.0 * P.uniform01(seed, 0, m * nx) - 1.0).reshape(m, nx)
+
+
+@pytest.mark.parametrize("generalized,precon", [(False, False), (False, True), (True, True), (True, False)])
+def test_lobpcg_reference_unit_test_problems(ctx, generalized, precon):
+    """The four diagonal problems of the reference's tests/LOBPCG_unit_test.cpp:123-208 (n = 1000, block 10, nev 5,
+    tau 1e-8) against the CPU restatement (same X0 and probe block) and the exact spectrum."""
+    from oracle import lobpcg_port as L
+    adiag, bdiag = np.linspace(-.5 * LOB_N, .5 * LOB_N, LOB_N), np.linspace(1.0, LOB_N, LOB_N)
+    X0 = _lob_x0(LOB_N, LOB_M)
+    Om = _lob_x0(LOB_N, LOB_M, seed=92)
+    A = lambda X: adiag[:, None] * X
+    B = (lambda X: bdiag[:, None] * X) if generalized else None
+    T = (lambda X: np.abs(adiag)[:, None] * X) if precon else None
+    th_ref, X_ref, it_ref, nc_ref = L.lobpcg(A, B, T, X0, LOB_NEV, 10 * LOB_N, LOB_TAU, Omega=Om)
+    dA = ctx.block_diag(ctx.to_device(adiag))
+    dB = ctx.block_diag(ctx.to_device(bdiag)) if generalized else None
+    dT = ctx.block_diag(ctx.to_device(np.abs(adiag))) if precon else None
+    th, X, it, nc = ctx.lobpcg(dA, dB, dT, ctx.to_device(X0), LOB_NEV, 10 * LOB_N, LOB_TAU, Omega=ctx.to_device(Om))
+    exact = np.sort(adiag / bdiag)[:LOB_NEV] if generalized else adiag[:LOB_NEV]
+    assert nc == nc_ref == LOB_NEV
+    assert np.linalg.norm(th - exact) < 1e-4 and np.linalg.norm(th_ref - exact) < 1e-4       # the reference's bar
+    assert np.allclose(th, th_ref, rtol=1e-9, atol=1e-9)
+    assert abs(it - it_ref) <= max(2, it_ref // 10)          # Gram rounding may shift convergence by an iteration or two
+
+
+def test_lobpcg_small_problem_with_literal_x0(ctx):
+    # LOBPCG_unit_test.cpp:94-120
+    lam = np.array([1., 2., 3., 4.])
+    X0 = np.array([[0.8147, 0.6324], [0.9058, 0.0975], [0.1270, 0.2785], [0.9134, 0.5469]])
+    th, X, it, nc = ctx.lobpcg(ctx.block_diag(ctx.to_device(lam)), None, None, ctx.to_device(X0), 2, 1000, 1e-8)
+    assert nc == 2 and np.linalg.norm(th - lam[:2]) < 1e-3
+    with pytest.raises(ValueError):
+        ctx.lobpcg(ctx.block_diag(ctx.to_device(lam)), None, None, ctx.to_device(X0), 3, 10)     # nev > nx (l.148)
+
+
+def test_lobpcg_laplacian_vs_oracle_and_exact_spectrum(ctx):
+    """Config C4 at small size: 7-point Dirichlet Laplacian on a 12 x 10 x 9 grid, Jacobi T = 1/6, block 16."""
+    from oracle import lobpcg_port as L
+    gx, gy, gz, nx, nev = 12, 10, 9, 16, 6
+    m = gx * gy * gz
+    lam = lambda g: 2.0 - 2.0 * np.cos(np.arange(1, g + 1) * np.pi / (g + 1))
+    exact = np.sort((lam(gz)[:, None, None] + lam(gy)[None, :, None] + lam(gx)[None, None, :]).ravel())
+    X0 = _lob_x0(m, nx, seed=31)
+    dA = ctx.block_laplacian3d(gx, gy, gz)
+    # the stencil kernel against the numpy operator
+    AX = ctx.block_apply(dA, ctx.to_device(X0)).cpu().numpy()
+    assert rel(AX, P.laplacian3d_apply(X0, gx, gy, gz)) < 1e-14
+    th_ref, _, it_ref, nc_ref = L.lobpcg(lambda X: P.laplacian3d_apply(X, gx, gy, gz), None, lambda R: R / 6.0, X0, nev,
+                                         500, 1e-8, Omega=X0)
+    th, X, it, nc = ctx.lobpcg(dA, None, ctx.block_scalar(1.0 / 6.0), ctx.to_device(X0), nev, 500, 1e-8)
+    assert nc == nc_ref == nev
+    assert np.allclose(th, exact[:nev], rtol=1e-7) and np.allclose(th, th_ref, rtol=1e-9)
+    assert abs(it - it_ref) <= max(2, it_ref // 10)
+    Xh = X.cpu().numpy()
+    R = P.laplacian3d_apply(Xh, gx, gy, gz) - Xh * th[None, :]
+    assert np.all(np.linalg.norm(R, axis=0) <= 1e-6 * np.linalg.norm(Xh, axis=0))
