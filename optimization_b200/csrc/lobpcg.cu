@@ -46,54 +46,78 @@ __global__ void __launch_bounds__(LB_THREADS) blk_stencil7_kernel(unsigned gx, u
   }
 }
 
-// ---- Gram: partial[bx][i][j] = sum over the CTA's rows of A[r, i] * B[r, 64 by + j]  (i < k1, j < min(64, k2 - 64 by)) ----
-constexpr int GR_TR = 16;          // rows per shared-memory tile
-__global__ void __launch_bounds__(LB_THREADS) blk_gram_kernel(unsigned long long m, const double *A, int lda, int k1,
+// ---- Gram on the fp64 tensor cores: partial[bx][i][j] = sum over the CTA's rows of A[r, i] * B[r, 64 by + j] -------
+// (i < k1 <= 192, j < min(64, k2 - 64 by)).  The Grams of LOBPCG are symmetric (S^T A S with A symmetric, S^T B S), and the
+// Rayleigh-Ritz step only uses one triangle (like the reference's self-adjoint eigensolver): only the block-upper
+// triangle is formed, i.e. column block `by` gets the rows i < 64 (by + 1) -- 6 of 9 blocks at ns = 192.
+// mma.sync.m8n8k4.f64: the "A" operand is the transposed S tile (A[i][r] = S[r][i]), the "B" operand the Z tile; the
+// row tiles of the block are dealt round-robin to the 8 warps (up to 3 each), every warp takes all eight column tiles
+// (up to 24 accumulator tiles = 24 independent MMA chains, enough to cover the long dependent-issue latency of the
+// fp64 MMA).  Shared-memory row strides are 4 (mod 16) doubles: conflict-free fragments.
+__device__ __forceinline__ void lb_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+constexpr int GR_TR = 32;          // rows per shared-memory tile (8 k-steps of 4 rows)
+constexpr int GR_LDA = 196;        // 192 + 4
+constexpr int GR_LDB = 68;         // 64 + 4
+__global__ void __launch_bounds__(LB_THREADS, 2) blk_gram_kernel(unsigned long long m, const double *A, int lda, int k1,
                                                               const double *B, int ldb, int k2, double *partial) {
-  __shared__ double As[GR_TR][LB_KMAX];
-  __shared__ double Bs[GR_TR][64];
-  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+  extern __shared__ double gsm[];
+  double *As = gsm;                          // [GR_TR][GR_LDA]
+  double *Bs = gsm + GR_TR * GR_LDA;         // [GR_TR][GR_LDB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;   // fragment coordinates: (row / col index, k index)
   const int j0 = 64 * blockIdx.y;
   const int kb = min(64, k2 - j0);
+  const int it_n = min((k1 + 7) >> 3, 8 * ((int)blockIdx.y + 1));   // row tiles of the block-upper triangle
   const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
-  double acc[12][4];
+  double acc[3][8][2];
 #pragma unroll
-  for (int u = 0; u < 12; ++u)
+  for (int u = 0; u < 3; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int v = 0; v < 8; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
   for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GR_TR) {
     const int rows = (int)min((unsigned long long)GR_TR, r_hi - r0);
     __syncthreads();
-    for (int e = tid; e < GR_TR * k1; e += LB_THREADS) {
-      const int rr = e / k1, c = e - rr * k1;
-      As[rr][c] = rr < rows ? A[(r0 + rr) * lda + c] : 0.0;
+    const int ka = min(8 * it_n, LB_KMAX);    // columns of A this block needs
+    for (int e = tid; e < GR_TR * ka; e += LB_THREADS) {
+      const int rr = e / ka, c = e - rr * ka;
+      As[rr * GR_LDA + c] = (rr < rows && c < k1) ? A[(r0 + rr) * lda + c] : 0.0;
     }
     for (int e = tid; e < GR_TR * 64; e += LB_THREADS) {
       const int rr = e >> 6, c = e & 63;
-      Bs[rr][c] = (rr < rows && c < kb) ? B[(r0 + rr) * ldb + j0 + c] : 0.0;
+      Bs[rr * GR_LDB + c] = (rr < rows && c < kb) ? B[(r0 + rr) * ldb + j0 + c] : 0.0;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int rr = 0; rr < GR_TR; ++rr) {
-      double b[4];
+#pragma unroll 2
+    for (int ks = 0; ks < GR_TR / 4; ++ks) {
+      const int kr = 4 * ks + fk;
+      double bf[8];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) b[v] = Bs[rr][tj + 16 * v];
+      for (int v = 0; v < 8; ++v) bf[v] = Bs[kr * GR_LDB + 8 * v + fr];
 #pragma unroll
-      for (int u = 0; u < 12; ++u) {
-        const double a = (ti + 16 * u < k1) ? As[rr][ti + 16 * u] : 0.0;
+      for (int u = 0; u < 3; ++u) {
+        const int itile = warp + 8 * u;
+        if (itile < it_n) {                   // warp-uniform
+          const double af = As[kr * GR_LDA + 8 * itile + fr];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a, b[v], acc[u][v]);
+          for (int v = 0; v < 8; ++v) lb_dmma(acc[u][v][0], acc[u][v][1], af, bf[v]);
+        }
       }
     }
   }
   double *out = partial + (size_t)blockIdx.x * k1 * k2;
 #pragma unroll
-  for (int u = 0; u < 12; ++u)
+  for (int u = 0; u < 3; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int i = ti + 16 * u, j = tj + 16 * v;
-      if (i < k1 && j < kb) out[(size_t)i * k2 + j0 + j] = acc[u][v];
-    }
+    for (int v = 0; v < 8; ++v)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int i = 8 * (warp + 8 * u) + fr, j = 8 * v + 2 * fk + c;
+        if (warp + 8 * u < it_n && i < k1 && j < kb) out[(size_t)i * k2 + j0 + j] = acc[u][v][c];
+      }
 }
 // G[e] = sum_b partial[b][e], fixed order
 __global__ void blk_reduce_kernel(const double *partial, int nb, int count, double *G) {
@@ -104,54 +128,48 @@ __global__ void blk_reduce_kernel(const double *partial, int nb, int count, doub
   }
 }
 
-// ---- block update: out[m x n2] = S[m x k] * C[k x n2]   (C row-major, ldc) ---------------------------------
+// ---- block update on the fp64 tensor cores: out[m x n2] = S[m x k] * C[k x n2]   (C row-major, ldc; n2 <= 64) ----------
+// 64-row tiles; warp w owns row tile w (8 rows) and all eight 8-column tiles: 8 independent MMA chains of up to 48 k-steps.
 constexpr int GM_TR = 64;
+constexpr int GM_LDS = 196, GM_LDC = 68;
 __global__ void __launch_bounds__(LB_THREADS) blk_gemm_kernel(unsigned long long m, const double *S, int lds, int k,
                                                               const double *C, int ldc, int n2, double *out, int ldo) {
   extern __shared__ double sm[];
-  double *Cs = sm;                         // [k][64]
-  double *Ss = sm + (size_t)LB_KMAX * 64;  // [GM_TR][LB_KMAX]
-  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
-  for (int e = tid; e < k * 64; e += LB_THREADS) {
+  double *Cs = sm;                              // [LB_KMAX][GM_LDC]
+  double *Ss = sm + (size_t)LB_KMAX * GM_LDC;   // [GM_TR][GM_LDS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int k4 = (k + 3) & ~3;
+  for (int e = tid; e < k4 * 64; e += LB_THREADS) {
     const int kk = e >> 6, c = e & 63;
-    Cs[kk * 64 + c] = c < n2 ? C[(size_t)kk * ldc + c] : 0.0;
+    Cs[kk * GM_LDC + c] = (kk < k && c < n2) ? C[(size_t)kk * ldc + c] : 0.0;
   }
   const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
   for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GM_TR) {
     const int rows = (int)min((unsigned long long)GM_TR, r_hi - r0);
     __syncthreads();
-    for (int e = tid; e < GM_TR * k; e += LB_THREADS) {
-      const int rr = e / k, c = e - rr * k;
-      Ss[rr * LB_KMAX + c] = rr < rows ? S[(r0 + rr) * lds + c] : 0.0;
+    for (int e = tid; e < GM_TR * k4; e += LB_THREADS) {
+      const int rr = e / k4, c = e - rr * k4;
+      Ss[rr * GM_LDS + c] = (rr < rows && c < k) ? S[(r0 + rr) * lds + c] : 0.0;
     }
     __syncthreads();
-    double acc[4][4];
+    double acc[8][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 8; ++v) acc[v][0] = acc[v][1] = 0.0;
+    for (int k0 = 0; k0 < k4; k0 += 4) {
+      const double af = Ss[(8 * warp + fr) * GM_LDS + k0 + fk];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-#pragma unroll 4
-    for (int kk = 0; kk < k; ++kk) {
-      double a[4], c[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = Ss[(ti + 16 * u) * LB_KMAX + kk];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) c[v] = Cs[kk * 64 + tj + 16 * v];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], c[v], acc[u][v]);
+      for (int v = 0; v < 8; ++v) lb_dmma(acc[v][0], acc[v][1], af, Cs[(k0 + fk) * GM_LDC + 8 * v + fr]);
     }
+    const int rr = 8 * warp + fr;
+    if (rr < rows)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int rr = ti + 16 * u;
-      if (rr < rows)
+      for (int v = 0; v < 8; ++v)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int c = tj + 16 * v;
-          if (c < n2) out[(r0 + rr) * ldo + c] = acc[u][v];
+        for (int c = 0; c < 2; ++c) {
+          const int col = 8 * v + 2 * fk + c;
+          if (col < n2) out[(r0 + rr) * ldo + col] = acc[v][c];
         }
-    }
   }
 }
 
@@ -209,8 +227,11 @@ __global__ void rr_equilibrate_kernel(int ns, const double *GA, const double *GB
   for (int e = threadIdx.x; e < ns * ns; e += blockDim.x) {
     const int i = e / ns, j = e - i * ns;
     const double w = sD[i] * sD[j];
-    EA[e] = 0.5 * (GA[i * ns + j] + GA[j * ns + i]) * w;
-    EB[e] = 0.5 * (GB[i * ns + j] + GB[j * ns + i]) * w;
+    const int ib = i >> 6, jb = j >> 6;     // only the block-upper triangle of the Grams was formed
+    const double a = ib == jb ? 0.5 * (GA[i * ns + j] + GA[j * ns + i]) : (ib < jb ? GA[i * ns + j] : GA[j * ns + i]);
+    const double b = ib == jb ? 0.5 * (GB[i * ns + j] + GB[j * ns + i]) : (ib < jb ? GB[i * ns + j] : GB[j * ns + i]);
+    EA[e] = a * w;
+    EB[e] = b * w;
   }
 }
 // C[k][j] (row-major, ld ns) = D[k] * Z(k, j), Z column-major eigenvectors from the solver (LOBPCG.h:61)
@@ -240,15 +261,22 @@ cudaError_t launch_blk_stencil7(unsigned gx, unsigned gy, unsigned gz, int k, co
 // G (k1 x k2, row-major) = A^T B ; partial: scratch of nb * k1 * k2 doubles
 cudaError_t launch_blk_gram(unsigned long long m, const double *A, int lda, int k1, const double *B, int ldb, int k2,
                             double *partial, int nb, double *G, cudaStream_t st) {
+  static bool attr = false;
+  const size_t smem = sizeof(double) * ((size_t)GR_TR * GR_LDA + (size_t)GR_TR * GR_LDB);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(blk_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    attr = true;
+  }
   dim3 grid(nb, (k2 + 63) / 64);
-  blk_gram_kernel<<<grid, LB_THREADS, 0, st>>>(m, A, lda, k1, B, ldb, k2, partial);
+  blk_gram_kernel<<<grid, LB_THREADS, smem, st>>>(m, A, lda, k1, B, ldb, k2, partial);
   blk_reduce_kernel<<<(k1 * k2 + 255) / 256, 256, 0, st>>>(partial, nb, k1 * k2, G);
   return cudaGetLastError();
 }
 cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int k, const double *C, int ldc, int n2, double *out,
                             int ldo, int nb, cudaStream_t st) {
   static bool attr = false;
-  const size_t smem = sizeof(double) * ((size_t)LB_KMAX * 64 + (size_t)GM_TR * LB_KMAX);
+  const size_t smem = sizeof(double) * ((size_t)LB_KMAX * GM_LDC + (size_t)GM_TR * GM_LDS);
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(blk_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
@@ -260,8 +288,9 @@ cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int 
 // R, and norms2[0:nx] = column sums of R^2, norms2[nx:2nx] = column sums of X^2
 cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, const double *X,
                                 const double *theta, double *R, double *partial, int nb, double *norms2, cudaStream_t st) {
-  blk_residual_kernel<<<nb, LB_THREADS, 0, st>>>(m, nx, AX, BX, X, theta, R, partial);
-  blk_reduce_kernel<<<1, 256, 0, st>>>(partial, nb, 2 * nx, norms2);
+  const int g = nb * 8;   // several CTAs per SM: the kernel is a plain stream with one load in flight per thread and array
+  blk_residual_kernel<<<g, LB_THREADS, 0, st>>>(m, nx, AX, BX, X, theta, R, partial);
+  blk_reduce_kernel<<<1, 256, 0, st>>>(partial, g, 2 * nx, norms2);
   return cudaGetLastError();
 }
 cudaError_t launch_blk_sumsq(unsigned long long total, const double *V, double *partial, int nb, double *out, cudaStream_t st) {

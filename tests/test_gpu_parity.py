@@ -423,3 +423,27 @@ def test_lobpcg_laplacian_vs_oracle_and_exact_spectrum(ctx):
     Xh = X.cpu().numpy()
     R = P.laplacian3d_apply(Xh, gx, gy, gz) - Xh * th[None, :]
     assert np.all(np.linalg.norm(R, axis=0) <= 1e-6 * np.linalg.norm(Xh, axis=0))
+
+
+def test_lobpcg_full_size_properties(ctx):
+    """Config C4: 160^3 Laplacian (m = 4 096 000), block 64, Jacobi 1/6, a fixed number of iterations; size-independent
+    checks against the analytic spectrum: Ritz values are upper bounds of the exact eigenvalues (Cauchy interlacing),
+    every Ritz value lies within its residual norm of an exact eigenvalue, B-orthonormal Ritz vectors, determinism."""
+    import torch
+    g, nx, nev, iters = 160, 64, 32, 8
+    m = g ** 3
+    X0 = (2.0 * P._torch_uniform01(31, 0, m * nx, "cuda:0") - 1.0).view(m, nx)
+    A, T = ctx.block_laplacian3d(g, g, g), ctx.block_scalar(1.0 / 6.0)
+    th, X, it, nc = ctx.lobpcg(A, None, T, X0, nev, iters, 1e-6)
+    th2, X2, it2, nc2 = ctx.lobpcg(A, None, T, X0, nev, iters, 1e-6)
+    assert it == it2 == iters and np.array_equal(th, th2) and torch.equal(X, X2)         # bitwise reproducible
+    lam1 = 2.0 - 2.0 * np.cos(np.arange(1, g + 1) * np.pi / (g + 1))
+    exact = np.sort((lam1[:, None, None] + lam1[None, :, None] + lam1[None, None, :]).ravel())
+    assert np.all(np.diff(th) >= 0) and np.all(th >= exact[:nev] * (1 - 1e-12))           # interlacing
+    Xc = X.contiguous()
+    R = ctx.block_apply(A, Xc) - Xc * torch.from_numpy(th).to(Xc.device)[None, :]
+    rn = (torch.linalg.norm(R, dim=0) / torch.linalg.norm(Xc, dim=0)).cpu().numpy()
+    dist = np.min(np.abs(th[:, None] - exact[None, :4096]), axis=1)
+    assert np.all(dist <= rn * (1 + 1e-9))                                                # |theta - lambda| <= |r| / |x|
+    G = (Xc.T @ Xc).cpu().numpy()
+    assert np.linalg.norm(G - np.eye(nev)) < 1e-9                                         # X^T B X = I (B = I)
