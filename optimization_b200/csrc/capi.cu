@@ -58,6 +58,8 @@ cudaError_t launch_blk_gram(unsigned long long m, const double *A, int lda, int 
                             double *partial, int nb, double *G, cudaStream_t st);
 cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int k, const double *C, int ldc, int n2, double *out,
                             int ldo, int nb, cudaStream_t st);
+cudaError_t launch_blk_update(unsigned long long m, const double *S, int lds, int ns, int nx, const double *C, int ldc, double *Xo,
+                              int ldx, double *Po, int ldp, int nb, cudaStream_t st);
 cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, const double *X,
                                 const double *theta, double *R, double *partial, int nb, double *norms2, cudaStream_t st);
 cudaError_t launch_blk_sumsq(unsigned long long total, const double *V, double *partial, int nb, double *out, cudaStream_t st);
@@ -83,6 +85,8 @@ struct ob200_context {
   std::string err;
   uint64_t launches = 0;
   cusolverDnHandle_t solver = nullptr;   // LOBPCG: dense generalised eigensolve of the Rayleigh-Ritz pencil (library)
+  unsigned char *lob_ws = nullptr;       // LOBPCG workspace slab (grow-only, reused across calls)
+  size_t lob_cap = 0;
   // workspace
   size_t vec_capacity = 0;        // doubles per work vector
   double *r = nullptr, *p0 = nullptr, *p1 = nullptr, *Hp = nullptr, *gs = nullptr; // gs: staging for g/s (host entry)
@@ -195,6 +199,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaFree(ctx->planes);
   cudaFree(ctx->plane_exp);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  cudaFree(ctx->lob_ws);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OB200_OK;
@@ -893,14 +898,13 @@ static int block_apply(ob200_context *ctx, const ob200_block_operator *Op, uint6
 }
 
 namespace {
-struct DevBuf {   // RAII for the call-local device buffers
-  std::vector<void *> ptrs;
-  ~DevBuf() { for (void *p : ptrs) cudaFree(p); }
-  template <class T> cudaError_t get(T **p, size_t count) {
-    void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
-    if (e == cudaSuccess) { ptrs.push_back(q); *p = static_cast<T *>(q); }
-    return e;
+struct Slab {   // carves 256-byte aligned buffers out of the context's LOBPCG workspace; pass 1 sizes, pass 2 hands out
+  unsigned char *base = nullptr;
+  size_t off = 0;
+  template <class T> void get(T **p, size_t count) {
+    const size_t bytes = (sizeof(T) * (count ? count : 1) + 255) & ~(size_t)255;
+    *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += bytes;
   }
 };
 }  // namespace
@@ -948,31 +952,43 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   const size_t mnx = (size_t)m * nx;
   int rc;
 
-  DevBuf mem;
-  double *S, *AS, *BS = nullptr, *AX, *BX = nullptr, *R, *W = nullptr, *P, *Xn, *tmp;
-  double *GA, *GB, *EA, *EB, *D, *theta, *C, *partial, *norms2, *work;
-  int *info_dev;
-  CK(mem.get(&S, (size_t)m * nsmax));
-  CK(mem.get(&AS, (size_t)m * nsmax));
-  if (B) CK(mem.get(&BS, (size_t)m * nsmax));
-  CK(mem.get(&AX, mnx));
-  if (B) CK(mem.get(&BX, mnx));
-  CK(mem.get(&R, mnx));
-  if (T) CK(mem.get(&W, mnx));
-  CK(mem.get(&P, mnx));
-  CK(mem.get(&Xn, mnx));
-  CK(mem.get(&tmp, mnx));
+  double *S = nullptr, *AS = nullptr, *BS = nullptr, *AX = nullptr, *BX = nullptr, *R = nullptr, *W = nullptr, *P = nullptr,
+         *Xn = nullptr, *tmp = nullptr;
+  double *GA = nullptr, *GB = nullptr, *EA = nullptr, *EB = nullptr, *D = nullptr, *theta = nullptr, *C = nullptr,
+         *partial = nullptr, *norms2 = nullptr, *work = nullptr;
+  int *info_dev = nullptr;
   const size_t nn = (size_t)nsmax * nsmax;
-  CK(mem.get(&GA, nn)); CK(mem.get(&GB, nn)); CK(mem.get(&EA, nn)); CK(mem.get(&EB, nn)); CK(mem.get(&C, nn));
-  CK(mem.get(&D, nsmax)); CK(mem.get(&theta, nsmax));
-  CK(mem.get(&partial, (size_t)nb * nn));
-  CK(mem.get(&norms2, 2 * nx + 8));
-  CK(mem.get(&info_dev, 1));
   int lwork = 0;
-  if (cusolverDnDsygvd_bufferSize(ctx->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nsmax, EA,
-                                  nsmax, EB, nsmax, theta, &lwork) != CUSOLVER_STATUS_SUCCESS)
+  if (cusolverDnDsygvd_bufferSize(ctx->solver, CUSOLVER_EIG_TYPE_1, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, nsmax,
+                                  ctx->dmat, nsmax, ctx->dmat, nsmax, ctx->dmat, &lwork) != CUSOLVER_STATUS_SUCCESS)   // size query only
     return fail(ctx, OB200_CUDA_ERROR, "cusolverDnDsygvd_bufferSize failed");
-  CK(mem.get(&work, (size_t)lwork));
+  for (int pass = 0; pass < 2; ++pass) {
+    Slab mem;
+    mem.base = pass ? ctx->lob_ws : nullptr;
+    mem.get(&S, (size_t)m * nsmax);
+    mem.get(&AS, (size_t)m * nsmax);
+    if (B) mem.get(&BS, (size_t)m * nsmax);
+    mem.get(&AX, mnx);
+    if (B) mem.get(&BX, mnx);
+    mem.get(&R, mnx);
+    if (T) mem.get(&W, mnx);
+    mem.get(&P, mnx);
+    mem.get(&Xn, mnx);
+    mem.get(&tmp, mnx);
+    mem.get(&GA, nn); mem.get(&GB, nn); mem.get(&EA, nn); mem.get(&EB, nn); mem.get(&C, nn);
+    mem.get(&D, (size_t)nsmax); mem.get(&theta, (size_t)nsmax);
+    mem.get(&partial, (size_t)nb * nn + (size_t)nb * 16 * nx);   // Gram partials (nb sets) / residual partials (8 nb sets)
+    mem.get(&norms2, (size_t)2 * nx + 8);
+    mem.get(&info_dev, (size_t)1);
+    mem.get(&work, (size_t)lwork);
+    if (!pass && mem.off > ctx->lob_cap) {
+      cudaFree(ctx->lob_ws);
+      ctx->lob_ws = nullptr;
+      ctx->lob_cap = 0;
+      CK(cudaMalloc(&ctx->lob_ws, mem.off));
+      ctx->lob_cap = mem.off;
+    }
+  }
 
   std::vector<double> h(2 * nx + 8), th(nsmax);
   auto frob = [&](const double *V, double *out) -> int {   // ||V||_F of an m x nx block
@@ -1035,9 +1051,8 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
     CK(launch_blk_gram(m, S, nsmax, ns, BSp, nsmax, ns, partial, nb, GB, st));              // l.230
     ctx->launches += 4;
     if ((rc = rayleigh_ritz(ctx, ns, GA, GB, EA, EB, D, theta, C, work, lwork, info_dev))) return rc;   // l.233
-    CK(launch_blk_gemm(m, S, nsmax, ns, C, ns, nx, Xn, nx, nb, st));                        // l.239  X = S C(:, 1:nx)
-    CK(launch_blk_gemm(m, S + nx, nsmax, ns - nx, C + (size_t)nx * ns, ns, nx, P, nx, nb, st));   // l.249  P = S_{W,P} C_{W,P}
-    ctx->launches += 2;
+    CK(launch_blk_update(m, S, nsmax, ns, nx, C, ns, Xn, nx, P, nx, nb, st));   // l.239 X = S C(:, 1:nx), l.249 P = S_{W,P} C_{W,P}
+    ctx->launches += 1;
     CK(cudaMemcpyAsync(X, Xn, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st));
     if ((rc = block_apply(ctx, A, m, nx, X, nx, AX, nx))) return rc;                        // l.242
     const double *BXq = X;

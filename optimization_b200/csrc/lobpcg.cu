@@ -173,6 +173,60 @@ __global__ void __launch_bounds__(LB_THREADS) blk_gemm_kernel(unsigned long long
   }
 }
 
+// ---- fused LOBPCG update (LOBPCG.h:239 + 249):  P = S[:, nx:ns] C[nx:ns, :],  X = S[:, :nx] C[:nx, :] + P ----------------
+// One pass over S instead of two and ns nx instead of (2 ns - nx) nx multiply-adds per row: the P part of the
+// contraction is shared.  Same tiling as blk_gemm_kernel, two accumulator sets per warp.
+__global__ void __launch_bounds__(LB_THREADS) blk_update_kernel(unsigned long long m, const double *S, int lds, int ns, int nx,
+                                                                const double *C, int ldc, double *Xo, int ldx, double *Po,
+                                                                int ldp) {
+  extern __shared__ double sm[];
+  double *Cs = sm;                              // [LB_KMAX][GM_LDC]
+  double *Ss = sm + (size_t)LB_KMAX * GM_LDC;   // [GM_TR][GM_LDS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int k4 = (ns + 3) & ~3;
+  for (int e = tid; e < k4 * 64; e += LB_THREADS) {
+    const int kk = e >> 6, c = e & 63;
+    Cs[kk * GM_LDC + c] = (kk < ns && c < nx) ? C[(size_t)kk * ldc + c] : 0.0;
+  }
+  const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
+  for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GM_TR) {
+    const int rows = (int)min((unsigned long long)GM_TR, r_hi - r0);
+    __syncthreads();
+    for (int e = tid; e < GM_TR * k4; e += LB_THREADS) {
+      const int rr = e / k4, c = e - rr * k4;
+      Ss[rr * GM_LDS + c] = (rr < rows && c < ns) ? S[(r0 + rr) * lds + c] : 0.0;
+    }
+    __syncthreads();
+    double ax[8][2], ap[8][2];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) ax[v][0] = ax[v][1] = ap[v][0] = ap[v][1] = 0.0;
+    for (int k0 = 0; k0 < k4; k0 += 4) {
+      const double af = Ss[(8 * warp + fr) * GM_LDS + k0 + fk];
+      const bool lowp = k0 < nx, highp = k0 + 3 >= nx;      // k-step touches the X part / the (W, P) part (warp-uniform)
+      const bool mine_low = k0 + fk < nx;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double c = Cs[(k0 + fk) * GM_LDC + 8 * v + fr];
+        if (lowp) lb_dmma(ax[v][0], ax[v][1], af, (highp && !mine_low) ? 0.0 : c);
+        if (highp) lb_dmma(ap[v][0], ap[v][1], af, (lowp && mine_low) ? 0.0 : c);
+      }
+    }
+    const int rr = 8 * warp + fr;
+    if (rr < rows)
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = 8 * v + 2 * fk + c;
+          if (col < nx) {
+            Po[(r0 + rr) * ldp + col] = ap[v][c];
+            Xo[(r0 + rr) * ldx + col] = ax[v][c] + ap[v][c];
+          }
+        }
+  }
+}
+
 // ---- R = AX - BX diag(theta); per-CTA partial column sums of R^2 and X^2 -----------------------------------------
 __global__ void __launch_bounds__(LB_THREADS) blk_residual_kernel(unsigned long long m, int nx, const double *AX, const double *BX,
                                                                   const double *X, const double *theta, double *R,
@@ -283,6 +337,18 @@ cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int 
     attr = true;
   }
   blk_gemm_kernel<<<nb, LB_THREADS, smem, st>>>(m, S, lds, k, C, ldc, n2, out, ldo);
+  return cudaGetLastError();
+}
+cudaError_t launch_blk_update(unsigned long long m, const double *S, int lds, int ns, int nx, const double *C, int ldc, double *Xo,
+                              int ldx, double *Po, int ldp, int nb, cudaStream_t st) {
+  static bool attr = false;
+  const size_t smem = sizeof(double) * ((size_t)LB_KMAX * GM_LDC + (size_t)GM_TR * GM_LDS);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(blk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    attr = true;
+  }
+  blk_update_kernel<<<nb, LB_THREADS, smem, st>>>(m, S, lds, ns, nx, C, ldc, Xo, ldx, Po, ldp);
   return cudaGetLastError();
 }
 // R, and norms2[0:nx] = column sums of R^2, norms2[nx:2nx] = column sums of X^2
