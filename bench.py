@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c2", action="store_true", help="skip the secondary config-C2 (sphere) measurement")
+    ap.add_argument("--no-c2", action="store_true", help="skip the secondary measurements (sphere C2, LOBPCG C4)")
     return ap.parse_args()
 
 
@@ -206,6 +206,32 @@ def sphere_c2(ctx, n=1 << 24, k=16):
         return {"error": repr(e)}
 
 
+def lobpcg_c4(ctx, g=160, nx=64, nev=32, iters=10):
+    """Secondary workload (BASELINE config C4, not the headline): LOBPCG on the 160^3 7-point Laplacian, block 64,
+    Jacobi preconditioner, a fixed number of iterations; time through the public C-ABI call (host-synchronous)."""
+    import time
+    import torch
+    from optimization_b200 import problems as P
+    try:
+        m = g ** 3
+        X0 = (2.0 * P._torch_uniform01(31, 0, m * nx, f"cuda:{ctx.device}") - 1.0).view(m, nx)
+        A, T = ctx.block_laplacian3d(g, g, g), ctx.block_scalar(1.0 / 6.0)
+        ctx.lobpcg(A, None, T, X0, nev, 3, 1e-6)            # warm-up: workspace, cuSOLVER handle
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th, X, it, nc = ctx.lobpcg(A, None, T, X0, nev, iters, 1e-6)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ns = 3 * nx
+        flops = it * (2 * 2 * m * ns * ns + 2 * m * ns * nx)   # two Grams (counted in full) + the fused block update
+        return {"workload": f"LOBPCG, 7-point Laplacian {g}^3 (m = {m}), block nx = {nx}, nev = {nev}, Jacobi 1/6, "
+                            f"{it} iterations", "value": it / dt, "unit": "iterations/s", "ms_per_iteration": 1e3 * dt / it,
+                "bound": "fp64 compute", "achieved_TFLOPs": flops / dt / 1e12,
+                "kernels": "blk_gram_kernel / blk_update_kernel (mma.sync.m8n8k4.f64), blk_stencil7_kernel, cusolverDnDsygvd"}
+    except Exception as e:  # never let the secondary measurement break the headline line
+        return {"error": repr(e)}
+
+
 # ----------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -297,6 +323,7 @@ def run_ours(args):
                        "row GEMM); inside the fused tCG step the HVP never runs stand-alone"}
     clocks = sampler.stop() if sampler else None
     c2 = sphere_c2(ctx) if (world == 1 and not args.no_c2) else None
+    c4 = lobpcg_c4(ctx) if (world == 1 and not args.no_c2) else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -323,6 +350,8 @@ def run_ours(args):
             line["hvp"] = hvp
         if c2:
             line["other_workloads"] = {"sphere_c2": c2}
+            if c4:
+                line["other_workloads"]["lobpcg_c4"] = c4
         if not args.no_cpu_baseline:
             info = cpu_reference(prob, 12)
             line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
