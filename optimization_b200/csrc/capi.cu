@@ -60,8 +60,9 @@ cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int 
                             int ldo, int nb, cudaStream_t st);
 cudaError_t launch_blk_update(unsigned long long m, const double *S, int lds, int ns, int nx, const double *C, int ldc, double *Xo,
                               int ldx, double *Po, int ldp, int nb, cudaStream_t st);
-cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, const double *X,
-                                const double *theta, double *R, double *partial, int nb, double *norms2, cudaStream_t st);
+cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, int ldb, const double *X,
+                                int ldx, const double *theta, double *R, double *partial, int nb, double *norms2,
+                                cudaStream_t st);
 cudaError_t launch_blk_sumsq(unsigned long long total, const double *V, double *partial, int nb, double *out, cudaStream_t st);
 cudaError_t launch_rr_equilibrate(int ns, const double *GA, const double *GB, double *EA, double *EB, double *D,
                                   cudaStream_t st);
@@ -952,8 +953,8 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   const size_t mnx = (size_t)m * nx;
   int rc;
 
-  double *S = nullptr, *AS = nullptr, *BS = nullptr, *AX = nullptr, *BX = nullptr, *R = nullptr, *W = nullptr, *P = nullptr,
-         *Xn = nullptr, *tmp = nullptr;
+  double *S = nullptr, *S2 = nullptr, *AS = nullptr, *BS = nullptr, *AX = nullptr, *BX = nullptr, *R = nullptr, *P = nullptr,
+         *tmp = nullptr;
   double *GA = nullptr, *GB = nullptr, *EA = nullptr, *EB = nullptr, *D = nullptr, *theta = nullptr, *C = nullptr,
          *partial = nullptr, *norms2 = nullptr, *work = nullptr;
   int *info_dev = nullptr;
@@ -966,14 +967,13 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
     Slab mem;
     mem.base = pass ? ctx->lob_ws : nullptr;
     mem.get(&S, (size_t)m * nsmax);
+    mem.get(&S2, (size_t)m * nsmax);     // the update writes the new X straight into the next basis (no copies of X)
     mem.get(&AS, (size_t)m * nsmax);
     if (B) mem.get(&BS, (size_t)m * nsmax);
     mem.get(&AX, mnx);
     if (B) mem.get(&BX, mnx);
     mem.get(&R, mnx);
-    if (T) mem.get(&W, mnx);
     mem.get(&P, mnx);
-    mem.get(&Xn, mnx);
     mem.get(&tmp, mnx);
     mem.get(&GA, nn); mem.get(&GB, nn); mem.get(&EA, nn); mem.get(&EB, nn); mem.get(&C, nn);
     mem.get(&D, (size_t)nsmax); mem.get(&theta, (size_t)nsmax);
@@ -1028,17 +1028,20 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   ctx->launches += 2;
   const double *BXc = tmp;
   if (B) { CK(cudaMemcpyAsync(BX, tmp, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st)); BXc = BX; }
-  CK(launch_blk_residual(m, nx, AX, BXc, X, theta, R, partial, nb, norms2, st));
+  CK(launch_blk_residual(m, nx, AX, BXc, nx, X, nx, theta, R, partial, nb, norms2, st));
   ctx->launches += 2;
 
   uint64_t nc = 0, it = 1;
   const size_t rowX = sizeof(double) * nx, rowS = sizeof(double) * nsmax;
+  // the current eigenvector block lives in the first nx columns of the current basis buffer (leading dimension nsmax)
+  CK(cudaMemcpy2DAsync(S, rowS, X, rowX, rowX, m, cudaMemcpyDeviceToDevice, st));            // l.210 (first iteration)
   for (it = 1; it < max_iters; ++it) {
-    const double *Wp = R;
-    if (T) { if ((rc = block_apply(ctx, T, m, nx, R, nx, W, nx))) return rc; Wp = W; }       // l.207
     const int act = nx - (int)nc;                                                           // soft locking
-    CK(cudaMemcpy2DAsync(S, rowS, X, rowX, rowX, m, cudaMemcpyDeviceToDevice, st));          // l.210
-    CK(cudaMemcpy2DAsync(S + nx, rowS, Wp + nc, rowX, sizeof(double) * act, m, cudaMemcpyDeviceToDevice, st));   // l.213
+    if (T) {   // l.207 + l.213: W = T(R), active columns written straight into the basis
+      if ((rc = block_apply(ctx, T, m, act, R + nc, nx, S + nx, nsmax))) return rc;
+    } else {
+      CK(cudaMemcpy2DAsync(S + nx, rowS, R + nc, rowX, sizeof(double) * act, m, cudaMemcpyDeviceToDevice, st));
+    }
     int ns = 2 * nx - (int)nc;
     if (it > 1) {
       CK(cudaMemcpy2DAsync(S + ns, rowS, P + nc, rowX, sizeof(double) * act, m, cudaMemcpyDeviceToDevice, st));  // l.217
@@ -1051,13 +1054,14 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
     CK(launch_blk_gram(m, S, nsmax, ns, BSp, nsmax, ns, partial, nb, GB, st));              // l.230
     ctx->launches += 4;
     if ((rc = rayleigh_ritz(ctx, ns, GA, GB, EA, EB, D, theta, C, work, lwork, info_dev))) return rc;   // l.233
-    CK(launch_blk_update(m, S, nsmax, ns, nx, C, ns, Xn, nx, P, nx, nb, st));   // l.239 X = S C(:, 1:nx), l.249 P = S_{W,P} C_{W,P}
+    CK(launch_blk_update(m, S, nsmax, ns, nx, C, ns, S2, nsmax, P, nx, nb, st));   // l.239 X = S C(:, 1:nx) -> next basis; l.249 P
     ctx->launches += 1;
-    CK(cudaMemcpyAsync(X, Xn, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st));
-    if ((rc = block_apply(ctx, A, m, nx, X, nx, AX, nx))) return rc;                        // l.242
-    const double *BXq = X;
-    if (B) { if ((rc = block_apply(ctx, B, m, nx, X, nx, BX, nx))) return rc; BXq = BX; }   // l.243
-    CK(launch_blk_residual(m, nx, AX, BXq, X, theta, R, partial, nb, norms2, st));          // l.246, 254
+    std::swap(S, S2);                                                                       // X = S[:, 0:nx] from here on
+    if ((rc = block_apply(ctx, A, m, nx, S, nsmax, AX, nx))) return rc;                     // l.242
+    const double *BXq = S;
+    int ldbx = nsmax;
+    if (B) { if ((rc = block_apply(ctx, B, m, nx, S, nsmax, BX, nx))) return rc; BXq = BX; ldbx = nx; }   // l.243
+    CK(launch_blk_residual(m, nx, AX, BXq, ldbx, S, nsmax, theta, R, partial, nb, norms2, st));   // l.246, 254
     ctx->launches += 2;
     CK(cudaMemcpyAsync(h.data(), norms2, sizeof(double) * 2 * nx, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(th.data(), theta, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
@@ -1069,6 +1073,7 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
     }
     if (nc == nev) break;                                                                   // l.277
   }
+  CK(cudaMemcpy2DAsync(X, rowX, S, rowS, rowX, m, cudaMemcpyDeviceToDevice, st));            // hand the eigenvector block back
   CK(cudaMemcpyAsync(th.data(), theta, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (uint64_t i = 0; i < nev; ++i) theta_host[i] = th[i];

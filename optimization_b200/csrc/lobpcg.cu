@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(LB_THREADS) blk_update_kernel(unsigned long lo
 
 // ---- R = AX - BX diag(theta); per-CTA partial column sums of R^2 and X^2 -----------------------------------------
 __global__ void __launch_bounds__(LB_THREADS) blk_residual_kernel(unsigned long long m, int nx, const double *AX, const double *BX,
-                                                                  const double *X, const double *theta, double *R,
-                                                                  double *partial /* [grid][2 nx] */) {
+                                                                  int ldb, const double *X, int ldx, const double *theta,
+                                                                  double *R, double *partial /* [grid][2 nx] */) {
   __shared__ double s_r[4][64], s_x[4][64];
   const int tid = threadIdx.x, c = tid & 63, g = tid >> 6;     // 4 row groups x 64 columns
   const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(LB_THREADS) blk_residual_kernel(unsigned long 
   if (c < nx) {
     const double th = theta[c];
     for (unsigned long long r = r_lo + g; r < r_hi; r += 4) {
-      const double x = X[r * nx + c];
-      const double v = AX[r * nx + c] - BX[r * nx + c] * th;
+      const double x = X[r * ldx + c];
+      const double v = AX[r * nx + c] - BX[r * ldb + c] * th;
       R[r * nx + c] = v;
       rr = fma(v, v, rr);
       xx = fma(x, x, xx);
@@ -352,10 +352,11 @@ cudaError_t launch_blk_update(unsigned long long m, const double *S, int lds, in
   return cudaGetLastError();
 }
 // R, and norms2[0:nx] = column sums of R^2, norms2[nx:2nx] = column sums of X^2
-cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, const double *X,
-                                const double *theta, double *R, double *partial, int nb, double *norms2, cudaStream_t st) {
+cudaError_t launch_blk_residual(unsigned long long m, int nx, const double *AX, const double *BX, int ldb, const double *X,
+                                int ldx, const double *theta, double *R, double *partial, int nb, double *norms2,
+                                cudaStream_t st) {
   const int g = nb * 8;   // several CTAs per SM: the kernel is a plain stream with one load in flight per thread and array
-  blk_residual_kernel<<<g, LB_THREADS, 0, st>>>(m, nx, AX, BX, X, theta, R, partial);
+  blk_residual_kernel<<<g, LB_THREADS, 0, st>>>(m, nx, AX, BX, ldb, X, ldx, theta, R, partial);
   blk_reduce_kernel<<<1, 256, 0, st>>>(partial, g, 2 * nx, norms2);
   return cudaGetLastError();
 }
