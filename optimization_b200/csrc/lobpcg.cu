@@ -73,6 +73,9 @@ __global__ void __launch_bounds__(LB_THREADS, 2) blk_gram_kernel(unsigned long l
   const int kb = min(64, k2 - j0);
   const int it_n = min((k1 + 7) >> 3, 8 * ((int)blockIdx.y + 1));   // row tiles of the block-upper triangle
   const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
+  // rows 16-byte aligned and of even length: vector loads (the bases of LOBPCG: ld = 3 nx or nx even); else scalar
+  const bool vec = !(lda & 1) && !(ldb & 1) && !((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) &&
+                   !(k1 & 1) && !(kb & 1);
   double acc[3][8][2];
 #pragma unroll
   for (int u = 0; u < 3; ++u)
@@ -81,14 +84,43 @@ __global__ void __launch_bounds__(LB_THREADS, 2) blk_gram_kernel(unsigned long l
   for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GR_TR) {
     const int rows = (int)min((unsigned long long)GR_TR, r_hi - r0);
     __syncthreads();
-    const int ka = min(8 * it_n, LB_KMAX);    // columns of A this block needs
-    for (int e = tid; e < GR_TR * ka; e += LB_THREADS) {
-      const int rr = e / ka, c = e - rr * ka;
-      As[rr * GR_LDA + c] = (rr < rows && c < k1) ? A[(r0 + rr) * lda + c] : 0.0;
-    }
-    for (int e = tid; e < GR_TR * 64; e += LB_THREADS) {
-      const int rr = e >> 6, c = e & 63;
-      Bs[rr * GR_LDB + c] = (rr < rows && c < kb) ? B[(r0 + rr) * ldb + j0 + c] : 0.0;
+    const int ka = min(8 * it_n, LB_KMAX);    // columns of A this block needs (a multiple of 8)
+    if (vec) {
+      // 16-byte loads, no index division: lane -> column pair (+32, +64), warp -> rows (+8, +16, +24); all loads of a
+      // thread are independent and issued back to back
+      const int tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+      for (int ra = 0; ra < 4; ++ra) {
+        const int rr = ty + 8 * ra;
+        const bool rok = rr < rows;
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          const int c2 = tx + 32 * cb;                    // double2 index within the row
+          if (2 * c2 < ka) {
+            double2 v = make_double2(0.0, 0.0);
+            if (rok && 2 * c2 < k1) {
+              v = *reinterpret_cast<const double2 *>(A + (r0 + rr) * lda + 2 * c2);
+              if (2 * c2 + 1 >= k1) v.y = 0.0;
+            }
+            *reinterpret_cast<double2 *>(As + rr * GR_LDA + 2 * c2) = v;
+          }
+        }
+        double2 w = make_double2(0.0, 0.0);
+        if (rok && 2 * tx < kb) {
+          w = *reinterpret_cast<const double2 *>(B + (r0 + rr) * ldb + j0 + 2 * tx);
+          if (2 * tx + 1 >= kb) w.y = 0.0;
+        }
+        *reinterpret_cast<double2 *>(Bs + rr * GR_LDB + 2 * tx) = w;
+      }
+    } else {
+      for (int e = tid; e < GR_TR * ka; e += LB_THREADS) {
+        const int rr = e / ka, c = e - rr * ka;
+        As[rr * GR_LDA + c] = (rr < rows && c < k1) ? A[(r0 + rr) * lda + c] : 0.0;
+      }
+      for (int e = tid; e < GR_TR * 64; e += LB_THREADS) {
+        const int rr = e >> 6, c = e & 63;
+        Bs[rr * GR_LDB + c] = (rr < rows && c < kb) ? B[(r0 + rr) * ldb + j0 + c] : 0.0;
+      }
     }
     __syncthreads();
 #pragma unroll 2
