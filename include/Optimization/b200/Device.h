@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "Optimization/LinearAlgebra/IterativeSolvers.h"
+#include "Optimization/LinearAlgebra/LOBPCG.h"
 #include "Optimization/Riemannian/Concepts.h"
 #include "Optimization/Riemannian/GradientDescent.h"
 #include "Optimization/Riemannian/TNT.h"
@@ -196,6 +197,40 @@ inline DeviceMatrix fused_stpcg(const OperatorState &st, const DeviceMatrix *min
   return s;
 }
 
+// ---- block operators for LOBPCG: descriptor functors (callable, and recognised by LinearAlgebra::LOBPCG) ---------
+struct BlockOperator {
+  ob200_context *ctx = nullptr;
+  ob200_block_operator op{};
+  std::shared_ptr<const DeviceMatrix> diag;    // keeps the diagonal alive for OB200_BLK_DIAG
+  DeviceMatrix operator()(const DeviceMatrix &X) const {
+    DeviceMatrix out = X.like();
+    check(ctx, ob200_block_apply(ctx, &op, X.rows(), X.cols(), X.data(), X.cols(), out.data(), X.cols()));
+    return out;
+  }
+  static BlockOperator diagonal(ob200_context *c, size_t m, const double *d_host) {
+    BlockOperator b;
+    b.ctx = c;
+    b.diag = std::make_shared<const DeviceMatrix>(c, m, 1, d_host);
+    b.op.kind = OB200_BLK_DIAG;
+    b.op.diag_dev = b.diag->data();
+    return b;
+  }
+  static BlockOperator scalar(ob200_context *c, double alpha) {
+    BlockOperator b;
+    b.ctx = c;
+    b.op.kind = OB200_BLK_SCALAR;
+    b.op.alpha = alpha;
+    return b;
+  }
+  static BlockOperator laplacian3d(ob200_context *c, uint32_t gx, uint32_t gy, uint32_t gz) {
+    BlockOperator b;
+    b.ctx = c;
+    b.op.kind = OB200_BLK_STENCIL7;
+    b.op.gx = gx; b.op.gy = gy; b.op.gz = gz;
+    return b;
+  }
+};
+
 // ---- Stiefel trace minimisation  f(Y) = 1/2 tr(Y^T A Y),  A block-diagonal bf16 -----------------
 // Provides the functor set TNT<DeviceMatrix, DeviceMatrix, double>(f, QM, metric, retract, Y0, ...) takes.
 class StiefelTraceMin {
@@ -352,6 +387,33 @@ struct InnerViews<b200::DeviceMatrix, b200::DeviceMatrix, double, Args...> {
 };
 }  // namespace detail
 }  // namespace Riemannian
+
+// ---- dispatch hook of LOBPCG for device block vectors --------------------------------------------------------
+namespace LinearAlgebra {
+namespace detail {
+template <>
+struct DeviceLOBPCG<std::vector<double>, b200::DeviceMatrix, double> {
+  using M = b200::DeviceMatrix;
+  using Op = SymmetricLinearOperator<M>;
+  static bool run(const Op &A, const std::optional<Op> &B, const std::optional<Op> &T, const M &X0, size_t nev, size_t max_iters,
+                  size_t &num_iters, size_t &nc, double tau, std::pair<std::vector<double>, M> &out) {
+    const b200::BlockOperator *a = A.template target<b200::BlockOperator>();
+    const b200::BlockOperator *b = B ? B->template target<b200::BlockOperator>() : nullptr;
+    const b200::BlockOperator *t = T ? T->template target<b200::BlockOperator>() : nullptr;
+    if (!a || (B && !b) || (T && !t)) return false;
+    M X = X0;
+    std::vector<double> theta(nev, 0.0);
+    uint64_t it = 0, conv = 0;
+    b200::check(a->ctx, ob200_lobpcg(a->ctx, &a->op, b ? &b->op : nullptr, t ? &t->op : nullptr, X.rows(), X.cols(), X.data(),
+                                     nev, max_iters, tau, nullptr, theta.data(), &it, &conv));
+    num_iters = it;
+    nc = conv;
+    out = std::make_pair(std::move(theta), std::move(X));   // X: m x nx, the first nev columns are the eigenvector estimates
+    return true;
+  }
+};
+}  // namespace detail
+}  // namespace LinearAlgebra
 
 // ---- dispatch hook of STPCG for device matrices ---------------------------------------------------
 namespace LinearAlgebra {

@@ -189,7 +189,8 @@ def test_header_layer_has_reference_layout():
     for rel in ("Optimization/Base/Concepts.h", "Optimization/Riemannian/Concepts.h",
                 "Optimization/Riemannian/TNT.h", "Optimization/Riemannian/GradientDescent.h",
                 "Optimization/Riemannian/TNLS.h", "Optimization/LinearAlgebra/Concepts.h",
-                "Optimization/LinearAlgebra/IterativeSolvers.h", "Optimization/Util/Stopwatch.h",
+                "Optimization/LinearAlgebra/IterativeSolvers.h", "Optimization/LinearAlgebra/LOBPCG.h",
+                "Optimization/Util/Stopwatch.h",
                 "Optimization/b200/Device.h", "optimization_b200.h"):
         assert os.path.exists(os.path.join(ROOT, "include", rel)), rel
 
@@ -263,3 +264,31 @@ def test_device_sphere_tnt_matches_reference_golden(golden, tmp_path):
     x = np.fromfile(xo)
     x_ref = arr["sphere100_tnt_x"]
     assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-10     # final iterate
+
+
+@pytest.mark.gpu
+def test_device_lobpcg_header_entry_point(tmp_path):
+    """LinearAlgebra::LOBPCG<std::vector<double>, DeviceMatrix>(A, B, T, X0, nev, max_iters, num_iters, nc, tau) with
+    block-operator descriptor functors: the diagonal problems of the reference's LOBPCG unit tests against the CPU
+    restatement and the exact spectrum."""
+    from oracle import lobpcg_port as L
+    exe = _compile("lobpcg_device_check", link=True)
+    n, nx, nev = 1000, 10, 5
+    ad, bd = np.linspace(-.5 * n, .5 * n, n), np.linspace(1.0, n, n)
+    X0 = (2.0 * P.uniform01(91, 0, n * nx) - 1.0).reshape(n, nx)
+    f = tmp_path / "lob.bin"
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<QQ", n, nx))
+        for a in (ad, bd, X0):
+            fh.write(np.ascontiguousarray(a).tobytes())
+    got = _lines(subprocess.run([exe, str(f)], check=True, capture_output=True, text=True).stdout)
+    A, B, T = (lambda X: ad[:, None] * X), (lambda X: bd[:, None] * X), (lambda X: np.abs(ad)[:, None] * X)
+    for name, Bop, exact in (("diag", None, ad[:nev]), ("diag_generalized", B, np.sort(ad / bd)[:nev])):
+        th_ref, _, it_ref, nc_ref = L.lobpcg(A, Bop, T, X0, nev, n, 1e-8, Omega=X0)
+        g = got[name]
+        assert g["nc"] == nc_ref == nev and g["x_cols"] == nx
+        assert np.linalg.norm(np.array(g["theta"]) - exact) < 1e-4                     # the reference tests' bar
+        assert np.allclose(g["theta"], th_ref, rtol=1e-9, atol=1e-9)
+        assert abs(g["num_iters"] - it_ref) <= max(2, it_ref // 10)
+    assert got["apply"]["max_err"] == 0.0
+    assert got["invalid_argument"]["thrown"] == 2
