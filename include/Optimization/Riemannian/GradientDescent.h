@@ -48,6 +48,28 @@ struct GradientDescentResult : public SmoothOptimizerResult<Variable, Scalar> {
   std::vector<size_t> linesearch_iterations;   // trial stepsizes used by each accepted iteration
 };
 
+namespace detail {
+// closing report of a verbose run: one line naming the stopping rule that fired and the quantity it tested
+template <typename Scalar>
+void report_gradient_descent(GradientDescentStatus why, Scalar gnorm, Scalar rel_decrease, Scalar step_norm, Scalar f,
+                             double seconds, const GradientDescentParams<Scalar> &prm) {
+  std::cout << "\n\nGradient descent stopped: ";
+  switch (why) {
+    case GradientDescentStatus::Gradient: std::cout << "gradient norm " << gnorm << " below " << prm.gradient_tolerance; break;
+    case GradientDescentStatus::RelativeDecrease:
+      std::cout << "relative decrease " << rel_decrease << " below " << prm.relative_decrease_tolerance;
+      break;
+    case GradientDescentStatus::Stepsize: std::cout << "step length " << step_norm << " below " << prm.stepsize_tolerance; break;
+    case GradientDescentStatus::LineSearch:
+      std::cout << "no sufficient decrease within " << prm.max_ls_iterations << " trial stepsizes";
+      break;
+    case GradientDescentStatus::IterationLimit: std::cout << "iteration limit " << prm.max_iterations << " reached"; break;
+    case GradientDescentStatus::ElapsedTime: std::cout << "time limit " << prm.max_computation_time << " s exceeded"; break;
+  }
+  std::cout << "\n  f = " << f << ", |grad f| = " << gnorm << ", " << seconds << " s\n" << std::endl;
+}
+}  // namespace detail
+
 template <typename Variable, typename Tangent, typename Scalar = double, typename... Args>
 GradientDescentResult<Variable, Scalar>
 GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField<Variable, Tangent, Args...> &grad_f,
@@ -86,7 +108,7 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
 
   if (talk) {
     std::cout << std::scientific << std::setprecision(int(params.precision));
-    std::cout << "Gradient descent optimization: " << std::endl << std::endl;
+    std::cout << "Riemannian gradient descent (Armijo backtracking)\n" << std::endl;
   }
 
   const auto t0 = Stopwatch::tick();
@@ -101,8 +123,8 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
     out.gradient_norms.push_back(gnorm);
     if (params.log_iterates) out.iterates.push_back(x);
     if (talk)
-      std::cout << "Iter: " << std::setw(it_width) << it << ", time: " << now << ", f: "
-                << std::setw(int(params.precision) + 7) << fx << ", |g|: " << gnorm;
+      std::cout << "[" << std::setw(it_width) << it << "] t " << now << "  f " << std::setw(int(params.precision) + 7) << fx
+                << "  |grad| " << gnorm;
 
     if (gnorm < params.gradient_tolerance) {
       out.status = GradientDescentStatus::Gradient;
@@ -126,7 +148,7 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
       df = fx - f_trial;
       accepted = df > params.sigma * t * gnorm * gnorm;
     }
-    if (talk) std::cout << ", ls iters: " << std::setw(ls_width) << trials;
+    if (talk) std::cout << "  trials " << std::setw(ls_width) << trials;
     if (!accepted) {
       out.status = GradientDescentStatus::LineSearch;
       break;
@@ -137,7 +159,7 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
     out.linesearch_iterations.push_back(trials);
     out.update_step_norms.push_back(step_norm);
     if (user_function) (*user_function)(it, now, x, fx, g, h, df, args...);
-    if (talk) std::cout << ", |h|: " << step_norm << ", df: " << df;
+    if (talk) std::cout << "  |step| " << step_norm << "  decrease " << df;
 
     // move
     x = x_trial;
@@ -161,35 +183,7 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
   out.f = fx;
   out.gradfx_norm = gnorm;
 
-  if (talk) {
-    std::cout << std::endl << std::endl << "Optimization finished!" << std::endl;
-    switch (out.status) {
-      case GradientDescentStatus::Gradient:
-        std::cout << "Found first-order critical point! (Gradient norm: " << gnorm << ")" << std::endl;
-        break;
-      case GradientDescentStatus::RelativeDecrease:
-        std::cout << "Algorithm terminated due to insufficient relative decrease: " << rel_decrease << " < "
-                  << params.relative_decrease_tolerance << std::endl;
-        break;
-      case GradientDescentStatus::Stepsize:
-        std::cout << "Algorithm terminated due to excessively small step size: |h| = " << step_norm << " < "
-                  << params.stepsize_tolerance << std::endl;
-        break;
-      case GradientDescentStatus::LineSearch:
-        std::cout << "Algorithm terminated due to linesearch's inability to find a stepsize with sufficient decrease"
-                  << std::endl;
-        break;
-      case GradientDescentStatus::IterationLimit:
-        std::cout << "Algorithm exceeded maximum number of outer iterations" << std::endl;
-        break;
-      case GradientDescentStatus::ElapsedTime:
-        std::cout << "Algorithm exceeded maximum allowed computation time: " << out.elapsed_time << " > "
-                  << params.max_computation_time << std::endl;
-        break;
-    }
-    std::cout << "Final objective value: " << out.f << std::endl;
-    std::cout << "Total elapsed computation time: " << out.elapsed_time << " seconds" << std::endl << std::endl;
-  }
+  if (talk) detail::report_gradient_descent(out.status, gnorm, rel_decrease, step_norm, out.f, out.elapsed_time, params);
   return out;
 }
 

@@ -134,7 +134,7 @@ TNLS(const Mapping<VariableX, VectorY, Args...> &F, const JacobianPairFunction<V
 
   if (talk) {
     std::cout << std::scientific << std::setprecision(int(params.precision));
-    std::cout << "Truncated-Newton trust-region optimization: " << std::endl << std::endl;
+    std::cout << "Truncated-Newton least squares (trust region, inner solver LSQR)\n" << std::endl;
   }
 
   const auto t0 = Stopwatch::tick();
@@ -150,8 +150,8 @@ TNLS(const Mapping<VariableX, VectorY, Args...> &F, const JacobianPairFunction<V
     out.trust_region_radius.push_back(Delta);
     if (params.log_iterates) out.iterates.push_back(x);
     if (talk)
-      std::cout << "Iter: " << std::setw(it_width) << it << ", time: " << now << ", |F(x)|: "
-                << std::setw(int(params.precision) + 7) << Fnorm << ", |grad|: " << gnorm;
+      std::cout << "[" << std::setw(it_width) << it << "] t " << now << "  |F| " << std::setw(int(params.precision) + 7) << Fnorm
+                << "  |grad| " << gnorm;
 
     if (Fnorm < params.root_tolerance) {
       out.status = TNLSStatus::Root;
@@ -172,8 +172,7 @@ TNLS(const Mapping<VariableX, VectorY, Args...> &F, const JacobianPairFunction<V
     if (precon) h = precon->first(x, h, args...);   // back to the original coordinates
     hnorm = std::sqrt(metric_X(x, h, h, args...));
     if (talk)
-      std::cout << ", Delta: " << Delta << ", inner iters: " << std::setw(in_width) << inner << ", |h|: " << hnorm
-                << ", |h|_M: " << h_M_norm;
+      std::cout << "  radius " << Delta << "  LSQR " << std::setw(in_width) << inner << "  |h| " << hnorm << "  |h|_M " << h_M_norm;
 
     // trial point, actual vs predicted decrease of |F|^2
     VariableX x_trial = retract_X(x, h, args...);
@@ -189,8 +188,8 @@ TNLS(const Mapping<VariableX, VectorY, Args...> &F, const JacobianPairFunction<V
     const Scalar rho = actual / predicted;
     const bool accepted = !std::isnan(rho) && rho > params.eta1;
     if (talk)
-      std::cout << ", dL: " << std::setw(int(params.precision) + 7) << dL << ", rho: "
-                << std::setw(int(params.precision) + 7) << rho << ". " << (accepted ? "Step accepted" : "Step REJECTED!");
+      std::cout << "  decrease " << std::setw(int(params.precision) + 7) << dL << "  gain " << std::setw(int(params.precision) + 7)
+                << rho << (accepted ? "  accepted" : "  rejected");
 
     out.inner_iterations.push_back(inner);
     out.update_step_norms.push_back(hnorm);
@@ -238,40 +237,13 @@ TNLS(const Mapping<VariableX, VectorY, Args...> &F, const JacobianPairFunction<V
   out.gradfx_norm = gnorm;
 
   if (talk) {
-    std::cout << std::endl << std::endl << "Optimization finished!" << std::endl;
-    switch (out.status) {
-      case TNLSStatus::Root:
-        std::cout << "Found root of F(x) = 0! (Residual norm: " << Fnorm << ")" << std::endl;
-        break;
-      case TNLSStatus::Gradient:
-        std::cout << "Found first-order critical point! (Gradient norm: " << gnorm << ")" << std::endl;
-        break;
-      case TNLSStatus::RelativeDecrease:
-        std::cout << "Algorithm terminated due to insufficient relative decrease: " << rel_decrease << " < "
-                  << params.relative_decrease_tolerance << std::endl;
-        break;
-      case TNLSStatus::Stepsize:
-        std::cout << "Algorithm terminated due to excessively small step size: |h| = " << hnorm << " < "
-                  << params.stepsize_tolerance << std::endl;
-        break;
-      case TNLSStatus::TrustRegion:
-        std::cout << "Algorithm terminated due to excessively small trust region radius: " << Delta << " < "
-                  << params.Delta_tolerance << std::endl;
-        break;
-      case TNLSStatus::IterationLimit:
-        std::cout << "Algorithm exceeded maximum number of outer iterations" << std::endl;
-        break;
-      case TNLSStatus::ElapsedTime:
-        std::cout << "Algorithm exceeded maximum allowed computation time: (" << out.elapsed_time << " > "
-                  << params.max_computation_time << " seconds)" << std::endl;
-        break;
-      case TNLSStatus::UserFunction:
-        std::cout << "Algorithm terminated due to user-supplied stopping criterion" << std::endl;
-        break;
-    }
-    std::cout << "Final objective value: " << out.f << std::endl;
-    std::cout << "Norm of Riemannian gradient: " << out.gradfx_norm << std::endl;
-    std::cout << "Total elapsed computation time: " << out.elapsed_time << " seconds" << std::endl << std::endl;
+    static const char *const why[] = {"residual norm below root_tolerance", "gradient norm below gradient_tolerance",
+                                      "relative decrease below relative_decrease_tolerance",
+                                      "step length below stepsize_tolerance", "trust-region radius below Delta_tolerance",
+                                      "iteration limit reached", "time limit exceeded", "stopped by the user function"};
+    std::cout << "\n\nTNLS stopped: " << why[int(out.status)] << "\n  |F(x)| = " << out.f << ", |grad| = " << out.gradfx_norm
+              << ", last relative decrease " << rel_decrease << ", last |h| " << hnorm << ", Delta " << Delta << ", "
+              << out.elapsed_time << " s\n" << std::endl;
     std::cout << std::defaultfloat << std::setprecision(6);
   }
   return out;
