@@ -64,3 +64,30 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./](refapi|_ref|stpcg_port|liboracle)",
                                      txt, flags=re.M), f
+
+
+def test_ctypes_mirror_matches_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/optimization_b200.h as the C compiler lays it out == the ctypes
+    mirror in optimization_b200/capi.py (an ABI drift would corrupt descriptors silently)."""
+    import ctypes as C
+    import subprocess
+    structs = {"ob200_operator": capi.Operator, "ob200_precon": capi.Precon, "ob200_stpcg_params": capi.StpcgParams,
+               "ob200_stpcg_result": capi.StpcgResult, "ob200_block_operator": capi.BlockOperator}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "optimization_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.splitlines():
+        parts = line.split()
+        cls = structs[parts[0]]
+        assert int(parts[1]) == C.sizeof(cls), parts[0]
+        offs = [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert [int(x) for x in parts[2:]] == offs, parts[0]
