@@ -113,19 +113,29 @@ def measured_peak():
 # ----------------------------------------------------------------------------------
 # CPU reference arm: the reference's own STPCG header (oracle/_ref) on host cores
 # ----------------------------------------------------------------------------------
-def cpu_reference(prob, max_iterations, repeats=1):
-    """Times the reference CPU path on a bounded sample: ONE solve of the same
-    workload capped at `max_iterations` CG iterations, all host threads."""
+def host_cores():
+    """Host cores this process may use (NOT OMP_NUM_THREADS: torch.distributed.run forces that to 1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(prob, max_iterations, threads=None, repeats=1):
+    """Times the reference CPU path on a bounded sample: ONE solve of the same workload capped at
+    `max_iterations` CG iterations on `threads` OpenMP threads (default: every host core, set through the
+    stand-in type's own num_threads() clause, so the launcher's OMP_NUM_THREADS does not matter)."""
     from oracle import refapi
     kind = "reference"
+    kw = dict(SOLVE, max_iterations=max_iterations)
     try:
         R = refapi.RefOracle()
-        threads = R.max_threads()
+        threads = host_cores() if threads is None else int(threads)
         R.set_threads(threads)
         rs = R.stiefel(prob)
 
         def run():
-            return rs.stpcg(prob.Y0, prob.g, **dict(SOLVE, max_iterations=max_iterations))[2]
+            return rs.stpcg(prob.Y0, prob.g, **kw)
     except (FileNotFoundError, OSError):
         kind = "port"
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
@@ -133,17 +143,28 @@ def cpu_reference(prob, max_iterations, repeats=1):
         threads = 1
 
         def run():
-            return Pt.stpcg_stiefel(prob, prob.Y0, prob.g, **dict(SOLVE, max_iterations=max_iterations))[2]
-    best = None
-    its = 0
+            return Pt.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)[:3]
+    best, out = None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        its = run()
+        out = run()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return dict(value=its / best, unit=UNIT, cores=threads, kind=kind, seconds=best, iterations=its,
+    s_ref, mnorm, its = out[0], out[1], out[2]
+    return dict(value=its / best, unit=UNIT, cores=threads, kind=kind, seconds=best, iterations=its, s=s_ref,
+                update_step_M_norm=mnorm,
                 sample=f"one solve capped at {max_iterations} CG iterations ({its} run) of the same workload, "
-                       f"{threads} OpenMP threads of {os.cpu_count()} host cores; HostMat stand-in for Eigen")
+                       f"{threads} OpenMP thread(s) of {host_cores()} host cores; HostMat stand-in for Eigen")
+
+
+def cpu_baseline_rows(prob, full=True):
+    """all-core row (a full solve to the natural residual target when `full`: it doubles as the parity
+    reference) and the Eigen-faithful 1-thread row (capped at 12 iterations)."""
+    allc = cpu_reference(prob, SOLVE["max_iterations"] if full else 12)
+    one = cpu_reference(prob, 12, threads=1)
+    row = {k: allc[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    row["one_thread"] = {k: one[k] for k in ("value", "unit", "cores", "sample")}
+    return row, allc
 
 
 def run_reference(args):
@@ -163,13 +184,15 @@ def run_reference(args):
         its += info["iterations"]
     dt = time.perf_counter() - t0
     v = its / dt
+    one = cpu_reference(prob, cap, threads=1)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": workload_name(args.n),
                                             "step": f"one reference STPCG solve capped at {cap} iterations"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                             "sample": info["sample"]},
+                             "sample": info["sample"],
+                             "one_thread": {k: one[k] for k in ("value", "unit", "cores", "sample")}},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -230,6 +253,47 @@ def lobpcg_c4(ctx, g=160, nx=64, nev=32, iters=10):
                 "kernels": "blk_gram_kernel / blk_update_kernel (mma.sync.m8n8k4.f64), blk_stencil7_kernel, cusolverDnDsygvd"}
     except Exception as e:  # never let the secondary measurement break the headline line
         return {"error": repr(e)}
+
+
+def stiefel_fallbacks(ctx, prob, n):
+    """The headline kernel needs every block of A to be 22-bit block-fixed-point (the synthetic A is, by
+    construction).  Secondary measurements of what other operators get: (i) the same A with the tcgen05 path switched
+    off (fp64 tensor-core kernel), (ii) a generic bf16 A (bell-shaped off-diagonals rounded to bf16: exponent spread
+    of ~26 bits per block), which the library routes to the fp64 tensor-core kernel by itself."""
+    import torch
+    from optimization_b200 import problems as P
+    from optimization_b200.sharded import SingleStiefel
+    out = {}
+    try:
+        peak, _ = measured_peak()
+
+        def rate(solver):
+            for _ in range(2):
+                solver.solve_device(**SOLVE)
+            its, kms = 0, 0.0
+            for _ in range(5):
+                o = solver.solve_device(**SOLVE)
+                its += o.num_iterations
+                kms += o.solve_kernel_ms
+            ach = solver.step_bytes_total() * its / kms / 1e6
+            return {"value": its / (kms * 1e-3), "unit": UNIT, "cg_iterations_per_solve": its / 5,
+                    "kernel_path": ctx.last_path, "achieved_GBps": ach, "frac_of_measured_peak": ach / peak}
+        s0 = SingleStiefel(ctx, prob)
+        ctx.set_option("tcgen05", 0)
+        try:
+            out["stiefel_dmma_fallback"] = dict(rate(s0), workload="same workload, ob200_set_option('tcgen05', 0): "
+                                                "tcg_stiefel_kernel (A p on the fp64 tensor cores)")
+        finally:
+            ctx.set_option("tcgen05", 1)
+        del s0
+        torch.cuda.empty_cache()
+        pg = P.make_stiefel_critical(n, 32, generic_bf16=True)
+        s1 = SingleStiefel(ctx, pg)
+        out["stiefel_generic_bf16_A"] = dict(rate(s1), workload="make_stiefel_critical(generic_bf16=True): off-diagonals "
+                                             "= bf16-rounded bell-shaped samples (not block-fixed-point); default options")
+    except Exception as e:  # never let the secondary measurement break the headline line
+        out["error"] = repr(e)
+    return out
 
 
 # ----------------------------------------------------------------------------------
@@ -322,8 +386,49 @@ def run_ours(args):
                "what": "ob200_hvp (stand-alone Hess f(Y)[V]: block contraction, projection Gram read back by the host, "
                        "row GEMM); inside the fused tCG step the HVP never runs stand-alone"}
     clocks = sampler.stop() if sampler else None
+    # ---- parity inside the bench: the solve just timed against the reference's own STPCG on the host, and
+    #      (N > 1) bit identity of the row-sharded solve with a one-GPU solve of the whole problem -----------------
+    out = solver.solve_device(**SOLVE)
+    s_loc = out.s.cpu().numpy()
+    parity = None
+    cpu_rows = None
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (solver.lo, s_loc))
+        s_full = np.concatenate([p_[1] for p_ in sorted(parts, key=lambda t: t[0])], axis=0) if rank == 0 else None
+    else:
+        s_full = s_loc
+    if rank == 0:
+        parity = {"num_iterations": int(out.num_iterations), "exit_reason": out.exit_reason}
+        if world > 1:
+            c1 = Context(local)                          # independent one-GPU context, whole problem
+            from optimization_b200.sharded import SingleStiefel
+            o1 = SingleStiefel(c1, prob).solve_device(**SOLVE)
+            s1 = o1.s.cpu().numpy()
+            parity["vs_one_gpu"] = {"bit_identical": bool(np.array_equal(s1, s_full)
+                                                          and o1.num_iterations == out.num_iterations
+                                                          and o1.exit_reason == out.exit_reason
+                                                          and o1.update_step_M_norm == out.update_step_M_norm),
+                                    "max_abs_diff": float(np.abs(s1 - s_full).max()),
+                                    "num_iterations_one_gpu": int(o1.num_iterations)}
+            c1.close()
+        if not args.no_cpu_baseline:
+            cpu_rows, ref = cpu_baseline_rows(prob, full=True)
+            s_ref = ref["s"]
+            parity["vs_reference"] = {
+                "oracle": f"oracle/_ref (the reference's own IterativeSolvers.h STPCG, {ref['cores']} threads)"
+                          if ref["kind"] == "reference" else "oracle/stpcg_port.c (C restatement)",
+                "num_iterations_reference": int(ref["iterations"]),
+                "iterations_equal": bool(int(ref["iterations"]) == int(out.num_iterations)),
+                "rel_err_s": float(np.linalg.norm(s_full - s_ref) / np.linalg.norm(s_ref)),
+                "rel_err_update_step_M_norm": float(abs(out.update_step_M_norm - ref["update_step_M_norm"])
+                                                    / abs(ref["update_step_M_norm"])),
+                "tolerance": 1e-10}
+            parity["vs_reference"]["ok"] = bool(parity["vs_reference"]["iterations_equal"]
+                                                and parity["vs_reference"]["rel_err_s"] < 1e-10)
     c2 = sphere_c2(ctx) if (world == 1 and not args.no_c2) else None
     c4 = lobpcg_c4(ctx) if (world == 1 and not args.no_c2) else None
+    fb = stiefel_fallbacks(ctx, prob, n) if (world == 1 and not args.no_c2) else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -352,9 +457,12 @@ def run_ours(args):
             line["other_workloads"] = {"sphere_c2": c2}
             if c4:
                 line["other_workloads"]["lobpcg_c4"] = c4
-        if not args.no_cpu_baseline:
-            info = cpu_reference(prob, 12)
-            line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if fb:
+                line["other_workloads"].update(fb)
+        if parity:
+            line["parity"] = parity
+        if cpu_rows:
+            line["cpu_baseline"] = cpu_rows
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -139,7 +139,7 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
     Tangent h;
     Variable x_trial;
     Scalar f_trial = fx, df = 0;
-    while (!accepted && trials < params.max_ls_iterations) {
+    do {   // at least one trial even when max_ls_iterations == 0, like the reference (GradientDescent.h:270-286)
       ++trials;
       t *= params.beta;
       h = -t * g;
@@ -147,7 +147,7 @@ GradientDescent(const Objective<Variable, Scalar, Args...> &f, const VectorField
       f_trial = f(x_trial, args...);
       df = fx - f_trial;
       accepted = df > params.sigma * t * gnorm * gnorm;
-    }
+    } while (!accepted && trials < params.max_ls_iterations);
     if (talk) std::cout << "  trials " << std::setw(ls_width) << trials;
     if (!accepted) {
       out.status = GradientDescentStatus::LineSearch;

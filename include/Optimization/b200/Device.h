@@ -108,6 +108,16 @@ class DeviceMatrix {
     check(ctx_, ob200_axpby(ctx_, size(), a, d_, 0.0, nullptr, d_));
     return *this;
   }
+  // true elementwise division (the `u /= beta`, `v /= alpha` of LSQR, reference IterativeSolvers.h:707-799)
+  DeviceMatrix &operator/=(double a) {
+    check(ctx_, ob200_div(ctx_, size(), d_, a, d_));
+    return *this;
+  }
+  friend DeviceMatrix operator/(const DeviceMatrix &v, double a) {
+    DeviceMatrix out = v.like();
+    check(v.ctx_, ob200_div(v.ctx_, v.size(), v.d_, a, out.d_));
+    return out;
+  }
 
  private:
   void alloc() {

@@ -48,10 +48,20 @@ extern "C" {
 
 typedef struct ob200_context ob200_context;
 
-/* Create a context on `device` (CUDA ordinal).  `stream` is a cudaStream_t to
- * issue work on, or NULL to let the context create its own non-blocking
- * stream.  Fails loudly (OB200_CUDA_ERROR) if there is no usable GPU: there is
- * no CPU fallback anywhere in this library. */
+/* Create a context on `device` (CUDA ordinal).  Fails loudly (OB200_CUDA_ERROR) if
+ * there is no usable GPU: there is no CPU fallback anywhere in this library.
+ *
+ * Stream contract.  Every kernel and copy of the library is issued on ONE stream:
+ *   stream == NULL            the context creates its own cudaStreamNonBlocking stream.  It has NO implicit
+ *                             ordering with the legacy default stream: a caller that produces inputs or consumes
+ *                             outputs on another stream must order the two itself (ob200_synchronize, events).
+ *   stream == cudaStreamLegacy ((void *)0x1) or cudaStreamPerThread ((void *)0x2)
+ *                             the CUDA default stream of that flavour (what a caller whose own work runs on
+ *                             "stream 0" must pass: a literal 0 cannot be told apart from NULL).
+ *   any other cudaStream_t    work is issued on the caller's stream, in order with the caller's own work.
+ * Entries that return scalars to the host (ob200_dot, ob200_stpcg, the model calls ...) synchronise that stream
+ * before returning; entries that only enqueue work (ob200_axpby, ob200_hadamard, ob200_block_apply, ob200_hvp)
+ * do not: their outputs are ordered after them on the same stream. */
 int ob200_create(int device, void *stream, ob200_context **ctx);
 int ob200_destroy(ob200_context *ctx);
 const char *ob200_last_error(const ob200_context *ctx);
@@ -76,7 +86,8 @@ int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, 
 
 /* Validation aid: out = A V for the block-diagonal bf16 A (n x 32 V), either on the
  * fp64 tensor cores (use_tcgen05 = 0, mma.sync DMMA) or through the exact bf16
- * digit-plane scheme on tcgen05 (use_tcgen05 = 1). */
+ * digit-plane scheme on tcgen05 (use_tcgen05 = 1: one TMEM lane per thread; 2: the 16-lane
+ * fragment read-back the persistent kernel uses). */
 int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A_bf16_dev, const double *V_dev,
                             double *out_dev, int use_tcgen05);
 
@@ -181,6 +192,9 @@ int ob200_dots(ob200_context *ctx, uint64_t n, int count, const double *const *a
 /* out = alpha * x + beta * y   (out may alias x or y) */
 int ob200_axpby(ob200_context *ctx, uint64_t n, double alpha, const double *x_dev, double beta,
                 const double *y_dev, double *out_dev);
+/* out = x / a, one IEEE division per element (out may alias x): the `v /= Scalar` of the reference's LSQR / TNLS
+ * loops (IterativeSolvers.h:707-799, TNLS.h) on device vectors */
+int ob200_div(ob200_context *ctx, uint64_t n, const double *x_dev, double a, double *out_dev);
 /* out = d .* x */
 int ob200_hadamard(ob200_context *ctx, uint64_t n, const double *d_dev, const double *x_dev,
                    double *out_dev);

@@ -31,7 +31,7 @@ EXPORTS = [
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
-    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path",
+    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path", "ob200_div",
 ]
 
 
@@ -116,6 +116,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_dots.argtypes = [vp, u64, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(dbl)]
     lib.ob200_axpby.argtypes = [vp, u64, dbl, vp, dbl, vp, vp]
     lib.ob200_hadamard.argtypes = [vp, u64, vp, vp, vp]
+    lib.ob200_div.argtypes = [vp, u64, vp, dbl, vp]
     lib.ob200_stiefel_model.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(dbl), vp,
                                         C.POINTER(dbl)]
     lib.ob200_stiefel_retract.argtypes = [vp, u64, u64, vp, vp, vp]

@@ -36,8 +36,10 @@ int gram_exponent_host(double bound);
 cudaError_t launch_stiefel_planes(const unsigned short *A, unsigned long long nblk, unsigned char *planes,
                                   int *plane_exp, int *unsupported, int sm_count, cudaStream_t st);
 cudaError_t launch_stiefel_ap_tc(unsigned long long n_rows, const unsigned char *planes, const int *plane_exp,
-                                 const double *P, double *Wout, int grid, cudaStream_t st);
+                                 const double *P, double *Wout, int frag_readback, int grid, cudaStream_t st);
 size_t stiefel_planes_bytes(unsigned long long nblk);
+cudaError_t launch_stiefel_checksum(const unsigned short *A, unsigned long long nblk, unsigned long long *out,
+                                    int sm_count, cudaStream_t st);
 cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
                                   const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm);
@@ -74,6 +76,7 @@ cudaError_t launch_axpby(unsigned long long N, double alpha, const double *x, do
                          double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_hadamard(unsigned long long N, const double *d, const double *x, double *out,
                             int sm_count, cudaStream_t st);
+cudaError_t launch_div(unsigned long long N, const double *x, double a, double *out, int sm_count, cudaStream_t st);
 }  // namespace ob200
 
 using namespace ob200;
@@ -113,6 +116,9 @@ struct ob200_context {
   uint64_t planes_n = 0;
   size_t planes_cap = 0;
   bool planes_ok = false;
+  unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
+  unsigned long long *dsum = nullptr;      // device / pinned-host word for the per-solve checksum of A
+  unsigned long long *hsum = nullptr;
   int opt_tcgen05 = 1;            // use the tcgen05 digit-plane contraction when A allows it
   int last_path = 0;              // 1 = tcgen05 kernel, 0 = fp64 tensor-core kernel
   // multi-GPU exchange (CUDA IPC peer memory)
@@ -171,6 +177,8 @@ int ob200_create(int device, void *stream, ob200_context **out) {
   CK(cudaMalloc(&ctx->dscal, sizeof(double) * 8));
   CK(cudaMalloc(&ctx->dmat, sizeof(double) * 2 * 32 * 32));
   CK(cudaMalloc(&ctx->dbits, 64));
+  CK(cudaMalloc(&ctx->dsum, 8));
+  CK(cudaMallocHost(&ctx->hsum, 8));
   CK(cudaMallocHost(&ctx->hres, sizeof(TcgDeviceResult)));
   CK(cudaMallocHost(&ctx->hscal, sizeof(double) * 8));
   CK(cudaMallocHost(&ctx->hacc, sizeof(u64) * ACC_WORDS));
@@ -190,7 +198,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->r); cudaFree(ctx->p0); cudaFree(ctx->p1); cudaFree(ctx->Hp); cudaFree(ctx->gs);
   cudaFree(ctx->acc); cudaFree(ctx->barrier); cudaFree(ctx->dres); cudaFree(ctx->dscal);
-  cudaFree(ctx->dmat); cudaFree(ctx->dbits);
+  cudaFree(ctx->dmat); cudaFree(ctx->dbits); cudaFree(ctx->dsum); cudaFreeHost(ctx->hsum);
   cudaFreeHost(ctx->hres); cudaFreeHost(ctx->hscal); cudaFreeHost(ctx->hacc); cudaFreeHost(ctx->hmat);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int r = 0; r < MAX_RANKS; ++r)
@@ -308,6 +316,7 @@ int ob200_malloc(ob200_context *ctx, size_t bytes, void **p) {
 }
 int ob200_free(ob200_context *ctx, void *p) {
   if (!ctx) return OB200_INVALID_ARGUMENT;
+  if (p && p == ctx->planes_key) { ctx->planes_key = nullptr; ctx->planes_ok = false; }   // cached digit planes die with their A
   CK(cudaFree(p));
   return OB200_OK;
 }
@@ -360,16 +369,30 @@ static int ensure_staging(ob200_context *ctx, size_t N) {
   return OB200_OK;
 }
 
-// Digit planes of A for the tcgen05 contraction (built once per A; see tc_common.cuh).
-// Sets ctx->planes_ok = false when some block is not 16-bit block-fixed-point: the
-// caller then stays on the fp64 tensor-core path.
-static int ensure_planes(ob200_context *ctx, const uint16_t *A, uint64_t n) {
-  if (ctx->planes_key == A && ctx->planes_n == n) return OB200_OK;
+// Digit planes of A for the tcgen05 contraction (see tc_common.cuh), cached per operator.  The cache key is
+// (device pointer, n, CONTENT CHECKSUM of A): planes_checksum_async() enqueues the checksum of the caller's A
+// on every solve (one pass over A, a few microseconds), planes_validate() -- called after the stream has been
+// synchronised -- rebuilds the planes whenever pointer, size or checksum differ.  An A updated in place, or a
+// different A that the allocator placed at the address of a freed one, can therefore never meet stale planes.
+// Sets ctx->planes_ok = false when some block is not 22-bit block-fixed-point: the caller then stays on the
+// fp64 tensor-core path.
+static int planes_checksum_async(ob200_context *ctx, const uint16_t *A, uint64_t n) {
+  const unsigned long long nblk = (n + 127) / 128;
+  CK(cudaMemsetAsync(ctx->dsum, 0, 8, ctx->stream));
+  CK(launch_stiefel_checksum(A, nblk, ctx->dsum, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(ctx->hsum, ctx->dsum, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return OB200_OK;
+}
+static int planes_validate(ob200_context *ctx, const uint16_t *A, uint64_t n) {   // stream synchronised by the caller
+  const unsigned long long sum = *ctx->hsum;
+  if (ctx->planes_key == A && ctx->planes_n == n && ctx->planes_sum == sum) return OB200_OK;
   const unsigned long long nblk = (n + 127) / 128;
   const size_t bytes = stiefel_planes_bytes(nblk);
+  ctx->planes_key = nullptr;
   if (bytes > ctx->planes_cap) {
     cudaFree(ctx->planes); cudaFree(ctx->plane_exp);
-    ctx->planes = nullptr; ctx->plane_exp = nullptr; ctx->planes_cap = 0; ctx->planes_key = nullptr;
+    ctx->planes = nullptr; ctx->plane_exp = nullptr; ctx->planes_cap = 0;
     CK(cudaMalloc(&ctx->planes, bytes));
     CK(cudaMalloc(&ctx->plane_exp, sizeof(int) * (nblk + 1)));
     ctx->planes_cap = bytes;
@@ -383,7 +406,14 @@ static int ensure_planes(ob200_context *ctx, const uint16_t *A, uint64_t n) {
   ctx->planes_ok = (bad == 0);
   ctx->planes_key = A;
   ctx->planes_n = n;
+  ctx->planes_sum = sum;
   return OB200_OK;
+}
+static int ensure_planes(ob200_context *ctx, const uint16_t *A, uint64_t n) {
+  int rc = planes_checksum_async(ctx, A, n);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return planes_validate(ctx, A, n);
 }
 
 // Cross-rank fold of set[off, off+count) (no-op on one GPU).  All ranks call it in lockstep.
@@ -509,11 +539,9 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   }
   CK(cudaSetDevice(ctx->device));
   if ((rc = ensure_vectors(ctx, N))) return rc;
+  const bool want_tc = (H->kind == OB200_OP_STIEFEL_BLOCKDIAG && ctx->opt_tcgen05);
   bool use_tc = false;
-  if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG && ctx->opt_tcgen05) {
-    if ((rc = ensure_planes(ctx, H->A_bf16_dev, H->n))) return rc;
-    use_tc = ctx->planes_ok;
-  }
+  if (want_tc && (rc = planes_checksum_async(ctx, H->A_bf16_dev, H->n))) return rc;   // validated after the sync below
   const uint64_t launches0 = ctx->launches;
   cudaStream_t st = ctx->stream;
 
@@ -549,6 +577,10 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG)
     CK(cudaMemcpyAsync(ctx->dmat, H->S_host, sizeof(double) * 32 * 32, cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
+  if (want_tc) {
+    if ((rc = planes_validate(ctx, H->A_bf16_dev, H->n))) return rc;
+    use_tc = ctx->planes_ok;
+  }
   const double rv0 = ctx->hscal[0];
   const double r0_norm = std::sqrt(rv0);                                            // l.275
   const double target = r0_norm * std::min(prm->kappa_fgr, std::pow(r0_norm, prm->theta));  // l.278-279
@@ -655,6 +687,13 @@ int ob200_axpby(ob200_context *ctx, uint64_t n, double alpha, const double *x, d
   ctx->launches += 1;
   return OB200_OK;
 }
+int ob200_div(ob200_context *ctx, uint64_t n, const double *x, double a, double *out) {
+  if (!ctx || !x || !out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_div(n, x, a, out, ctx->sm_count, ctx->stream));
+  ctx->launches += 1;
+  return OB200_OK;
+}
 int ob200_hadamard(ob200_context *ctx, uint64_t n, const double *d, const double *x, double *out) {
   if (!ctx || !d || !x || !out) return OB200_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
@@ -723,7 +762,7 @@ int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A, c
     int rc = ensure_planes(ctx, A, n);
     if (rc) return rc;
     if (!ctx->planes_ok) return fail(ctx, OB200_UNSUPPORTED, "A is not 16-bit block-fixed-point: tcgen05 path unavailable");
-    CK(launch_stiefel_ap_tc(n, ctx->planes, ctx->plane_exp, V, out, grid, ctx->stream));
+    CK(launch_stiefel_ap_tc(n, ctx->planes, ctx->plane_exp, V, out, use_tcgen05 == 2 ? 1 : 0, grid, ctx->stream));
   } else {
     CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, ctx->stream));
     CK(launch_stiefel_apply(n, A, V, nullptr, nullptr, out, ctx->acc, 1.0, grid, ctx->stream));

@@ -115,6 +115,26 @@ hadamard_kernel(unsigned long long N, const double *d, const double *x, double *
   }
 }
 
+// out = x / a with a true IEEE division per element (LSQR / TNLS normalise with `v /= Scalar`,
+// reference IterativeSolvers.h:707-799; a multiply by the reciprocal would round differently)
+__global__ void __launch_bounds__(TCG_THREADS)
+div_kernel(unsigned long long N, const double *x, double a, double *out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long units = (N + 255ull) / 256ull;
+  for (unsigned long long u = (unsigned long long)blockIdx.x * TCG_WARPS + warp; u < units;
+       u += (unsigned long long)gridDim.x * TCG_WARPS) {
+    const unsigned long long e0 = u * 256ull;
+    double2 xv[4], o[4];
+    l1_load_run(x, N, e0, lane, xv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[i].x = __ddiv_rn(xv[i].x, a);
+      o[i].y = __ddiv_rn(xv[i].y, a);
+    }
+    l1_store_run(out, N, e0, lane, o);
+  }
+}
+
 static int l1_grid(unsigned long long N, int sm_count) {
   const unsigned long long units = (N + 255ull) / 256ull;
   unsigned long long g = (units + TCG_WARPS - 1) / TCG_WARPS;
@@ -142,6 +162,10 @@ cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStr
 cudaError_t launch_axpby(unsigned long long N, double alpha, const double *x, double beta, const double *y,
                          double *out, int sm_count, cudaStream_t st) {
   axpby_kernel<<<l1_grid(N, sm_count), TCG_THREADS, 0, st>>>(N, alpha, x, beta, y, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_div(unsigned long long N, const double *x, double a, double *out, int sm_count, cudaStream_t st) {
+  div_kernel<<<l1_grid(N, sm_count), TCG_THREADS, 0, st>>>(N, x, a, out);
   return cudaGetLastError();
 }
 cudaError_t launch_hadamard(unsigned long long N, const double *d, const double *x, double *out,

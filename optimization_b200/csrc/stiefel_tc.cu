@@ -50,14 +50,15 @@ __global__ void __launch_bounds__(256) stiefel_planes_kernel(const unsigned shor
     unsigned char *Pb = planes + b * (size_t)TC_ABLOCK;
     // one thread per (row, 16-byte chunk): 128 rows x 8 chunks of 16 k
     for (int idx = threadIdx.x; idx < TC_NB * 8; idx += blockDim.x) {
-      const int r = idx >> 3, c = idx & 7;                     // k = 16 c .. 16 c + 15
+      const int r = idx >> 3, c = idx & 7;                     // image row (TMEM lane) r, k = 16 c .. 16 c + 15
+      const int rs = (int)tc_row_of_lane((uint32_t)r);         // block row held by that lane
       uint32_t w2[4], w1[4], w0[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint32_t x2 = 0, x1 = 0, x0 = 0;
 #pragma unroll
         for (int z = 0; z < 4; ++z) {
-          const unsigned v = Ab[r * TC_NB + 16 * c + 4 * q + z];
+          const unsigned v = Ab[rs * TC_NB + 16 * c + 4 * q + z];
           const int e = (v >> 7) & 0xff;
           const unsigned frac = v & 0x7f;
           int val = 0;
@@ -83,13 +84,34 @@ __global__ void __launch_bounds__(256) stiefel_planes_kernel(const unsigned shor
   }
 }
 
+// Position-dependent 64-bit checksum of the bf16 blocks of A (wrapping integer sum: order independent).  The
+// digit planes are cached per operator; every solve re-validates the cache against this checksum, so an A that
+// was updated in place -- or a different A that the allocator placed at the same address -- is never multiplied
+// with stale planes.  Reads A once (25.6 MB at n = 1e5: a few microseconds).
+__global__ void __launch_bounds__(256) stiefel_checksum_kernel(const uint4 *A16, unsigned long long nvec,
+                                                                unsigned long long *out) {
+  unsigned long long acc = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(A16 + i);
+    const unsigned long long lo = ((unsigned long long)v.y << 32) | v.x, hi = ((unsigned long long)v.w << 32) | v.z;
+    unsigned long long z = (lo ^ (i * 0x9E3779B97F4A7C15ull)) * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 29;
+    z += (hi ^ ((i + 0x632BE59BD9B4E019ull) * 0x94D049BB133111EBull)) * 0xD6E8FEB86659FD93ull;
+    acc += z ^ (z >> 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 constexpr size_t APTC_SMEM = 1024 /*align slack*/ + TC_ABLOCK + TC_QBYTES + 256;
 
 extern __shared__ __align__(16) unsigned char tc_smem_raw[];
 
 __global__ void __launch_bounds__(256, 1)
 stiefel_ap_tc_kernel(unsigned long long n_rows, const unsigned char *planes, const int *plane_exp, const double *P,
-                     double *Wout) {
+                     double *Wout, int frag_readback) {
   unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *Asm = base;
   unsigned char *Qsm = base + TC_ABLOCK;
@@ -149,9 +171,25 @@ stiefel_ap_tc_kernel(unsigned long long n_rows, const unsigned char *planes, con
     }
     mbar_wait(&bars[1], parity);
     tc_fence_after();
-    {
+    if (frag_readback) {
+      // the read-back of the persistent kernel's M warps: 16-lane groups in the mma.sync accumulator arrangement
+      const int q4 = warp & 3, chalf = warp >> 2, m = lane >> 2, j = lane & 3;
+      const double sc = scalbn(1.0, plane_exp[b] + E + 10);
+#pragma unroll 1
+      for (int g16 = 0; g16 < 2; ++g16) {
+        double out[8];
+        recombine_frag16(tmem_base + ((uint32_t)(32 * q4 + 16 * g16) << 16) + 16 * chalf, out);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          const int row = 64 * g16 + 16 * q4 + m + ((k & 2) ? 8 : 0);
+          const int col = 16 * chalf + ((k & 4) ? 8 : 0) + 2 * j;
+          const unsigned long long grow = r0 + row;
+          if (grow < n_rows) stcg2(Wout + (size_t)grow * TC_N + col, make_double2(out[k] * sc, out[k + 1] * sc));
+        }
+      }
+    } else {
       const int q4 = warp & 3, chalf = warp >> 2;                 // TMEM lane quarter, column half
-      const int row = 32 * q4 + lane;
+      const int row = (int)tc_row_of_lane((uint32_t)(32 * q4 + lane));
       double out[16];
       recombine_row16(tmem_base + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
       const double sc = scalbn(1.0, plane_exp[b] + E + 10);
@@ -177,14 +215,20 @@ cudaError_t launch_stiefel_planes(const unsigned short *A, unsigned long long nb
   return cudaGetLastError();
 }
 cudaError_t launch_stiefel_ap_tc(unsigned long long n_rows, const unsigned char *planes, const int *plane_exp,
-                                 const double *P, double *Wout, int grid, cudaStream_t st) {
+                                 const double *P, double *Wout, int frag_readback, int grid, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(stiefel_ap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APTC_SMEM);
     if (e) return e;
     attr = true;
   }
-  stiefel_ap_tc_kernel<<<grid, 256, APTC_SMEM, st>>>(n_rows, planes, plane_exp, P, Wout);
+  stiefel_ap_tc_kernel<<<grid, 256, APTC_SMEM, st>>>(n_rows, planes, plane_exp, P, Wout, frag_readback);
+  return cudaGetLastError();
+}
+cudaError_t launch_stiefel_checksum(const unsigned short *A, unsigned long long nblk, unsigned long long *out,
+                                    int sm_count, cudaStream_t st) {
+  const unsigned long long nvec = nblk * (TC_NB * TC_NB * sizeof(unsigned short) / sizeof(uint4));
+  stiefel_checksum_kernel<<<4 * sm_count, 256, 0, st>>>(reinterpret_cast<const uint4 *>(A), nvec, out);
   return cudaGetLastError();
 }
 size_t stiefel_planes_bytes(unsigned long long nblk) { return (size_t)nblk * TC_ABLOCK; }

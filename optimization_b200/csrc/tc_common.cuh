@@ -96,6 +96,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
+// 16 lanes x 16 consecutive 32-bit columns in the mma.sync accumulator arrangement: thread (m = lane >> 2,
+// j = lane & 3) receives   v[0], v[1] = row m,     columns 2j, 2j + 1        v[4], v[5] = row m,     columns 8 + 2j, 9 + 2j
+//                          v[2], v[3] = row m + 8, columns 2j, 2j + 1        v[6], v[7] = row m + 8, columns 8 + 2j, 9 + 2j
+// (rows relative to the lane field of taddr, which must be a multiple of 16 inside the warp's lane quarter).
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors ---------------------------------------------------------------
@@ -130,6 +140,14 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 // Byte offset of the 16-byte chunk c (k = 16c .. 16c+15) of row r:
 __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(uint32_t r, uint32_t c) {
   return r * 128u + ((c ^ (r & 7u)) << 4);
+}
+// Row order of the A images (the M index of the MMA = TMEM lane of the accumulators).  TMEM lane l = 32 q + 16 g + i
+// (q: the lane quarter a warp can read, warp % 4; g: 16-lane group; i < 16) holds block row
+//   tc_row_of_lane(l) = 64 g + 16 q + i ,
+// so the LOWER half block (rows 0..63) sits in the first 16 lanes of every quarter and the UPPER half in the last 16:
+// whichever half (or both) a CTA owns, all its read-back warps take part.
+__host__ __device__ __forceinline__ uint32_t tc_row_of_lane(uint32_t l) {
+  return 64u * ((l >> 4) & 1u) + 16u * (l >> 5) + (l & 15u);
 }
 constexpr uint32_t TC_NB = 128;                       // block rows / cols (M and K)
 constexpr uint32_t TC_N = 32;                         // p
@@ -210,6 +228,25 @@ __device__ __forceinline__ void slice_tile_to_smem(const double (&p)[8][2], doub
       *reinterpret_cast<uint2 *>(Qsm + s * TC_QTILE + off) = make_uint2(w[0], w[1]);
     }
   }
+}
+
+// Recombination in the fragment arrangement of tmem_ld_16x256b_x2: out[k] <-> v[k] of that load, i.e. this thread's
+// 2 rows x 4 columns of   sum_u D_u 2^(-8u)   over the 16 lanes / 16 columns addressed by taddr (accumulator 0).
+__device__ __forceinline__ void recombine_frag16(uint32_t taddr, double (&out)[8]) {
+  long long part[2][8];
+#pragma unroll
+  for (int gq = 0; gq < 2; ++gq) {
+    uint32_t v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) tmem_ld_16x256b_x2(taddr + (4 * gq + u) * TC_N, v[u]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      part[gq][c] = (long long)(int)v[3][c] + ((long long)(int)v[2][c] << 8) + ((long long)(int)v[1][c] << 16) +
+                    ((long long)(int)v[0][c] << 24);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) out[c] = fma((double)part[1][c], 0x1p-32, (double)part[0][c]) * 0x1p-24;
 }
 
 // Recombination of the eight int32 accumulators of this thread's row:

@@ -400,7 +400,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           recombine_row16(tmem_base + (v & 1) * TC_TMEM_COLS + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
           tc_fence_before();
           const double sc = scalbn(1.0, __ldg(plane_exp + bfirst + i - 1) + E_prev + 10);
-          double *wrow = Wsm + (v & 1) * (ST_NB * WS) + (32 * q4 + lane) * WS + 16 * chalf;
+          double *wrow = Wsm + (v & 1) * (ST_NB * WS) + tc_row_of_lane((uint32_t)(32 * q4 + lane)) * WS + 16 * chalf;
 #pragma unroll
           for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(wrow + c) = make_double2(out[c] * sc, out[c + 1] * sc);
           mbar_arrive(&mb[MB_Z_FULL + (v & 1)]);

@@ -52,8 +52,11 @@ class Context:
         self.device = int(device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.current_stream(self.device)
+        # torch's default stream is the legacy default stream, whose handle is 0; the C ABI reads NULL as "create a
+        # private non-blocking stream" (no ordering with torch's work), so stream 0 is passed as cudaStreamLegacy (0x1).
+        handle = self.stream.cuda_stream or 0x1
         h = C.c_void_p()
-        rc = self.lib.ob200_create(self.device, C.c_void_p(self.stream.cuda_stream), C.byref(h))
+        rc = self.lib.ob200_create(self.device, C.c_void_p(handle), C.byref(h))
         if rc != capi.OK:
             raise capi.Ob200Error(rc, "ob200_create failed (no usable GPU?)")
         self.h = h

@@ -49,6 +49,13 @@ def to_bf16_bits(x: np.ndarray) -> np.ndarray:
     return (bits >> np.uint32(16)).astype(np.uint16)
 
 
+def round_to_bf16(x: np.ndarray) -> np.ndarray:
+    """Round doubles to the nearest bf16 value (ties to even), returned as float64."""
+    bits = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    bits = (bits + np.uint64(0x7FFF) + ((bits >> np.uint64(16)) & np.uint64(1))) & np.uint64(0xFFFF0000)
+    return bits.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
 def from_bf16_bits(b: np.ndarray) -> np.ndarray:
     return (b.astype(np.uint32) << np.uint32(16)).view(np.float32).astype(np.float64)
 
@@ -77,7 +84,7 @@ class StiefelProblem:
 
 
 def stiefel_rows(n: int, nb: int, row0: int, row1: int, seed: int = 21,
-                 diag_width: float = 28.0, low: np.ndarray | None = None) -> np.ndarray:
+                 diag_width: float = 28.0, low: np.ndarray | None = None, generic_bf16: bool = False) -> np.ndarray:
     """A blocks covering rows [row0,row1) (block aligned) as float64 (nblk_local, nb, nb).
 
     Block = diag(c) + R, c in [3, 3+diag_width) on a 1/4 grid, R symmetric with
@@ -93,7 +100,12 @@ def stiefel_rows(n: int, nb: int, row0: int, row1: int, seed: int = 21,
         u = uniform01(seed, base, nb * nb).reshape(nb, nb)
         m = np.floor(u * 63.0) - 31.0            # integers in [-31, 31]
         R = np.zeros((nb, nb))
-        R[iu] = (m * 2.0 ** -11)[iu]
+        if generic_bf16:
+            # generic bf16 data: bell-shaped samples of scale 2^-7 rounded to bf16 (full 8-bit significands, exponents
+            # spread over far more than 22 bits within a block: such an A is NOT block-fixed-point)
+            R[iu] = round_to_bf16(gaussish(seed + 7, base, nb * nb).reshape(nb, nb) * 2.0 ** -7)[iu]
+        else:
+            R[iu] = (m * 2.0 ** -11)[iu]
         R = R + R.T
         assert 0.0 < diag_width <= 28.0
         dg = 3.0 + np.floor(u.diagonal() * diag_width * 4.0) / 4.0   # [3, 3+width) step 1/4
@@ -135,7 +147,7 @@ def make_stiefel(n: int, p: int = 32, nb: int = 128, seed: int = 21,
 
 
 def make_stiefel_critical(n: int, p: int = 32, nb: int = 128, seed: int = 21,
-                          diag_width: float = 28.0) -> StiefelProblem:
+                          diag_width: float = 28.0, generic_bf16: bool = False) -> StiefelProblem:
     """Stand-alone tCG workload (config C3 throughput runs): Y0 = E_L Q is an exact
     minimiser (E_L spans the eigenvalue-1 invariant subspace of A, Q a p x p
     rotation), so Hess f(Y0) = P(A V - V) is positive definite on the horizontal
@@ -145,7 +157,7 @@ def make_stiefel_critical(n: int, p: int = 32, nb: int = 128, seed: int = 21,
     cost is invariant under Y -> Y Q), and tCG leaves through the trust-region
     boundary after a handful of iterations: `make_stiefel` covers that regime."""
     L = low_rows(n, p)
-    A = stiefel_rows(n, nb, 0, n, seed, diag_width, L)
+    A = stiefel_rows(n, nb, 0, n, seed, diag_width, L, generic_bf16)
     Qm, Rq = np.linalg.qr(gaussish(seed + 5, 0, p * p).reshape(p, p))
     Qm = Qm * np.sign(np.diag(Rq))[None, :]
     Y0 = np.zeros((n, p))

@@ -230,6 +230,112 @@ def test_stiefel_full_size_properties(ctx):
     assert oh.num_iterations == o1.num_iterations and np.array_equal(oh.s, s1.cpu().numpy())
 
 
+def _host_oracle():
+    """The reference's own STPCG header (oracle/_ref, all host cores) when the prebuilt library travelled with the
+    snapshot, else the single-threaded C restatement."""
+    import os
+    from oracle import refapi
+    try:
+        R = refapi.RefOracle()
+        R.set_threads(len(os.sched_getaffinity(0)))
+        return R, None
+    except (FileNotFoundError, OSError):
+        return None, refapi.PortOracle()
+
+
+@pytest.mark.parametrize("which", ["critical", "noisy"])
+def test_stiefel_full_size_vs_reference(ctx, build_oracle, which):
+    """BASELINE size (config C3, Stiefel(100000, 32)): the fused kernel against the reference's STPCG on the host --
+    iteration count and exit bit-exact, iterate and M-norm within 1e-10 (reference IterativeSolvers.h:285-422)."""
+    prob = P.make_stiefel_critical(100000, 32) if which == "critical" else P.make_stiefel(100000, 32, y_noise=.2)
+    A, Y, H = stiefel_setup(ctx, prob)
+    cases = [dict(Delta=1e6, max_iterations=200, kappa_fgr=1e-9, theta=0.)] if which == "critical" else \
+            [dict(Delta=3.0, max_iterations=60, kappa_fgr=1e-3, theta=.5), dict(Delta=1e6, max_iterations=25, kappa_fgr=1e-9, theta=0.)]
+    R, port = _host_oracle()
+    rs = R.stiefel(prob) if R else None
+    for kw in cases:
+        if rs:
+            s_ref, mn_ref, it_ref = rs.stpcg(prob.Y0, prob.g, **kw)
+        else:
+            s_ref, mn_ref, it_ref, _ = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
+        out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+        assert ctx.last_path == "tcgen05"
+        assert out.num_iterations == it_ref
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+        if which == "critical":
+            assert out.exit_reason == "residual" and 20 < it_ref < 200
+
+
+def test_sphere_full_size_vs_reference(ctx, build_oracle):
+    """BASELINE size (config C2, n = 2^24, k = 16): same inputs on both sides (generated on the device, copied to the
+    host), CG iterations capped so the CPU side finishes in seconds; counts / exits exact, iterate within 1e-10."""
+    import types
+    n, k = 1 << 24, 16
+    d, Ut, sigma, x0, g = P.make_sphere_critical_device(n, k, device="cuda:0")
+    H = ctx.sphere_operator(d, None, sigma, x0, Ut=Ut)
+    prob = types.SimpleNamespace(n=n, k=k, d=d.cpu().numpy(), U=np.ascontiguousarray(Ut.t().contiguous().cpu().numpy()),
+                                 sigma=sigma, x0=x0.cpu().numpy(), g=g.cpu().numpy())
+    gn = float(np.linalg.norm(prob.g))
+    R, port = _host_oracle()
+    for kw in (dict(Delta=1e6 * gn, max_iterations=6, kappa_fgr=1e-10, theta=0.),
+               dict(Delta=.2 * gn, max_iterations=40, kappa_fgr=.1, theta=.5)):
+        if R:
+            s_ref, mn_ref, it_ref = R.sphere_stpcg(prob, prob.x0, prob.g, **kw)
+        else:
+            s_ref, mn_ref, it_ref, _ = port.stpcg_sphere(prob, prob.x0, prob.g, None, **kw)
+        out = ctx.stpcg(g, H, **kw)
+        assert out.num_iterations == it_ref
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+
+
+@pytest.mark.parametrize("n", [128, 300, 1000, 4096 + 32])
+def test_block_apply_tcgen05_readbacks_match_fp64(ctx, n):
+    """A V for the block-diagonal bf16 A: the exact digit-plane tcgen05 contraction with both TMEM read-back
+    arrangements (one lane per thread; 16-lane fragments, the persistent kernel's) against the fp64 tensor-core
+    product and numpy.  Exercises the row order of the A images (tc_row_of_lane)."""
+    import ctypes as C
+    import torch
+    from optimization_b200.device import _ptr
+    prob = P.make_stiefel(n, 32, y_noise=.2)
+    A, Y, H = stiefel_setup(ctx, prob)
+    V = ctx.to_device(prob.g * np.exp(P.uniform01(5, 0, n)[:, None] * 8.0 - 4.0))       # row scales over e^8
+    outs = []
+    for mode in (0, 1, 2):
+        o = torch.zeros_like(V)
+        ctx._check(ctx.lib.ob200_debug_block_apply(ctx.h, n, _ptr(A), _ptr(V), _ptr(o), mode))
+        outs.append(o.cpu().numpy())
+    Ad = P.from_bf16_bits(prob.A_bf16)
+    Vh = V.cpu().numpy()
+    want = np.zeros_like(Vh)
+    for b in range(prob.nblk):
+        r0, r1 = 128 * b, min(n, 128 * b + 128)
+        want[r0:r1] = Ad[b, :r1 - r0, :r1 - r0] @ Vh[r0:r1]
+    for o in outs:
+        assert rel(o, want) < 1e-14
+    assert np.array_equal(outs[1], outs[2])          # same integers, same recombination: bit-identical
+
+
+def test_planes_cache_follows_the_matrix(ctx, port):
+    """The cached tcgen05 digit planes are keyed by pointer, size AND content: an A rewritten in place at the same
+    address (what a caching allocator produces when one problem replaces another) must not meet stale planes."""
+    import torch
+    p1 = P.make_stiefel_critical(1024, 32, seed=21)
+    p2 = P.make_stiefel_critical(1024, 32, seed=33)
+    kw = dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.)
+    A = torch.from_numpy(p1.A_bf16.astype(np.int16)).to("cuda:0")
+    for prob in (p1, p2, p1):
+        A.copy_(torch.from_numpy(prob.A_bf16.astype(np.int16)))          # same device address, new content
+        Y = ctx.to_device(prob.Y0)
+        H = ctx.stiefel_operator(A, Y)
+        out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
+        assert ctx.last_path == "tcgen05"
+        assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+
+
 # ---- sphere Rayleigh-quotient Hessian, A = diag + low rank (configs C1 / C2) ------------------
 def sphere_setup(ctx, prob):
     d, U, x = ctx.to_device(prob.d), ctx.to_device(prob.U), ctx.to_device(prob.x0)
