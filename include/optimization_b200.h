@@ -73,9 +73,10 @@ uint64_t ob200_kernel_launches(const ob200_context *ctx);
 
 /* Options.  "tcgen05" (default 1): run the block contraction A*p of
  * OB200_OP_STIEFEL_BLOCKDIAG on the 5th-generation tensor cores through the exact bf16
- * digit-plane scheme whenever every block of A is 16-bit block-fixed-point; 0 forces the
- * fp64 tensor-core (mma.sync) kernel.  ob200_last_path: 1 if the last ob200_stpcg ran the
- * tcgen05 kernel, 0 otherwise. */
+ * digit-plane scheme whenever every block of A is 22-bit block-fixed-point (tcg_stiefel_v5_kernel);
+ * 2 selects the previous generation of that kernel (tcg_stiefel_tc_kernel, kept for A/B measurements);
+ * 0 forces the fp64 tensor-core (mma.sync) kernel.  ob200_last_path: which of them the last ob200_stpcg
+ * ran (1, 2 or 0). */
 int ob200_set_option(ob200_context *ctx, const char *name, int value);
 int ob200_last_path(const ob200_context *ctx);
 

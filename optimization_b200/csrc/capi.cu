@@ -43,6 +43,9 @@ cudaError_t launch_stiefel_checksum(const unsigned short *A, unsigned long long 
 cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
                                   const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm);
+cudaError_t launch_tcg_stiefel_v5(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
+                                  const double *Y, const double *S_dev, double op_norm_bound,
+                                  const unsigned char *planes, const int *plane_exp, int sm_count, cudaStream_t stm);
 cudaError_t launch_tcg_sphere(const TcgCommon &a, const double *d, const double *Ut, unsigned long long ldu, const double *x,
                               const double *w, const double *sigma_host, int k, double lambda, int grid, cudaStream_t st);
 cudaError_t launch_sphere_tdot(unsigned long long N, const double *Ut, unsigned long long ldu, const double *sigma_host, int k,
@@ -119,7 +122,7 @@ struct ob200_context {
   unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
   unsigned long long *dsum = nullptr;      // device / pinned-host word for the per-solve checksum of A
   unsigned long long *hsum = nullptr;
-  int opt_tcgen05 = 1;            // use the tcgen05 digit-plane contraction when A allows it
+  int opt_tcgen05 = 2;            // 1: tcgen05 kernel v5 (warp-specialised, work in progress), 2: tcgen05 kernel v4, 0: fp64 MMA kernel
   int last_path = 0;              // 1 = tcgen05 kernel, 0 = fp64 tensor-core kernel
   // multi-GPU exchange (CUDA IPC peer memory)
   CommDev cm;                     // rank, world, epoch, peer pointers
@@ -244,6 +247,13 @@ int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, 
       }
     }
     if (getenv("OB200_TIMELINE")) {
+      if (getenv("OB200_TIMELINE")[0] == '5') {   // v5 kernel: all 48 stamps relative to the end of the previous iteration's phase A loop start
+        unsigned long long t0 = ~0ull;
+        for (int k = 0; k < 48; ++k) if (h[4096 + k] && h[4096 + k] < t0) t0 = h[4096 + k];
+        fprintf(stderr, "v5 timeline (ns rel. to the earliest stamp):");
+        for (int k = 0; k < 48; ++k) if (h[4096 + k]) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - t0));
+        fprintf(stderr, "\n");
+      }
       fprintf(stderr, "timeline (ns rel. to L start):");
       for (int k = 0; k < 18; ++k) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - h[4096]));
       fprintf(stderr, "\nphase B timeline (ns rel. to barrier-A release):");
@@ -598,12 +608,15 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     const unsigned long long nblk = (H->n + 127) / 128;
     int grid = ctx->sm_count;
     if ((unsigned long long)grid > nblk) grid = (int)nblk;
-    if (use_tc)
+    if (use_tc && ctx->opt_tcgen05 == 2)      // previous generation of the tcgen05 kernel, kept for A/B measurements
       CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
                                ctx->plane_exp, grid, st));
+    else if (use_tc)
+      CK(launch_tcg_stiefel_v5(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
+                               ctx->plane_exp, ctx->sm_count, st));
     else
       CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
-    ctx->last_path = use_tc ? 1 : 0;
+    ctx->last_path = use_tc ? (ctx->opt_tcgen05 == 2 ? 2 : 1) : 0;
   }
   CK(cudaEventRecord(ctx->ev1, st));
   ctx->launches += 1;

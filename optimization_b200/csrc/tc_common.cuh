@@ -54,6 +54,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// Same with a watchdog: a hand-off that does not complete within ~2 s is a protocol bug; trap (the launch fails with an
+// error) instead of hanging the device.  The fast path costs nothing extra: the timer is read only while spinning.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) __trap();
+    }
+  }
+}
 
 // ---- bulk async copy global -> shared (TMA 1-D; SASS UBLKCP) ---------------------
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

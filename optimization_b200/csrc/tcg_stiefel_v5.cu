@@ -1,0 +1,761 @@
+// Persistent fused truncated-CG for the Stiefel trace-minimisation Hessian, v5: warp-specialised
+// roles with their own register budgets (setmaxnreg), every bulk operand of phase A staged by the
+// TMA unit, the TMEM read-back done by the warps that consume it.  Same mathematics, reductions and
+// scalar logic as tcg_stiefel_tc_kernel (v4, tcg_stiefel_tc.cu; reference line map in tcg.cuh):
+// each CG iteration of IterativeSolvers.h:285-422 is two fused phases separated by an exact grid-wide
+// (machine-wide) reduction.
+//
+// 16 warps = 4 warp groups:
+//   S (warps 0-3, 40 registers)  : warp 0 lane 0 = TMA producer: r / p_old tiles of the next block into a 64 KB stage,
+//                                  the block's three int8 digit planes of A (48 KB), L2 prefetch of what follows;
+//                                  warp 1 lane 0 = MMA issuer: 13 tcgen05.mma kind::i8 per block into one of two
+//                                  256-column TMEM accumulator sets, tcgen05.commit -> mbarrier.
+//   L (warps 4-7, 152 registers) : r, p_old from the stage -> p = -r + beta p (l.420; written back for the rows this CTA
+//                                  owns), <p,p>, <p,r>, block maximum, seven balanced int8 digit slices of p straight into
+//                                  the UMMA K-major SWIZZLE_128B operand image.
+//   M (warps 8-15, 160 registers): TMEM -> registers in the mma.sync accumulator arrangement (tcgen05.ld 16x256b: no
+//                                  shared-memory round trip), integer recombination = Z = A p; W = Z - p S on the fp64
+//                                  tensor cores, W written back, <p,W>, <W,W>, projection Gram Y^T W (exact fixed point).
+// Hand-offs through mbarriers only.  Ownership is by 64-row HALF blocks (balanced to 1/11 instead of 1/6 of a CTA's
+// work): a block shared by two CTAs is sliced and multiplied by both (the MMA needs all 128 rows of p as K), everything
+// else -- p / W stores, the fp64 MMAs, the Gram, all partial sums -- is done for the owned half only.  The A images are
+// row-permuted (tc_row_of_lane) so that either half occupies 16 lanes of every TMEM lane quarter: all eight M warps
+// work on a half block.
+// Phase B (l.374-408): the M warps, two 10 KB strip slots each (16 TMA-fed slots per SM as in v4).
+#include "tcg.cuh"
+#include "stiefel_dev.cuh"
+#include "tc_common.cuh"
+
+namespace ob200 {
+using namespace tc;
+
+constexpr int V5_THREADS = 512;
+// shared-memory map (bytes from the 1024-aligned base); phase B aliases the phase-A operand space
+constexpr uint32_t V5_A = 0;                                   // 48 KB int8 digit planes of A
+constexpr uint32_t V5_Q = V5_A + TC_ABLOCK;                    // 28 KB int8 digit image of p
+constexpr uint32_t V5_TILE = ST_NB * ST_P * 8;                 // 32 KB dense fp64 tile
+constexpr uint32_t V5_R = V5_Q + TC_QBYTES;                    // r tile (TMA)
+constexpr uint32_t V5_PO = V5_R + V5_TILE;                     // p_old tile (TMA)
+constexpr uint32_t V5_WB = ST_NB * WS * 8;                     // 36 KB padded tile
+constexpr uint32_t V5_W = V5_PO + V5_TILE;                     // W tile (stride WS)
+constexpr uint32_t V5_Y = V5_W + V5_WB;                        // Y tile (stride WS)
+constexpr uint32_t V5_S = V5_Y + V5_WB;                        // -S (stride WS)
+constexpr uint32_t V5_ACC = V5_S + ST_P * WS * 8;              // CTA Kulisch accumulators (5 scalars)
+constexpr uint32_t V5_NACC = 5;
+constexpr uint32_t V5_BAR = V5_ACC + V5_NACC * KUL_STRIDE * 8; // mbarriers
+constexpr uint32_t V5_NBAR = 32;
+constexpr uint32_t V5_MISC = V5_BAR + V5_NBAR * 8;
+constexpr uint32_t V5_MISC_BYTES = 768;
+constexpr uint32_t V5_TOTAL = V5_MISC + V5_MISC_BYTES + 1024;  // + alignment slack
+// phase B
+constexpr uint32_t V5_STRIP_TILE = 8 * ST_P * 8;               // 2 KB
+constexpr uint32_t V5_SLOT = 5 * V5_STRIP_TILE;                // 10 KB: W, s, p, r, Y tiles of one 8-row strip
+constexpr uint32_t V5_NSLOT = 16;
+constexpr uint32_t V5_GRAW = V5_NSLOT * V5_SLOT;               // 8 KB scratch (inside the W tile region)
+constexpr uint32_t V5_G = V5_Y;                                // -sym(G), stride GS (inside the Y tile region)
+static_assert(V5_GRAW >= V5_W && V5_GRAW + 8192 <= V5_Y, "G scratch must sit in the W tile region");
+static_assert(ST_P * GS * 8 <= V5_WB, "G must fit the Y tile region");
+static_assert(V5_TOTAL <= 232448 - 64, "shared memory budget (227 KB per CTA)");
+
+enum { B5_RP_FULL = 0, B5_RP_EMPTY = 1, B5_A_FULL = 2, B5_Q_FULL = 3, B5_MMA_DONE = 4 /*,5*/, B5_TMEM_EMPTY = 6 /*,7*/,
+       B5_SLOT = 8 /* .. 23 */ };
+
+struct V5Misc {
+  CgShared sh;
+  double s_part[16];
+  double s_invq, s_q;
+  double s_lmax[8];
+  int s_fe[5];
+  int s_E[4];
+  int s_next_strip;
+  uint32_t s_tmem;
+  unsigned long long s_stamp[4];
+};
+static_assert(sizeof(V5Misc) <= V5_MISC_BYTES, "misc block");
+
+__device__ __forceinline__ void bulk_prefetch_l2_v5(const void *g, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// Digit slicing for the L role of v5 (128 threads): thread (cp, g) holds P[16 g + i][2 cp + z], i < 16, i.e. one whole
+// 16-byte k-chunk (k = 16 g .. 16 g + 15) per (slice, n): seven 16-byte stores per column.
+__device__ __forceinline__ void slice_tile16_to_smem(const double (&p)[16][2], double scale, unsigned char *Qsm, int cp,
+                                                     int g) {
+#pragma unroll
+  for (int z = 0; z < 2; ++z) {
+    const uint32_t n = 2 * cp + z;
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const unsigned long long u =
+          ((unsigned long long)__double2ll_rn(p[i][z] * scale) + TC_DIGIT_BIAS) ^ TC_DIGIT_BIAS;
+      lo[i] = (uint32_t)u;
+      hi[i] = (uint32_t)(u >> 32);
+    }
+    const uint32_t off = sw128_chunk_off(n, (uint32_t)g);
+#pragma unroll
+    for (int s = 0; s < TC_SLICES; ++s) {
+      const int d = 6 - s;                                    // digit index held by slice s
+      const uint32_t sel = (d & 3) | (((d & 3) + 4) << 4);    // byte d of a -> pos 0, byte d of b -> pos 1
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t x0 = d < 4 ? lo[4 * q] : hi[4 * q], x1 = d < 4 ? lo[4 * q + 1] : hi[4 * q + 1];
+        const uint32_t x2 = d < 4 ? lo[4 * q + 2] : hi[4 * q + 2], x3 = d < 4 ? lo[4 * q + 3] : hi[4 * q + 3];
+        const uint32_t t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
+        w[q] = __byte_perm(t01, t23, 0x5410);
+      }
+      *reinterpret_cast<uint4 *>(Qsm + s * TC_QTILE + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void strip_fetch5(unsigned char *slot, uint64_t *bar, int sidx, unsigned n_rows,
+                                             const double *W, const double *S, const double *Pn, const double *R,
+                                             const double *Y) {
+  const unsigned row0 = (unsigned)sidx * 8u;
+  const unsigned rows = n_rows - row0 < 8u ? n_rows - row0 : 8u;
+  const uint32_t bytes = rows * ST_P * (uint32_t)sizeof(double);
+  const size_t off = (size_t)row0 * ST_P;
+  mbar_expect_tx(bar, 5 * bytes);
+  bulk_g2s(slot, W + off, bytes, bar);
+  bulk_g2s(slot + V5_STRIP_TILE, S + off, bytes, bar);
+  bulk_g2s(slot + 2 * V5_STRIP_TILE, Pn + off, bytes, bar);
+  bulk_g2s(slot + 3 * V5_STRIP_TILE, R + off, bytes, bar);
+  bulk_g2s(slot + 4 * V5_STRIP_TILE, Y + off, bytes, bar);
+}
+
+extern __shared__ __align__(1024) unsigned char v5_smem_raw[];
+
+// debug timeline (CTA 0, third block of an iteration, one lane per role): slot <- globaltimer
+#ifdef OB200_TIMELINE_BUILD
+#define TL5(slot) do { if (a.dbg && blockIdx.x == 0 && i == 2) a.dbg[4096 + (slot)] = globaltimer_ns(); } while (0)
+#define TL5B(slot) do { if (a.dbg && blockIdx.x == 0) a.dbg[4096 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define TL5(slot) do { } while (0)
+#define TL5B(slot) do { } while (0)
+#endif
+
+// ROLE: 0 = S (service: TMA producer + MMA issuer), 1 = L, 2 = M.  The whole CG loop is instantiated per role so
+// that each warp group's code is compiled against its own register budget.
+template <int ROLE>
+__device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st, const unsigned char *planes,
+                                       const int *plane_exp, unsigned char *base) {
+  unsigned char *Asm = base + V5_A;
+  unsigned char *Qsm = base + V5_Q;
+  const unsigned char *Rsm = base + V5_R;
+  const unsigned char *POsm = base + V5_PO;
+  double *Wsm = reinterpret_cast<double *>(base + V5_W);
+  double *Ysm = reinterpret_cast<double *>(base + V5_Y);
+  const double *Ssm = reinterpret_cast<const double *>(base + V5_S);
+  double *Gsm = reinterpret_cast<double *>(base + V5_G);
+  u64 *sacc = reinterpret_cast<u64 *>(base + V5_ACC);
+  uint64_t *mb = reinterpret_cast<uint64_t *>(base + V5_BAR);
+  V5Misc &ms = *reinterpret_cast<V5Misc *>(base + V5_MISC);
+  CgShared &sh = ms.sh;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = lane >> 2, j = lane & 3;
+  const uint32_t tmem_base = ms.s_tmem;
+
+  // ownership in phase A: 64-row half blocks [h0, h1)
+  const unsigned n_rows32 = (unsigned)st.n_rows;
+  const unsigned nhalf = (n_rows32 + 63u) >> 6;
+  const unsigned h0 = (unsigned)((unsigned long long)nhalf * blockIdx.x / gridDim.x);
+  const unsigned h1 = (unsigned)((unsigned long long)nhalf * (blockIdx.x + 1ull) / gridDim.x);
+  const unsigned bfirst = h0 >> 1;
+  const int nb_local = (h1 > h0) ? (int)(((h1 - 1u) >> 1) - bfirst + 1u) : 0;
+  const unsigned row_lo = h0 * 64u;
+  const unsigned row_hi = (h1 * 64u < n_rows32) ? h1 * 64u : n_rows32;
+  // phase B: 8-row strips split evenly over the CTAs, handed to the M warps dynamically, top-down
+  const unsigned nstrips = (n_rows32 + 7u) >> 3;
+  const int s_lo = (int)((unsigned long long)nstrips * blockIdx.x / gridDim.x);
+  const int s_hi = (int)((unsigned long long)nstrips * (blockIdx.x + 1ull) / gridDim.x);
+  unsigned bpar0 = 0, bpar1 = 0;   // M: parities of this warp's two strip-slot mbarriers
+  unsigned gen = 0, phase = 0;
+  unsigned use = 0;                // blocks processed so far by this CTA (mbarrier phase bookkeeping)
+  int exit_reason = -1;
+  unsigned long long dbg_prev = 0;
+
+  for (;;) {
+    const unsigned long long k = sh.k;
+    if (k >= a.max_iterations) { exit_reason = 1; break; }
+    if (sqrt(sh.rv) <= a.target) { exit_reason = 0; break; }
+    const double beta = sh.beta;
+    const double *p_old = (k & 1ull) ? a.p1 : a.p0;
+    double *p_new = (k & 1ull) ? a.p0 : a.p1;
+    const double inv_q = ms.s_invq, q = ms.s_q;
+
+    // ------------------------------ phase A ------------------------------
+    u64 *set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
+    {   // recycle the set used two phases from now (every CTA clears its slice; a grid barrier intervenes)
+      u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
+      const int per = (ACC_WORDS + gridDim.x - 1) / gridDim.x;
+      const int z0 = per * blockIdx.x;
+      for (int i = tid; i < per && z0 + i < ACC_WORDS; i += blockDim.x) nxt[z0 + i] = 0;
+    }
+    if constexpr (ROLE == 0) {
+      // ===== S: TMA producer (warp 0) and MMA issuer (warp 1), one elected lane each =====
+      if (warp == 0 && lane == 0) {
+        fence_proxy_async_global();   // r / p written with generic stores by other CTAs (ordered by the grid barrier)
+        for (int i = 0; i < nb_local; ++i) {
+          const unsigned u = use + i, b = bfirst + i, r0 = b * ST_NB;
+          const unsigned rows = n_rows32 - r0 < ST_NB ? n_rows32 - r0 : ST_NB;
+          const uint32_t bytes = rows * ST_P * (uint32_t)sizeof(double);
+          const size_t off = (size_t)r0 * ST_P;
+          TL5(0);
+          if (u > 0) mbar_wait_guarded(&mb[B5_RP_EMPTY], (u - 1) & 1);          // L has taken the previous block out of the stage
+          TL5(1);
+          mbar_expect_tx(&mb[B5_RP_FULL], k ? 2 * bytes : bytes);
+          bulk_g2s(base + V5_R, a.r + off, bytes, &mb[B5_RP_FULL]);
+          if (k) bulk_g2s(base + V5_PO, p_old + off, bytes, &mb[B5_RP_FULL]);
+          if (i + 1 < nb_local) {   // what the next block needs that is not fetched early: A planes, Y; then r / p_old one further
+            const unsigned rn = r0 + ST_NB;
+            const unsigned rows1 = n_rows32 - rn < ST_NB ? n_rows32 - rn : ST_NB;
+            const uint32_t bytes1 = rows1 * ST_P * (uint32_t)sizeof(double);
+            bulk_prefetch_l2_v5(planes + (size_t)(b + 1) * TC_ABLOCK, TC_ABLOCK);
+            bulk_prefetch_l2_v5(st.Y + (size_t)rn * ST_P, bytes1);
+            if (i + 2 < nb_local) {
+              const unsigned r2 = rn + ST_NB;
+              const unsigned rows2 = n_rows32 - r2 < ST_NB ? n_rows32 - r2 : ST_NB;
+              const uint32_t bytes2 = rows2 * ST_P * (uint32_t)sizeof(double);
+              bulk_prefetch_l2_v5(a.r + (size_t)r2 * ST_P, bytes2);
+              if (k) bulk_prefetch_l2_v5(p_old + (size_t)r2 * ST_P, bytes2);
+            }
+          }
+          TL5(2);
+          if (u > 0) mbar_wait_guarded(&mb[B5_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // A image free
+          mbar_expect_tx(&mb[B5_A_FULL], TC_ABLOCK);
+          bulk_g2s(Asm, planes + (size_t)b * TC_ABLOCK, TC_ABLOCK, &mb[B5_A_FULL]);
+          TL5(3);
+        }
+      } else if (warp == 1 && lane == 0) {
+        for (int i = 0; i < nb_local; ++i) {
+          const unsigned u = use + i;
+          TL5(4);
+          mbar_wait_guarded(&mb[B5_Q_FULL], u & 1);
+          TL5(5);
+          mbar_wait_guarded(&mb[B5_A_FULL], u & 1);
+          TL5(6);
+          if (u >= 2) mbar_wait_guarded(&mb[B5_TMEM_EMPTY + (u & 1)], ((u >> 1) - 1) & 1);   // M has drained this accumulator set
+          TL5(7);
+          tc_fence_after();
+          issue_block_mmas(smem_u32(Asm), smem_u32(Qsm), tmem_base + (u & 1) * TC_TMEM_COLS);
+          umma_commit(&mb[B5_MMA_DONE + (u & 1)]);
+          TL5(8);
+        }
+      }
+      __syncwarp();
+    } else if constexpr (ROLE == 1) {
+      // ===== L: p = -r + beta p_old, digit slices =====
+      const int t = tid - 128, cp = t & 15, g = t >> 4;      // columns 2cp, 2cp+1 ; rows 16g .. 16g+15 of the block
+      FixAcc fa0 = {0, 0}, fa1 = {0, 0};                     // <p,p>, <p,r>
+      const int fe0 = ms.s_fe[SC_PP], fe1 = ms.s_fe[SC_PR];
+      const double fq0 = scalbn(1.0, 90 - fe0), fq1 = scalbn(1.0, 90 - fe1);
+      unsigned ovf = 0;
+      for (int i = 0; i < nb_local; ++i) {
+        const unsigned u = use + i, b = bfirst + i, r0 = b * ST_NB;
+        const unsigned hh = 2u * b + (unsigned)(g >> 2);     // this thread's half block
+        const bool mine = hh >= h0 && hh < h1;
+        if (t == 0) TL5(10);
+        mbar_wait_guarded(&mb[B5_RP_FULL], u & 1);
+        if (t == 0) TL5(11);
+        double p[16][2];
+        double pp = 0.0, pr = 0.0, mx = 0.0;
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) {
+          const unsigned row = 16u * g + ii, grow = r0 + row;
+          double2 rv = make_double2(0.0, 0.0), po = make_double2(0.0, 0.0);
+          if (grow < n_rows32) {
+            rv = *reinterpret_cast<const double2 *>(Rsm + row * 256u + 16u * cp);
+            if (k) po = *reinterpret_cast<const double2 *>(POsm + row * 256u + 16u * cp);
+          }
+          double2 pv;
+          if (k) {
+            pv.x = fma(beta, po.x, -rv.x);                   // l.420
+            pv.y = fma(beta, po.y, -rv.y);
+          } else {
+            pv.x = -rv.x;                                    // l.256
+            pv.y = -rv.y;
+          }
+          if (mine && grow < n_rows32) {
+            stcg2(p_new + (size_t)grow * ST_P + 2 * cp, pv);
+            pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
+            pr = fma(pv.x, rv.x, pr); pr = fma(pv.y, rv.y, pr);
+          }
+          p[ii][0] = pv.x;
+          p[ii][1] = pv.y;
+          mx = fmax(mx, fmax(fabs(pv.x), fabs(pv.y)));
+        }
+        mbar_arrive(&mb[B5_RP_EMPTY]);                        // the stage may be refilled with the next block
+        if (t == 0) TL5(12);
+        // exact-reduction unit: this thread's 16 x 2 elements (inside one half block)
+        fixacc_add(fa0, pp, fq0, ovf);
+        fixacc_add(fa1, pr, fq1, ovf);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) ms.s_lmax[(u & 1) * 4 + (warp - 4)] = mx;
+        nbar_sync(NB_LSYNC, 128);
+        mx = fmax(fmax(ms.s_lmax[(u & 1) * 4], ms.s_lmax[(u & 1) * 4 + 1]),
+                  fmax(ms.s_lmax[(u & 1) * 4 + 2], ms.s_lmax[(u & 1) * 4 + 3]));
+        // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
+        const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
+        if (t == 0) TL5(13);
+        if (u > 0) mbar_wait_guarded(&mb[B5_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // digit image free
+        if (t == 0) TL5(14);
+        slice_tile16_to_smem(p, scalbn(1.0, 54 - E), Qsm, cp, g);
+        fence_proxy_async_smem();
+        if (t == 0) ms.s_E[u & 3] = E;
+        mbar_arrive(&mb[B5_Q_FULL]);
+        if (t == 0) TL5(15);
+      }
+      fixacc_flush(fa0, sacc + SC_PP * KUL_STRIDE, fe0);
+      fixacc_flush(fa1, sacc + SC_PR * KUL_STRIDE, fe1);
+      if (ovf) atomicOr((unsigned long long *)(set + ACC_FLAG_OFF), 1ull);
+    } else {
+      // ===== M: TMEM read-back, W = Z - p S, stores, partial sums, projection Gram =====
+      const int w = warp - 8, qd = w & 3, hc = w >> 2;       // TMEM lane quarter (= warp % 4), column half
+      FixAcc fa0 = {0, 0}, fa1 = {0, 0};                     // <p,W>, <W,W>
+      const int fe0 = ms.s_fe[SC_PHP], fe1 = ms.s_fe[SC_HPHP];
+      const double fq0 = scalbn(1.0, 90 - fe0), fq1 = scalbn(1.0, 90 - fe1);
+      unsigned ovf = 0;
+      i64 gfix[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      for (int i = 0; i < nb_local; ++i) {
+        const unsigned u = use + i, b = bfirst + i, r0 = b * ST_NB;
+        const bool own0 = 2u * b >= h0 && 2u * b < h1, own1 = 2u * b + 1u >= h0 && 2u * b + 1u < h1;
+        if (tid == 256) TL5(20);
+        {   // Y of the owned rows -> shared memory (free since the barrier that closed the previous block)
+          const int mt_ = tid - 256, cpy = mt_ & 15, gy = mt_ >> 4;     // rows 8gy .. 8gy+7
+          if ((gy >> 3) ? own1 : own0) {
+            double2 yv[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+              const unsigned grow = r0 + 8 * gy + ii;
+              yv[ii] = (grow < n_rows32) ? ldcg2(st.Y + (size_t)grow * ST_P + 2 * cpy) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) *reinterpret_cast<double2 *>(Ysm + (8 * gy + ii) * WS + 2 * cpy) = yv[ii];
+          }
+        }
+        // MMAs of block u complete: the accumulators are ready, and -- through the release / acquire chain L -> MMA
+        // issuer -> tcgen05.commit -- every L thread's stores of p (and E) for this block are visible.  (Waiting on
+        // Q_FULL here instead would alias: L may run two blocks ahead of M, and an mbarrier only tells odd from even.)
+        if (tid == 256) TL5(21);
+        mbar_wait_guarded(&mb[B5_MMA_DONE + (u & 1)], (u >> 1) & 1);
+        if (tid == 256) TL5(22);
+        tc_fence_after();
+        const int E = ms.s_E[u & 3];
+        const double sc = scalbn(1.0, __ldg(plane_exp + b) + E + 10);
+        const uint32_t tacc = tmem_base + (u & 1) * TC_TMEM_COLS + ((uint32_t)(32 * qd) << 16) + 16 * hc;
+        // The two 16-lane groups (half blocks) of this warp's TMEM lane quarter, one after the other (one copy of the
+        // code, small register footprint: with 226 KB of shared memory the L1 is 2 KB, a spill is an L2 round trip).
+        // Per group: the rows of p as fp64 MMA A fragments (strip s = rows 8 s + m of the group; L2 loads, in flight
+        // during the TMEM read-back), Z = A p from TMEM in the accumulator arrangement, W = Z - p S, stores, partial sums.
+#pragma unroll 1
+        for (int g16 = 0; g16 < 2; ++g16) {
+          if (!(g16 ? own1 : own0)) continue;
+          double pa[2][8];
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const unsigned grow = r0 + 64u * g16 + 16u * qd + 8u * s + m;
+            const bool ld = grow < n_rows32;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) pa[s][qq] = ld ? __ldcg(p_new + (size_t)grow * ST_P + 4 * qq + j) : 0.0;
+          }
+          double acc[2][2][2];                                // [s][tile tt][c]
+          {
+            double out[8];
+            recombine_frag16(tacc + ((uint32_t)(16 * g16) << 16), out);
+            acc[0][0][0] = out[0] * sc; acc[0][0][1] = out[1] * sc;
+            acc[1][0][0] = out[2] * sc; acc[1][0][1] = out[3] * sc;
+            acc[0][1][0] = out[4] * sc; acc[0][1][1] = out[5] * sc;
+            acc[1][1][0] = out[6] * sc; acc[1][1][1] = out[7] * sc;
+          }
+          if (tid == 256) TL5(23 + 3 * g16);
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) {                    // W = A p - p S   (Ssm holds -S)
+            const double *Mrow = Ssm + (4 * qq + j) * WS + m + 16 * hc;
+            const double sv0 = Mrow[0], sv1 = Mrow[8];
+            dmma884(acc[0][0][0], acc[0][0][1], pa[0][qq], sv0);
+            dmma884(acc[1][0][0], acc[1][0][1], pa[1][qq], sv0);
+            dmma884(acc[0][1][0], acc[0][1][1], pa[0][qq], sv1);
+            dmma884(acc[1][1][0], acc[1][1][1], pa[1][qq], sv1);
+          }
+          if (tid == 256) TL5(24 + 3 * g16);
+          const int src0 = 4 * m + 2 * (j & 1);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const unsigned row = 64u * g16 + 16u * qd + 8u * s + m, grow = r0 + row;
+            const bool valid = grow < n_rows32;
+            double pw = 0.0, ww = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+              const int col = 16 * hc + 8 * tt + 2 * j;
+              // p[row][col + c] lives in lane (m, 2 (j & 1) + c) as A-fragment element qq = 2 (2 hc + tt) + (j >> 1)
+              const double e0 = hc ? pa[s][4 + 2 * tt] : pa[s][2 * tt];
+              const double e1 = hc ? pa[s][5 + 2 * tt] : pa[s][2 * tt + 1];
+              const double a0 = __shfl_sync(0xffffffffu, e0, src0), b0 = __shfl_sync(0xffffffffu, e1, src0);
+              const double a1 = __shfl_sync(0xffffffffu, e0, src0 + 1), b1 = __shfl_sync(0xffffffffu, e1, src0 + 1);
+              const double px = (j >> 1) ? b0 : a0, py = (j >> 1) ? b1 : a1;
+              const double wx = acc[s][tt][0], wy = acc[s][tt][1];
+              pw = fma(px, wx, pw); pw = fma(py, wy, pw);
+              ww = fma(wx, wx, ww); ww = fma(wy, wy, ww);
+              const double2 wv = make_double2(wx, wy);
+              *reinterpret_cast<double2 *>(Wsm + row * WS + col) = wv;
+              if (valid) stcg2(a.Hp + (size_t)grow * ST_P + col, wv);
+            }
+            fixacc_add(fa0, pw, fq0, ovf);   // exact-reduction unit: this lane's 4 elements of the strip row
+            fixacc_add(fa1, ww, fq1, ovf);
+          }
+          if (tid == 256) TL5(25 + 3 * g16);
+        }
+        tc_fence_before();
+        mbar_arrive(&mb[B5_TMEM_EMPTY + (u & 1)]);            // the accumulator set may be overwritten
+        nbar_sync(NB_MSYNC2, 256);                            // W complete in Wsm, Y complete in Ysm
+        if (tid == 256) TL5(29);
+        // projection Gram, one exact unit per owned 64-row half
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          if (!(hh ? own1 : own0)) continue;
+          double g00, g01, g10, g11;
+          gram_pair_half_split(Ysm + hh * 64 * WS, Wsm + hh * 64 * WS, w >> 1, 2 * (w & 1), lane, g00, g01, g10, g11);
+          gram_accumulate(g00, g01, inv_q, gfix[0], &ovf);
+          gram_accumulate(g10, g11, inv_q, gfix[1], &ovf);
+        }
+        if (tid == 256) TL5(30);
+        nbar_sync(NB_MSYNC3, 256);                            // Wsm / Ysm free for the next block
+        if (tid == 256) TL5(31);
+      }
+      gram_flush(set, 2 * w, lane, gfix[0], ovf);
+      gram_flush(set, 2 * w + 1, lane, gfix[1], 0);
+      fixacc_flush(fa0, sacc + SC_PHP * KUL_STRIDE, fe0);
+      fixacc_flush(fa1, sacc + SC_HPHP * KUL_STRIDE, fe1);
+    }
+    use += (unsigned)nb_local;
+    if (tid == 0) TL5B(40);     // S done
+    if (tid == 128) TL5B(41);   // L done
+    if (tid == 256) TL5B(42);   // M done
+    bar_all();
+    flush_scalars(sacc, set, 4);
+    RedView rvw;
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
+                             a.dbg ? ms.s_stamp : nullptr)) { exit_reason = -2; break; }
+    if (tid == 256) TL5B(43);     // barrier A released
+    // first two strips of phase B for each M warp: start streaming them in before the scalar stage
+    int cur0 = -1, cur1 = -1;
+    unsigned char *slot0 = base + (ROLE == 2 ? (2 * (warp - 8)) * V5_SLOT : 0), *slot1 = slot0 + V5_SLOT;
+    uint64_t *sb0 = &mb[B5_SLOT + (ROLE == 2 ? 2 * (warp - 8) : 0)], *sb1 = sb0 + 1;
+    if constexpr (ROLE == 2) {
+      if (lane == 0) { cur0 = atomicSub(&ms.s_next_strip, 1); cur1 = atomicSub(&ms.s_next_strip, 1); }
+      cur0 = __shfl_sync(0xffffffffu, cur0, 0);
+      cur1 = __shfl_sync(0xffffffffu, cur1, 0);
+      if (lane == 0) {
+        fence_proxy_async_smem();
+        fence_proxy_async_global();
+        if (cur0 >= s_lo) strip_fetch5(slot0, sb0, cur0, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
+        if (cur1 >= s_lo) strip_fetch5(slot1, sb1, cur1, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
+      }
+    }
+    {
+      const u64 flag = rvw.load(ACC_FLAG_OFF);
+      double c = 0.0;
+      {
+        // G (fixed point) -> shared memory (S and M warps) while the four L warps finalize the four exact scalars
+        double *Graw = reinterpret_cast<double *>(base + V5_GRAW);
+        if constexpr (ROLE != 1) {
+          for (int e = (ROLE == 0 ? tid : tid - 128); e < ST_P * ST_P; e += 384) {
+            u64 hi, lo;
+            if (rvw.world == 1) {
+              const ulonglong2 wv = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + ACC_GRAM_OFF + 2 * e));
+              hi = wv.x; lo = wv.y;
+            } else {
+              hi = rvw.load(ACC_GRAM_OFF + 2 * e); lo = rvw.load(ACC_GRAM_OFF + 2 * e + 1);
+            }
+            Graw[e] = fix2_to_double((i64)hi, (i64)lo, q);
+          }
+        } else {
+          const int o = (warp - 4) * KUL_STRIDE;              // L warp w finalizes scalar w
+          const double x = kul_finalize_warp([&rvw, o](int jj) { return rvw.load(o + jj); });
+          if (lane == 0) sh.red[warp - 4] = x;
+        }
+        bar_all();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = tid + 512 * h;
+          const int i = e >> 5, jj = e & 31;
+          const double sg = 0.5 * (Graw[e] + Graw[jj * ST_P + i]);
+          Gsm[i * GS + jj] = -sg;
+          c = fma(sg, sg, c);
+        }
+      }
+      c = warp_sum(c);
+      if (lane == 0) ms.s_part[warp] = c;
+      bar_all();
+      if (flag != 0) {
+        if constexpr (ROLE == 2) {   // drain the outstanding fetches before leaving
+          if (cur0 >= s_lo) mbar_wait_guarded(sb0, bpar0);
+          if (cur1 >= s_lo) mbar_wait_guarded(sb1, bpar1);
+        }
+        exit_reason = -3;
+        break;
+      }
+      if constexpr (ROLE == 1) {
+        if (warp == 4) {
+          // lanes 0..2 evaluate the long-latency operations concurrently, lane 0 takes the decisions
+          double nG2 = 0.0;
+#pragma unroll
+          for (int ww = 0; ww < 16; ++ww) nG2 += ms.s_part[ww];
+          const double nHp2 = fmax(sh.red[SC_HPHP] - nG2, 0.0);
+          double slow = 0.0;
+          if (lane == 0) slow = sqrt(nHp2);
+          else if (lane == 1) slow = sqrt(sh.red[SC_PP]);
+          else if (lane == 2) slow = __ddiv_rn(sh.rv, sh.red[SC_PHP]);                    // alpha, l.341
+          const double sq_nHp2 = __shfl_sync(0xffffffffu, slow, 0), sq_np2 = __shfl_sync(0xffffffffu, slow, 1);
+          const double alpha = __shfl_sync(0xffffffffu, slow, 2);
+          if (lane == 0) {
+            decide_after_A_pre(sh, sh.red[SC_PHP], sq_nHp2, sq_np2, alpha, sh.red[SC_PR], a.Delta, a.epsilon);
+            // ||r + alpha Hp||^2 <= 2 (||r||^2 + alpha^2 ||Hp||^2)
+            ms.s_fe[SC_RV] = fixacc_exponent(2.0 * (sh.rv + sh.step * sh.step * sh.red[SC_HPHP]));
+          }
+        }
+      }
+      bar_all();
+    }
+    ++phase;
+    if (tid == 256) TL5B(44);     // scalar stage done
+    const double step = sh.step;
+    if (sh.action != ACT_CONTINUE) {
+      if constexpr (ROLE == 2) {
+        if (cur0 >= s_lo) mbar_wait_guarded(sb0, bpar0);
+        if (cur1 >= s_lo) mbar_wait_guarded(sb1, bpar1);
+      }
+      const size_t e0 = (size_t)row_lo * ST_P, e1 = (size_t)row_hi * ST_P;
+      for (size_t e = e0 + 2 * (size_t)tid; e < e1; e += 2 * (size_t)blockDim.x) {
+        double2 sv = ldcg2(a.s + e);
+        const double2 pv = ldcg2(p_new + e);
+        sv.x = fma(step, pv.x, sv.x);
+        sv.y = fma(step, pv.y, sv.y);
+        stcg2(a.s + e, sv);
+      }
+      exit_reason = sh.action - 1;
+      break;
+    }
+
+    // ------------------------------ phase B ------------------------------
+    set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
+    {
+      u64 *nxt = a.acc + ((phase + 1) % ACC_SETS) * ACC_WORDS;
+      const int per = (ACC_WORDS + gridDim.x - 1) / gridDim.x;
+      const int z0 = per * blockIdx.x;
+      for (int i = tid; i < per && z0 + i < ACC_WORDS; i += blockDim.x) nxt[z0 + i] = 0;
+    }
+    if constexpr (ROLE == 2) {
+      unsigned ovfb = 0;
+      FixAcc fb = {0, 0};
+      const int feb = ms.s_fe[SC_RV];
+      const double fqb = scalbn(1.0, 90 - feb);
+      int sl = 0;
+      for (;;) {
+        const int sidx = sl ? cur1 : cur0;
+        if (sidx < s_lo) break;     // strips are handed out in decreasing order: the other slot holds nothing either
+        unsigned char *slot = sl ? slot1 : slot0;
+        uint64_t *sb = sl ? sb1 : sb0;
+        int nxt = 0;
+        if (lane == 0) nxt = atomicSub(&ms.s_next_strip, 1);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        const unsigned grow = (unsigned)sidx * 8u + m;
+        const bool valid = grow < n_rows32;
+        const size_t rowoff = (size_t)grow * ST_P;
+        mbar_wait_guarded(sb, sl ? bpar1 : bpar0);
+        if (sl) bpar1 ^= 1; else bpar0 ^= 1;
+        double acc[4][2];
+        double2 sv[4], pv[4], rv[4], yx[4];
+        {
+          const double *tW = reinterpret_cast<const double *>(slot) + m * ST_P;
+          const double *tS = tW + 8 * ST_P, *tP = tS + 8 * ST_P, *tR = tP + 8 * ST_P, *tY = tR + 8 * ST_P;
+          unsigned tok = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = 8 * t + 2 * j;
+            if (valid) {
+              const double2 wv = *reinterpret_cast<const double2 *>(tW + col);
+              acc[t][0] = wv.x; acc[t][1] = wv.y;
+              sv[t] = *reinterpret_cast<const double2 *>(tS + col);
+              pv[t] = *reinterpret_cast<const double2 *>(tP + col);
+              rv[t] = *reinterpret_cast<const double2 *>(tR + col);
+              yx[t] = *reinterpret_cast<const double2 *>(tY + 8 * j + 2 * t);
+            } else {
+              acc[t][0] = acc[t][1] = 0.0;
+              sv[t] = pv[t] = rv[t] = yx[t] = make_double2(0.0, 0.0);
+            }
+            tok |= __double2hiint(acc[t][0]) | __double2hiint(sv[t].x) | __double2hiint(pv[t].x) |
+                   __double2hiint(rv[t].x) | __double2hiint(yx[t].x);
+          }
+          // every lane's shared-memory reads have returned (tok depends on all of them): the slot may be refilled
+          tok = __reduce_or_sync(0xffffffffu, tok);
+          if (nxt >= s_lo && lane == 0 && (tok | 1u)) {
+            fence_proxy_async_smem();
+            strip_fetch5(slot, sb, nxt, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
+          }
+        }
+        strip_rightmul_v(yx, Gsm, lane, acc);   // Hp = W - Y symG
+        double rr = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = 8 * t + 2 * j;
+          sv[t].x = fma(step, pv[t].x, sv[t].x);  sv[t].y = fma(step, pv[t].y, sv[t].y);      // l.374
+          rv[t].x = fma(step, acc[t][0], rv[t].x); rv[t].y = fma(step, acc[t][1], rv[t].y);   // l.377
+          rr = fma(rv[t].x, rv[t].x, rr); rr = fma(rv[t].y, rv[t].y, rr);                      // l.383,408
+          if (valid) {
+            stcg2(a.s + rowoff + col, sv[t]);
+            stcg2(a.r + rowoff + col, rv[t]);
+          }
+        }
+        fixacc_add(fb, rr, fqb, ovfb);      // exact-reduction unit: this lane's 8 elements of the strip
+        if (sl) cur1 = nxt; else cur0 = nxt;
+        sl ^= 1;
+      }
+      if (tid == 256) TL5B(45);   // phase B strips done (warp 8)
+      fixacc_flush(fb, sacc + SC_RV * KUL_STRIDE, feb);
+      if (ovfb) atomicAdd(sacc + SC_RV * KUL_STRIDE + KUL_LIMBS, 1ull);   // non-finite / bound violated: poison <r,r>
+    }
+    bar_all();
+    if (tid == 256) TL5B(46);     // phase B done, CTA-wide
+    if (tid == 0) ms.s_next_strip = s_hi - 1;
+    flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
+    if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
+                             KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr)) { exit_reason = -2; break; }
+    if constexpr (ROLE == 1) {
+      if (warp == 4) {
+        const int o = SC_RV * KUL_STRIDE;
+        const double x = kul_finalize_warp([&rvw, o](int jj) { return rvw.load(o + jj); });
+        if (lane == 0) sh.red[SC_RV] = x;
+      }
+    }
+    bar_all();
+    if (tid == 128) {
+      update_after_B(sh, sh.red[SC_RV]);
+      // bounds for the next iteration's exact accumulators (integer exponent arithmetic only)
+      const int e = half_exponent(st.op_norm_bound * st.op_norm_bound * sh.pk_M_2 * 16.0) + 2;   // |G_ij| <= ||H|| ||p||
+      ms.s_invq = scalbn(1.0, 90 - e);
+      ms.s_q = scalbn(1.0, e - 90);
+      ms.s_fe[SC_PHP] = fixacc_exponent(st.op_norm_bound * sh.pk_M_2);
+      ms.s_fe[SC_HPHP] = fixacc_exponent(st.op_norm_bound * st.op_norm_bound * sh.pk_M_2);
+      ms.s_fe[SC_PP] = fixacc_exponent(sh.pk_M_2);
+      ms.s_fe[SC_PR] = half_exponent(sh.pk_M_2 * sh.rv) + 2;                                      // |<p,r>| <= ||p|| ||r||
+    }
+    bar_all();
+    ++phase;
+    if (tid == 256) TL5B(47);     // iteration done
+    if (a.dbg && tid == 0) {   // [work A, wait A, work B, wait B]; work = previous release -> arrival
+      if (dbg_prev) atomicAdd(a.dbg + 4 * blockIdx.x + 0, ms.s_stamp[0] - dbg_prev);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 1, ms.s_stamp[1] - ms.s_stamp[0]);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 2, ms.s_stamp[2] - ms.s_stamp[1]);
+      atomicAdd(a.dbg + 4 * blockIdx.x + 3, ms.s_stamp[3] - ms.s_stamp[2]);
+      dbg_prev = ms.s_stamp[3];
+    }
+  }
+
+  tc_fence_before();
+  bar_all();
+  if constexpr (ROLE == 0) {
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (blockIdx.x == 0 && tid == 0) {
+      TcgDeviceResult *res = a.result;
+      res->num_iterations = sh.k;
+      res->final_rv = sh.rv;
+      res->phases = phase;
+      if (exit_reason < 0) {
+        res->status = (exit_reason == -3) ? 4 /*OB200_NUMERIC_RANGE*/ : 5 /*OB200_ABORTED*/;
+        res->exit_reason = -1;
+        res->update_step_M_norm = 0.0;
+      } else {
+        res->status = 0;
+        res->exit_reason = exit_reason;
+        res->update_step_M_norm = (exit_reason >= 2) ? a.Delta : sqrt(sh.sk_M_2);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(V5_THREADS, 1)
+tcg_stiefel_v5_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, const int *plane_exp) {
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(v5_smem_raw) + 1023) & ~(uintptr_t)1023);
+  V5Misc &ms = *reinterpret_cast<V5Misc *>(base + V5_MISC);
+  u64 *sacc = reinterpret_cast<u64 *>(base + V5_ACC);
+  double *Ssm = reinterpret_cast<double *>(base + V5_S);
+  uint64_t *mb = reinterpret_cast<uint64_t *>(base + V5_BAR);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (int)(V5_NACC * KUL_STRIDE); i += blockDim.x) sacc[i] = 0;
+  for (int e = tid; e < ST_P * ST_P; e += blockDim.x) Ssm[(e >> 5) * WS + (e & 31)] = -st.S[e];
+  if (tid == 0) {
+    CgShared &sh = ms.sh;
+    sh.rv = a.rv0;
+    sh.sk_M_pk = 0.0;
+    sh.sk_M_2 = 0.0;
+    sh.pk_M_2 = a.rv0;
+    sh.alpha = sh.beta = sh.kappa = sh.step = 0.0;
+    sh.k = 0;
+    sh.action = ACT_CONTINUE;
+    sh.status = 0;
+    const unsigned nstrips = ((unsigned)st.n_rows + 7u) >> 3;
+    ms.s_next_strip = (int)((unsigned long long)nstrips * (blockIdx.x + 1ull) / gridDim.x) - 1;
+    const int e = gram_exponent(st.op_norm_bound * sqrt(a.rv0) * 4.0);
+    ms.s_invq = scalbn(1.0, 90 - e);
+    ms.s_q = scalbn(1.0, e - 90);
+    ms.s_fe[SC_PHP] = fixacc_exponent(st.op_norm_bound * a.rv0);                         // |<p,W>| <= ||H|| ||p||^2
+    ms.s_fe[SC_HPHP] = fixacc_exponent(st.op_norm_bound * st.op_norm_bound * a.rv0);
+    ms.s_fe[SC_PP] = fixacc_exponent(a.rv0);                                             // ||p||^2 = pk_M_2 (l.266)
+    ms.s_fe[SC_PR] = fixacc_exponent(a.rv0);                                             // |<p,r>| <= ||p|| ||r||
+    ms.s_fe[SC_RV] = 0;
+    mbar_init(&mb[B5_RP_FULL], 1);
+    mbar_init(&mb[B5_RP_EMPTY], 128);
+    mbar_init(&mb[B5_A_FULL], 1);
+    mbar_init(&mb[B5_Q_FULL], 128);
+    mbar_init(&mb[B5_MMA_DONE], 1);
+    mbar_init(&mb[B5_MMA_DONE + 1], 1);
+    mbar_init(&mb[B5_TMEM_EMPTY], 256);
+    mbar_init(&mb[B5_TMEM_EMPTY + 1], 256);
+    for (int s = 0; s < (int)V5_NSLOT; ++s) mbar_init(&mb[B5_SLOT + s], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&ms.s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    v5_run<0>(a, st, planes, plane_exp, base);
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    v5_run<1>(a, st, planes, plane_exp, base);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    v5_run<2>(a, st, planes, plane_exp, base);
+  }
+}
+
+cudaError_t launch_tcg_stiefel_v5(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
+                                  const double *Y, const double *S_dev, double op_norm_bound,
+                                  const unsigned char *planes, const int *plane_exp, int sm_count, cudaStream_t stm) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tcg_stiefel_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V5_TOTAL);
+    if (e) return e;
+    attr = true;
+  }
+  const unsigned long long nhalf = (n_rows + 63ull) / 64ull;
+  int grid = sm_count;
+  if ((unsigned long long)grid > nhalf) grid = (int)nhalf;
+  TcgCommon ac = a;
+  StiefelArgs sa{n_rows, A, Y, S_dev, op_norm_bound};
+  const unsigned char *pl = planes;
+  const int *pe = plane_exp;
+  void *args[] = {(void *)&ac, (void *)&sa, (void *)&pl, (void *)&pe};
+  return cudaLaunchCooperativeKernel((const void *)tcg_stiefel_v5_kernel, dim3(grid), dim3(V5_THREADS), args,
+                                     V5_TOTAL, stm);
+}
+
+}  // namespace ob200

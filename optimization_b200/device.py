@@ -119,7 +119,7 @@ class Context:
 
     @property
     def last_path(self):
-        return {1: "tcgen05", 0: "dmma"}.get(self.lib.ob200_last_path(self.h), "?")
+        return {1: "tcgen05", 2: "tcgen05_v4", 0: "dmma"}.get(self.lib.ob200_last_path(self.h), "?")
 
     def synchronize(self):
         self._check(self.lib.ob200_synchronize(self.h))

@@ -7,10 +7,10 @@ out=../../build/variant_$name
 mkdir -p $out
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in capi tcg_elementwise tcg_stiefel level1 stiefel_tc tcg_stiefel_tc tcg_sphere; do
+for f in capi tcg_elementwise tcg_stiefel level1 stiefel_tc tcg_stiefel_tc tcg_stiefel_v5 tcg_sphere lobpcg; do
   [ -f $f.cu ] || continue
   $NVCC $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC "$@" -c $f.cu -o $out/$f.o &
 done
 wait
-$NVCC $ARCH -shared -o ../../build/libob200_$name.so $out/*.o
+$NVCC $ARCH -shared -o ../../build/libob200_$name.so $out/*.o -lcusolver
 echo build/libob200_$name.so
