@@ -119,6 +119,8 @@ struct ob200_context {
   uint64_t planes_n = 0;
   size_t planes_cap = 0;
   bool planes_ok = false;
+  unsigned long long *blk_stats = nullptr; // per-block maxima of r / p for the v5 Stiefel kernel (10 words per block)
+  size_t blk_stats_cap = 0;
   unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
   unsigned long long *dsum = nullptr;      // device / pinned-host word for the per-solve checksum of A
   unsigned long long *hsum = nullptr;
@@ -210,6 +212,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaFree(ctx->dbg);
   cudaFree(ctx->planes);
   cudaFree(ctx->plane_exp);
+  cudaFree(ctx->blk_stats);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   cudaFree(ctx->lob_ws);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -574,6 +577,20 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   a.result = ctx->dres;
   a.dbg = ctx->dbg;
   a.cm = ctx->cm;
+  a.blk_stats = nullptr;
+  a.nblk_stats = 0;
+  if (want_tc && ctx->opt_tcgen05 == 1) {   // v5 kernel: block maxima of r (seeded by the init kernel) and p
+    const size_t nblk = (H->n + 127) / 128;
+    if (nblk > ctx->blk_stats_cap) {
+      cudaFree(ctx->blk_stats);
+      ctx->blk_stats = nullptr; ctx->blk_stats_cap = 0;
+      CK(cudaMalloc(&ctx->blk_stats, sizeof(unsigned long long) * 10 * nblk));
+      ctx->blk_stats_cap = nblk;
+    }
+    CK(cudaMemsetAsync(ctx->blk_stats, 0, sizeof(unsigned long long) * 10 * nblk, ctx->stream));
+    a.blk_stats = ctx->blk_stats;
+    a.nblk_stats = nblk;
+  }
 
   // s = 0, r = g, <r, v>  (IterativeSolvers.h:211-266)
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SETS * ACC_WORDS, st));

@@ -367,10 +367,11 @@ struct RedView {   // reduced word j = sum_r base0[r * stride + j]
 __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned &gen, int *abort_flag,
                                                     const CommDev &cm, unsigned long long gphase, u64 *set,
                                                     int off, int count, RedView &view,
-                                                    unsigned long long *stamps = nullptr /* shared memory */) {
+                                                    unsigned long long *stamps = nullptr /* shared memory */,
+                                                    unsigned leader = 0 /* thread that arrives / spins for the CTA */) {
   __shared__ int s_ok, s_last;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == leader) {
     gen += 1;
     const unsigned target = gen * gridDim.x;
     __threadfence();
@@ -435,7 +436,7 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == leader) {
     if (stamps) stamps[1] = globaltimer_ns();
     s_ok = (*((volatile int *)abort_flag) == 0);
   }

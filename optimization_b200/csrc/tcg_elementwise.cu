@@ -65,6 +65,14 @@ __global__ void __launch_bounds__(TCG_THREADS) tcg_init_kernel(TcgCommon a) {
     store_run<4>(a.s, a.N, e0, lane, z);
     part = warp_sum(part);
     if (lane == 0) kul_add_atomic(sacc, part);
+    if (a.blk_stats) {   // max |r| per 128 x 32 block (16 runs of 256 elements), order independent
+      double mx = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx = fmax(mx, fmax(fabs(g[i].x), fabs(g[i].y)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) atomicMax(a.blk_stats + (u >> 4), (unsigned long long)__double_as_longlong(mx));
+    }
   }
   __syncthreads();
   flush_scalars(sacc, a.acc + SC_RV * KUL_STRIDE, 1);

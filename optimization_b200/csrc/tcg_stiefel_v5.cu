@@ -5,18 +5,21 @@
 // each CG iteration of IterativeSolvers.h:285-422 is two fused phases separated by an exact grid-wide
 // (machine-wide) reduction.
 //
-// 16 warps = 4 warp groups:
-//   S (warps 0-3, 40 registers)  : warp 0 lane 0 = TMA producer: r / p_old tiles of the next block into a 64 KB stage,
+// 20 warps = 5 warp groups:
+//   S (warps 0-3, 24 registers)  : warp 0 lane 0 = TMA producer: r / p_old tiles of the next block into a 64 KB stage,
 //                                  the block's three int8 digit planes of A (48 KB), L2 prefetch of what follows;
 //                                  warp 1 lane 0 = MMA issuer: 13 tcgen05.mma kind::i8 per block into one of two
 //                                  256-column TMEM accumulator sets, tcgen05.commit -> mbarrier.
-//   L (warps 4-7, 152 registers) : r, p_old from the stage -> p = -r + beta p (l.420; written back for the rows this CTA
-//                                  owns), <p,p>, <p,r>, block maximum, seven balanced int8 digit slices of p straight into
-//                                  the UMMA K-major SWIZZLE_128B operand image.
-//   M (warps 8-15, 160 registers): TMEM -> registers in the mma.sync accumulator arrangement (tcgen05.ld 16x256b: no
+//   L (warps 4-7, 80 registers)  : r, p_old from the stage -> p = -r + beta p (l.420; written back for the rows this CTA
+//                                  owns), <p,p>, <p,r>, block maximum; second pass over the stage: seven balanced int8
+//                                  digit slices of p straight into the UMMA K-major SWIZZLE_128B operand image.
+//   M (warps 8-15, 144 registers): TMEM -> registers in the mma.sync accumulator arrangement (tcgen05.ld 16x256b: no
 //                                  shared-memory round trip), integer recombination = Z = A p; W = Z - p S on the fp64
-//                                  tensor cores, W written back, <p,W>, <W,W>, projection Gram Y^T W (exact fixed point).
-// Hand-offs through mbarriers only.  Ownership is by 64-row HALF blocks (balanced to 1/11 instead of 1/6 of a CTA's
+//                                  tensor cores, W written back and staged per 64-row half, <p,W>, <W,W>.
+//   G (warps 16-19, 88 registers): projection Gram Y^T W of the staged half (fp64 tensor cores, exact fixed-point
+//                                  accumulation), Y of the next half fetched with cp.async meanwhile.
+// The fp64 MMA has a dependent-issue latency of ~210 cycles on this part (tools/probe/dmma16.cu): M and G are latency
+// chains, so they run as separate, pipelined roles.  Hand-offs through mbarriers only.  Ownership is by 64-row HALF blocks (balanced to 1/11 instead of 1/6 of a CTA's
 // work): a block shared by two CTAs is sliced and multiplied by both (the MMA needs all 128 rows of p as K), everything
 // else -- p / W stores, the fp64 MMAs, the Gram, all partial sums -- is done for the owned half only.  The A images are
 // row-permuted (tc_row_of_lane) so that either half occupies 16 lanes of every TMEM lane quarter: all eight M warps
@@ -29,7 +32,7 @@
 namespace ob200 {
 using namespace tc;
 
-constexpr int V5_THREADS = 512;
+constexpr int V5_THREADS = 640;
 // shared-memory map (bytes from the 1024-aligned base); phase B aliases the phase-A operand space
 constexpr uint32_t V5_A = 0;                                   // 48 KB int8 digit planes of A
 constexpr uint32_t V5_Q = V5_A + TC_ABLOCK;                    // 28 KB int8 digit image of p
@@ -46,7 +49,7 @@ constexpr uint32_t V5_BAR = V5_ACC + V5_NACC * KUL_STRIDE * 8; // mbarriers
 constexpr uint32_t V5_NBAR = 32;
 constexpr uint32_t V5_MISC = V5_BAR + V5_NBAR * 8;
 constexpr uint32_t V5_MISC_BYTES = 768;
-constexpr uint32_t V5_TOTAL = V5_MISC + V5_MISC_BYTES + 1024;  // + alignment slack
+constexpr uint32_t V5_TOTAL = V5_MISC + V5_MISC_BYTES;         // (+ up to 1 KB of alignment padding after the static part)
 // phase B
 constexpr uint32_t V5_STRIP_TILE = 8 * ST_P * 8;               // 2 KB
 constexpr uint32_t V5_SLOT = 5 * V5_STRIP_TILE;                // 10 KB: W, s, p, r, Y tiles of one 8-row strip
@@ -55,14 +58,14 @@ constexpr uint32_t V5_GRAW = V5_NSLOT * V5_SLOT;               // 8 KB scratch (
 constexpr uint32_t V5_G = V5_Y;                                // -sym(G), stride GS (inside the Y tile region)
 static_assert(V5_GRAW >= V5_W && V5_GRAW + 8192 <= V5_Y, "G scratch must sit in the W tile region");
 static_assert(ST_P * GS * 8 <= V5_WB, "G must fit the Y tile region");
-static_assert(V5_TOTAL <= 232448 - 64, "shared memory budget (227 KB per CTA)");
+static_assert(V5_TOTAL + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
 enum { B5_RP_FULL = 0, B5_RP_EMPTY = 1, B5_A_FULL = 2, B5_Q_FULL = 3, B5_MMA_DONE = 4 /*,5*/, B5_TMEM_EMPTY = 6 /*,7*/,
-       B5_SLOT = 8 /* .. 23 */ };
+       B5_SLOT = 8 /* .. 23 */, B5_W_FULL = 24 /*,25*/, B5_W_EMPTY = 26 /*,27*/ };
 
 struct V5Misc {
   CgShared sh;
-  double s_part[16];
+  double s_part[20];
   double s_invq, s_q;
   double s_lmax[8];
   int s_fe[5];
@@ -138,7 +141,7 @@ extern __shared__ __align__(1024) unsigned char v5_smem_raw[];
 #define TL5B(slot) do { } while (0)
 #endif
 
-// ROLE: 0 = S (service: TMA producer + MMA issuer), 1 = L, 2 = M.  The whole CG loop is instantiated per role so
+// ROLE: 0 = S (service: TMA producer + MMA issuer), 1 = L, 2 = M, 3 = G.  The whole CG loop is instantiated per role so
 // that each warp group's code is compiled against its own register budget.
 template <int ROLE>
 __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st, const unsigned char *planes,
@@ -176,6 +179,7 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
   unsigned bpar0 = 0, bpar1 = 0;   // M: parities of this warp's two strip-slot mbarriers
   unsigned gen = 0, phase = 0;
   unsigned use = 0;                // blocks processed so far by this CTA (mbarrier phase bookkeeping)
+  unsigned wuse = 0;               // M / G: fill / drain count of the two half-block W staging areas (16 bits each)
   int exit_reason = -1;
   unsigned long long dbg_prev = 0;
 
@@ -249,100 +253,118 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
       }
       __syncwarp();
     } else if constexpr (ROLE == 1) {
-      // ===== L: p = -r + beta p_old, digit slices =====
+      // ===== L: p = -r + beta p_old, digit slices -- ONE pass over the staged block =====
+      // The digit slices need a scale 2^E with |p| < 2^E over the block BEFORE the first element is cut.  Instead of a
+      // maximum pass and a second pass, E comes from a bound that is known when the block arrives:
+      //   max |p_new| <= max |r| + |beta| max |p_old|      (both maxima per 128-row block, exact, kept in blk_stats:
+      //   max |r| from phase B of the previous iteration / the init kernel, max |p_old| from this role one iteration ago)
+      // It is a deterministic function of exactly reduced data (identical on every CTA / GPU that handles the block) and
+      // at most a few bits above the true maximum: p is quantised to 2^(E-54), i.e. no coarser than ~2^-52 of the
+      // block maximum.
       const int t = tid - 128, cp = t & 15, g = t >> 4;      // columns 2cp, 2cp+1 ; rows 16g .. 16g+15 of the block
       FixAcc fa0 = {0, 0}, fa1 = {0, 0};                     // <p,p>, <p,r>
       const int fe0 = ms.s_fe[SC_PP], fe1 = ms.s_fe[SC_PR];
       const double fq0 = scalbn(1.0, 90 - fe0), fq1 = scalbn(1.0, 90 - fe1);
       unsigned ovf = 0;
+      const unsigned long long nbs = a.nblk_stats;
+      const unsigned long long *Rcur = a.blk_stats + (k & 1ull) * nbs;
+      unsigned long long *Rnext = a.blk_stats + ((k + 1ull) & 1ull) * nbs;
+      const unsigned long long *Pcur = a.blk_stats + 2 * nbs + (k & 1ull) * 4 * nbs;
+      unsigned long long *Pnext = a.blk_stats + 2 * nbs + ((k + 1ull) & 1ull) * 4 * nbs;
+      const double abeta = fabs(beta);
+      const bool kk = k != 0;
       for (int i = 0; i < nb_local; ++i) {
         const unsigned u = use + i, b = bfirst + i, r0 = b * ST_NB;
         const unsigned hh = 2u * b + (unsigned)(g >> 2);     // this thread's half block
         const bool mine = hh >= h0 && hh < h1;
+        const unsigned char *rrow = Rsm + (16u * g) * 256u + 16u * cp, *prow = POsm + (16u * g) * 256u + 16u * cp;
+        // scale from the bound (uniform over the CTA: every thread reads the same five words)
+        const double rmax = __longlong_as_double((long long)__ldcg(Rcur + b));
+        const ulonglong2 pm01 = __ldcg(reinterpret_cast<const ulonglong2 *>(Pcur + 4 * (size_t)b));
+        const ulonglong2 pm23 = __ldcg(reinterpret_cast<const ulonglong2 *>(Pcur + 4 * (size_t)b + 2));
+        const double pmax = fmax(fmax(__longlong_as_double((long long)pm01.x), __longlong_as_double((long long)pm01.y)),
+                                 fmax(__longlong_as_double((long long)pm23.x), __longlong_as_double((long long)pm23.y)));
+        const double bound = fma(abeta, pmax, rmax) * (1.0 + 0x1p-40);
+        const int E = (bound > 0.0) ? (int)((__double_as_longlong(bound) >> 52) & 0x7ff) - 1023 + 1 : 0;
+        const double scale = scalbn(1.0, 54 - E);
+        if (t == 0 && 2u * b >= h0) __stcg(Rnext + b, 0ull);           // max |r| of the NEXT iteration starts from zero
         if (t == 0) TL5(10);
         mbar_wait_guarded(&mb[B5_RP_FULL], u & 1);
         if (t == 0) TL5(11);
-        double p[16][2];
-        double pp = 0.0, pr = 0.0, mx = 0.0;
+        if (u > 0) mbar_wait_guarded(&mb[B5_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // digit image free
+        if (t == 0) TL5(12);
+        double mx = 0.0;
 #pragma unroll
-        for (int ii = 0; ii < 16; ++ii) {
-          const unsigned row = 16u * g + ii, grow = r0 + row;
-          double2 rv = make_double2(0.0, 0.0), po = make_double2(0.0, 0.0);
-          if (grow < n_rows32) {
-            rv = *reinterpret_cast<const double2 *>(Rsm + row * 256u + 16u * cp);
-            if (k) po = *reinterpret_cast<const double2 *>(POsm + row * 256u + 16u * cp);
+        for (int z = 0; z < 2; ++z) {                        // one column of the pair at a time
+          uint32_t lo[16], hi[16];
+          double pp0 = 0.0, pp1 = 0.0, pr0 = 0.0, pr1 = 0.0;
+#pragma unroll
+          for (int ii = 0; ii < 16; ++ii) {
+            const unsigned grow = r0 + 16u * g + ii;
+            const bool valid = grow < n_rows32, ok = valid && mine;
+            // branch-free (selects): rows beyond n and, in the first iteration, the p_old tile hold stale shared memory
+            double rv = *reinterpret_cast<const double *>(rrow + ii * 256u + 8u * z);
+            double po = *reinterpret_cast<const double *>(prow + ii * 256u + 8u * z);
+            rv = valid ? rv : 0.0;
+            po = (valid && kk) ? po : 0.0;
+            const double pv = fma(beta, po, -rv);                    // l.420; first iteration: beta = 0, p = -r (l.256)
+            if (ok) __stcg(p_new + (size_t)grow * ST_P + 2 * cp + z, pv);
+            const double pm = ok ? pv : 0.0;
+            if (ii & 1) { pp1 = fma(pm, pm, pp1); pr1 = fma(pm, rv, pr1); }
+            else        { pp0 = fma(pm, pm, pp0); pr0 = fma(pm, rv, pr0); }
+            mx = fmax(mx, fabs(pv));
+            const unsigned long long uu = ((unsigned long long)__double2ll_rn(pv * scale) + TC_DIGIT_BIAS) ^ TC_DIGIT_BIAS;
+            lo[ii] = (uint32_t)uu;
+            hi[ii] = (uint32_t)(uu >> 32);
           }
-          double2 pv;
-          if (k) {
-            pv.x = fma(beta, po.x, -rv.x);                   // l.420
-            pv.y = fma(beta, po.y, -rv.y);
-          } else {
-            pv.x = -rv.x;                                    // l.256
-            pv.y = -rv.y;
+          // exact-reduction unit: this thread's 16 elements of one column (inside one half block)
+          fixacc_add(fa0, pp0 + pp1, fq0, ovf);
+          fixacc_add(fa1, pr0 + pr1, fq1, ovf);
+          const uint32_t off = sw128_chunk_off((uint32_t)(2 * cp + z), (uint32_t)g);
+#pragma unroll
+          for (int sl = 0; sl < TC_SLICES; ++sl) {
+            const int d = 6 - sl;                                   // digit index held by slice sl
+            const uint32_t sel = (d & 3) | (((d & 3) + 4) << 4);    // byte d of a -> pos 0, byte d of b -> pos 1
+            uint32_t wq[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t x0 = d < 4 ? lo[4 * q4] : hi[4 * q4], x1 = d < 4 ? lo[4 * q4 + 1] : hi[4 * q4 + 1];
+              const uint32_t x2 = d < 4 ? lo[4 * q4 + 2] : hi[4 * q4 + 2], x3 = d < 4 ? lo[4 * q4 + 3] : hi[4 * q4 + 3];
+              const uint32_t t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
+              wq[q4] = __byte_perm(t01, t23, 0x5410);
+            }
+            *reinterpret_cast<uint4 *>(Qsm + sl * TC_QTILE + off) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
           }
-          if (mine && grow < n_rows32) {
-            stcg2(p_new + (size_t)grow * ST_P + 2 * cp, pv);
-            pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
-            pr = fma(pv.x, rv.x, pr); pr = fma(pv.y, rv.y, pr);
-          }
-          p[ii][0] = pv.x;
-          p[ii][1] = pv.y;
-          mx = fmax(mx, fmax(fabs(pv.x), fabs(pv.y)));
         }
         mbar_arrive(&mb[B5_RP_EMPTY]);                        // the stage may be refilled with the next block
-        if (t == 0) TL5(12);
-        // exact-reduction unit: this thread's 16 x 2 elements (inside one half block)
-        fixacc_add(fa0, pp, fq0, ovf);
-        fixacc_add(fa1, pr, fq1, ovf);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) ms.s_lmax[(u & 1) * 4 + (warp - 4)] = mx;
-        nbar_sync(NB_LSYNC, 128);
-        mx = fmax(fmax(ms.s_lmax[(u & 1) * 4], ms.s_lmax[(u & 1) * 4 + 1]),
-                  fmax(ms.s_lmax[(u & 1) * 4 + 2], ms.s_lmax[(u & 1) * 4 + 3]));
-        // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
-        const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
-        if (t == 0) TL5(13);
-        if (u > 0) mbar_wait_guarded(&mb[B5_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // digit image free
-        if (t == 0) TL5(14);
-        slice_tile16_to_smem(p, scalbn(1.0, 54 - E), Qsm, cp, g);
         fence_proxy_async_smem();
         if (t == 0) ms.s_E[u & 3] = E;
         mbar_arrive(&mb[B5_Q_FULL]);
         if (t == 0) TL5(15);
+        // max |p| of this block (all 128 rows) for the next iteration's bound: one word per L warp, no barrier
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) __stcg(Pnext + 4 * (size_t)b + (warp - 4), (unsigned long long)__double_as_longlong(mx));
+        // a |p| above the bound cannot happen with finite data; non-finite data is flagged by the exact accumulators
+        if (!(mx <= bound)) ovf = 1u;
       }
       fixacc_flush(fa0, sacc + SC_PP * KUL_STRIDE, fe0);
       fixacc_flush(fa1, sacc + SC_PR * KUL_STRIDE, fe1);
       if (ovf) atomicOr((unsigned long long *)(set + ACC_FLAG_OFF), 1ull);
-    } else {
-      // ===== M: TMEM read-back, W = Z - p S, stores, partial sums, projection Gram =====
+    } else if constexpr (ROLE == 2) {
+      // ===== M: TMEM read-back, W = Z - p S, stores, partial sums =====
       const int w = warp - 8, qd = w & 3, hc = w >> 2;       // TMEM lane quarter (= warp % 4), column half
       FixAcc fa0 = {0, 0}, fa1 = {0, 0};                     // <p,W>, <W,W>
       const int fe0 = ms.s_fe[SC_PHP], fe1 = ms.s_fe[SC_HPHP];
       const double fq0 = scalbn(1.0, 90 - fe0), fq1 = scalbn(1.0, 90 - fe1);
       unsigned ovf = 0;
-      i64 gfix[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
       for (int i = 0; i < nb_local; ++i) {
         const unsigned u = use + i, b = bfirst + i, r0 = b * ST_NB;
         const bool own0 = 2u * b >= h0 && 2u * b < h1, own1 = 2u * b + 1u >= h0 && 2u * b + 1u < h1;
-        if (tid == 256) TL5(20);
-        {   // Y of the owned rows -> shared memory (free since the barrier that closed the previous block)
-          const int mt_ = tid - 256, cpy = mt_ & 15, gy = mt_ >> 4;     // rows 8gy .. 8gy+7
-          if ((gy >> 3) ? own1 : own0) {
-            double2 yv[8];
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) {
-              const unsigned grow = r0 + 8 * gy + ii;
-              yv[ii] = (grow < n_rows32) ? ldcg2(st.Y + (size_t)grow * ST_P + 2 * cpy) : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) *reinterpret_cast<double2 *>(Ysm + (8 * gy + ii) * WS + 2 * cpy) = yv[ii];
-          }
-        }
+        if (tid == 256) TL5(21);
         // MMAs of block u complete: the accumulators are ready, and -- through the release / acquire chain L -> MMA
         // issuer -> tcgen05.commit -- every L thread's stores of p (and E) for this block are visible.  (Waiting on
         // Q_FULL here instead would alias: L may run two blocks ahead of M, and an mbarrier only tells odd from even.)
-        if (tid == 256) TL5(21);
         mbar_wait_guarded(&mb[B5_MMA_DONE + (u & 1)], (u >> 1) & 1);
         if (tid == 256) TL5(22);
         tc_fence_after();
@@ -373,6 +395,10 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
             acc[0][1][0] = out[4] * sc; acc[0][1][1] = out[5] * sc;
             acc[1][1][0] = out[6] * sc; acc[1][1][1] = out[7] * sc;
           }
+          if (g16 == 1 || !own1) {   // both read-backs of the block done: the accumulator set may be overwritten
+            tc_fence_before();
+            mbar_arrive(&mb[B5_TMEM_EMPTY + (u & 1)]);
+          }
           if (tid == 256) TL5(23 + 3 * g16);
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {                    // W = A p - p S   (Ssm holds -S)
@@ -384,6 +410,11 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
             dmma884(acc[1][1][0], acc[1][1][1], pa[1][qq], sv1);
           }
           if (tid == 256) TL5(24 + 3 * g16);
+          // the half's W staging area is free once G has finished the Gram of its previous occupant
+          {
+            const unsigned cnt = (wuse >> (16 * g16)) & 0xffffu;
+            if (cnt > 0) mbar_wait_guarded(&mb[B5_W_EMPTY + g16], (cnt - 1) & 1);
+          }
           const int src0 = 4 * m + 2 * (j & 1);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
@@ -409,29 +440,68 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
             fixacc_add(fa0, pw, fq0, ovf);   // exact-reduction unit: this lane's 4 elements of the strip row
             fixacc_add(fa1, ww, fq1, ovf);
           }
+          mbar_arrive(&mb[B5_W_FULL + g16]);                  // this thread's part of the half's W is staged
+          wuse += 1u << (16 * g16);
           if (tid == 256) TL5(25 + 3 * g16);
         }
-        tc_fence_before();
-        mbar_arrive(&mb[B5_TMEM_EMPTY + (u & 1)]);            // the accumulator set may be overwritten
-        nbar_sync(NB_MSYNC2, 256);                            // W complete in Wsm, Y complete in Ysm
-        if (tid == 256) TL5(29);
-        // projection Gram, one exact unit per owned 64-row half
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          if (!(hh ? own1 : own0)) continue;
-          double g00, g01, g10, g11;
-          gram_pair_half_split(Ysm + hh * 64 * WS, Wsm + hh * 64 * WS, w >> 1, 2 * (w & 1), lane, g00, g01, g10, g11);
-          gram_accumulate(g00, g01, inv_q, gfix[0], &ovf);
-          gram_accumulate(g10, g11, inv_q, gfix[1], &ovf);
-        }
-        if (tid == 256) TL5(30);
-        nbar_sync(NB_MSYNC3, 256);                            // Wsm / Ysm free for the next block
-        if (tid == 256) TL5(31);
       }
-      gram_flush(set, 2 * w, lane, gfix[0], ovf);
-      gram_flush(set, 2 * w + 1, lane, gfix[1], 0);
       fixacc_flush(fa0, sacc + SC_PHP * KUL_STRIDE, fe0);
       fixacc_flush(fa1, sacc + SC_HPHP * KUL_STRIDE, fe1);
+      if (ovf) atomicOr((unsigned long long *)(set + ACC_FLAG_OFF), 1ull);
+    } else {
+      // ===== G: projection Gram Y^T W, one exact unit per owned 64-row half =====
+      const int gw = warp - 16, gt = tid - 512;              // warp gw: Gram rows 8 gw .. 8 gw + 7 (columns of Y), all 32 columns
+      unsigned ovf = 0;
+      i64 gfix[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) gfix[nt][0] = gfix[nt][1] = gfix[nt][2] = gfix[nt][3] = 0;
+      // Y of a half -> its shared-memory area with cp.async (16-byte chunks, padded rows): issued one half ahead
+      auto fetch_y = [&](unsigned hh) {
+        const unsigned rbase = hh * 64u, hsel = hh & 1u;
+        const int cpy = gt & 15, gy = gt >> 4;                // 8 rows x 16 column pairs per pass
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          const unsigned rloc = 8u * ps + gy, grow = rbase + rloc;
+          double *dst = Ysm + (64u * hsel + rloc) * WS + 2 * cpy;
+          if (grow < n_rows32) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
+                         "l"(st.Y + (size_t)grow * ST_P + 2 * cpy) : "memory");
+          } else {
+            *reinterpret_cast<double2 *>(dst) = make_double2(0.0, 0.0);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if (h1 > h0) fetch_y(h0);
+      for (unsigned hh = h0; hh < h1; ++hh) {
+        const unsigned hsel = hh & 1u;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        nbar_sync(NB_MSYNC2, 128);       // Y(hh) visible to all G warps; everybody is done with the other half's area
+        if (hh + 1 < h1) fetch_y(hh + 1);
+        mbar_wait_guarded(&mb[B5_W_FULL + hsel], (wuse >> (16 * hsel)) & 1);
+        const double *Yh = Ysm + 64u * hsel * WS, *Wh = Wsm + 64u * hsel * WS;
+        // 4 tiles (gw, nt) x 2 k-halves = 8 independent accumulator chains of 8 steps
+        double ga[4][2][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) ga[nt][0][0] = ga[nt][0][1] = ga[nt][1][0] = ga[nt][1][1] = 0.0;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            const int krow = 4 * (8 * kh + qq) + j;
+            const double x = Yh[krow * WS + 8 * gw + m];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(ga[nt][kh][0], ga[nt][kh][1], x, Wh[krow * WS + 8 * nt + m]);
+          }
+        }
+        mbar_arrive(&mb[B5_W_EMPTY + hsel]);                  // M may stage the next occupant of this half
+        wuse += 1u << (16 * hsel);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          gram_accumulate(ga[nt][0][0] + ga[nt][1][0], ga[nt][0][1] + ga[nt][1][1], inv_q, gfix[nt], &ovf);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) gram_flush(set, 4 * gw + nt, lane, gfix[nt], nt == 0 ? ovf : 0);
     }
     use += (unsigned)nb_local;
     if (tid == 0) TL5B(40);     // S done
@@ -441,7 +511,7 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
     flush_scalars(sacc, set, 4);
     RedView rvw;
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
-                             a.dbg ? ms.s_stamp : nullptr)) { exit_reason = -2; break; }
+                             a.dbg ? ms.s_stamp : nullptr, 128u)) { exit_reason = -2; break; }
     if (tid == 256) TL5B(43);     // barrier A released
     // first two strips of phase B for each M warp: start streaming them in before the scalar stage
     int cur0 = -1, cur1 = -1;
@@ -462,10 +532,10 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
       const u64 flag = rvw.load(ACC_FLAG_OFF);
       double c = 0.0;
       {
-        // G (fixed point) -> shared memory (S and M warps) while the four L warps finalize the four exact scalars
+        // G (fixed point) -> shared memory (M and G warps) while the four L warps finalize the four exact scalars
         double *Graw = reinterpret_cast<double *>(base + V5_GRAW);
-        if constexpr (ROLE != 1) {
-          for (int e = (ROLE == 0 ? tid : tid - 128); e < ST_P * ST_P; e += 384) {
+        if constexpr (ROLE >= 2) {
+          for (int e = tid - 256; e < ST_P * ST_P; e += 384) {
             u64 hi, lo;
             if (rvw.world == 1) {
               const ulonglong2 wv = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + ACC_GRAM_OFF + 2 * e));
@@ -475,15 +545,13 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
             }
             Graw[e] = fix2_to_double((i64)hi, (i64)lo, q);
           }
-        } else {
+        } else if constexpr (ROLE == 1) {
           const int o = (warp - 4) * KUL_STRIDE;              // L warp w finalizes scalar w
           const double x = kul_finalize_warp([&rvw, o](int jj) { return rvw.load(o + jj); });
           if (lane == 0) sh.red[warp - 4] = x;
         }
         bar_all();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int e = tid + 512 * h;
+        for (int e = tid; e < ST_P * ST_P; e += V5_THREADS) {
           const int i = e >> 5, jj = e & 31;
           const double sg = 0.5 * (Graw[e] + Graw[jj * ST_P + i]);
           Gsm[i * GS + jj] = -sg;
@@ -506,7 +574,7 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
           // lanes 0..2 evaluate the long-latency operations concurrently, lane 0 takes the decisions
           double nG2 = 0.0;
 #pragma unroll
-          for (int ww = 0; ww < 16; ++ww) nG2 += ms.s_part[ww];
+          for (int ww = 0; ww < V5_THREADS / 32; ++ww) nG2 += ms.s_part[ww];
           const double nHp2 = fmax(sh.red[SC_HPHP] - nG2, 0.0);
           double slow = 0.0;
           if (lane == 0) slow = sqrt(nHp2);
@@ -614,6 +682,16 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
           }
         }
         fixacc_add(fb, rr, fqb, ovfb);      // exact-reduction unit: this lane's 8 elements of the strip
+        {   // max |r| per 128-row block for the scale bound of the next phase A (order independent)
+          double rm = 0.0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) rm = fmax(rm, fmax(fabs(rv[t].x), fabs(rv[t].y)));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+          if (lane == 0)
+            atomicMax(a.blk_stats + ((k + 1ull) & 1ull) * a.nblk_stats + ((unsigned)sidx >> 4),
+                      (unsigned long long)__double_as_longlong(rm));
+        }
         if (sl) cur1 = nxt; else cur0 = nxt;
         sl ^= 1;
       }
@@ -626,7 +704,7 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
     if (tid == 0) ms.s_next_strip = s_hi - 1;
     flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
-                             KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr)) { exit_reason = -2; break; }
+                             KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr, 128u)) { exit_reason = -2; break; }
     if constexpr (ROLE == 1) {
       if (warp == 4) {
         const int o = SC_RV * KUL_STRIDE;
@@ -682,7 +760,10 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
 
 __global__ void __launch_bounds__(V5_THREADS, 1)
 tcg_stiefel_v5_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, const int *plane_exp) {
-  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(v5_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // the dynamic shared-memory window is declared 1024-byte aligned (SWIZZLE_128B operand images); all pointers are
+  // derived from the array itself so that the compiler keeps them in the shared address space (LDS / STS, not generic)
+  unsigned char *base = v5_smem_raw;
+  if (smem_u32(base) & 1023u) __trap();
   V5Misc &ms = *reinterpret_cast<V5Misc *>(base + V5_MISC);
   u64 *sacc = reinterpret_cast<u64 *>(base + V5_ACC);
   double *Ssm = reinterpret_cast<double *>(base + V5_S);
@@ -719,21 +800,30 @@ tcg_stiefel_v5_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     mbar_init(&mb[B5_TMEM_EMPTY], 256);
     mbar_init(&mb[B5_TMEM_EMPTY + 1], 256);
     for (int s = 0; s < (int)V5_NSLOT; ++s) mbar_init(&mb[B5_SLOT + s], 1);
+    mbar_init(&mb[B5_W_FULL], 256);
+    mbar_init(&mb[B5_W_FULL + 1], 256);
+    mbar_init(&mb[B5_W_EMPTY], 128);
+    mbar_init(&mb[B5_W_EMPTY + 1], 128);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&ms.s_tmem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // register budgets per warp group: 640 threads are launched with 96 registers each (61440 in the CTA's pool)
+  //   S 24 x 128 + L 96 x 128 + M 136 x 256 + G 88 x 128 = 61440
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     v5_run<0>(a, st, planes, plane_exp, base);
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     v5_run<1>(a, st, planes, plane_exp, base);
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+  } else if (warp < 16) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     v5_run<2>(a, st, planes, plane_exp, base);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    v5_run<3>(a, st, planes, plane_exp, base);
   }
 }
 

@@ -9,6 +9,7 @@ import subprocess
 subprocess.run(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"), "port"], check=True)
 port = refapi.PortOracle()
 ctx = Context(0)
+ctx.set_option("tcgen05", 1)
 def rel(a, b): return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 sizes = [int(a) for a in sys.argv[1:]] or [128, 64, 300, 1000, 4096, 20000]
 ok = True

@@ -4,6 +4,7 @@ import numpy as np, torch, ctypes as C
 from optimization_b200 import problems as P
 from optimization_b200.device import Context
 ctx = Context(0)
+ctx.set_option("tcgen05", 1)
 n = 100000
 prob = P.make_stiefel_critical(n, 32)
 A = torch.from_numpy(prob.A_bf16.view(np.int16)).cuda(); Y = ctx.to_device(prob.Y0); g = ctx.to_device(prob.g)
