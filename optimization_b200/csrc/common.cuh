@@ -457,6 +457,21 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// fp64 tensor-core MMA, large shape: D(16x8) += A(16x16) * B(16x8).  With g = lane / 4, t = lane % 4:
+//   a[i] : A[row = g + 8 (i & 1)][k = t + 4 (i >> 1)],  i < 8
+//   b[i] : B[k = t + 4 i][col = g],                      i < 4
+//   c[i] : C[row = g + 8 (i >> 1)][col = 2 t + (i & 1)], i < 4
+// (layout verified by tools/probe/dmma16.cu).  Same throughput per flop as m8n8k4 on this part, but ~400 cycles of
+// dependent-issue latency for eight times the work (m8n8k4: ~210 cycles).
+__device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, "
+      "{%0,%1,%2,%3};"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+        "d"(b[2]), "d"(b[3]));
+}
+
 __device__ __forceinline__ double bf16_bits_to_double(unsigned short b) {
   return (double)__uint_as_float(((unsigned)b) << 16);
 }

@@ -288,8 +288,11 @@ __device__ __forceinline__ void recombine_row16(uint32_t tmem_row_addr /* lane |
                       ((long long)(int)v[0][c] << 24);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      out[8 * hcol + c] = fma((double)part[1][c], 0x1p-32, (double)part[0][c]) * 0x1p-24;
+    for (int c = 0; c < 8; ++c) {   // |part| < 2^48: exact int64 -> double through the 2^52 + 2^51 bias
+      const double p1 = __longlong_as_double(0x4338000000000000ll + part[1][c]) - 6755399441055744.0;
+      const double p0 = __longlong_as_double(0x4338000000000000ll + part[0][c]) - 6755399441055744.0;
+      out[8 * hcol + c] = fma(p1, 0x1p-32, p0) * 0x1p-24;
+    }
   }
 }
 

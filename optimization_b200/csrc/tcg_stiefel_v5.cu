@@ -373,12 +373,15 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
         const uint32_t tacc = tmem_base + (u & 1) * TC_TMEM_COLS + ((uint32_t)(32 * qd) << 16) + 16 * hc;
         // The two 16-lane groups (half blocks) of this warp's TMEM lane quarter, one after the other (one copy of the
         // code, small register footprint: with 226 KB of shared memory the L1 is 2 KB, a spill is an L2 round trip).
-        // Per group: the rows of p as fp64 MMA A fragments (strip s = rows 8 s + m of the group; L2 loads, in flight
-        // during the TMEM read-back), Z = A p from TMEM in the accumulator arrangement, W = Z - p S, stores, partial sums.
+        // Per group: the rows of p as fp64 MMA A fragments (strip s = rows 8 s + m of the group; L2 loads issued first,
+        // in flight during the TMEM read-back -- measured: an exposed L2 load costs 2-3 us under this traffic),
+        // Z = A p from TMEM in the accumulator arrangement, W = Z - p S, stores, partial sums.
+        // (Measured alternative: both groups interleaved with the p loads after the read-backs: 131 us per iteration
+        // instead of 120 -- the loads' latency is exposed; holding both groups' fragments across the read-backs spills.)
 #pragma unroll 1
         for (int g16 = 0; g16 < 2; ++g16) {
           if (!(g16 ? own1 : own0)) continue;
-          double pa[2][8];
+          double pa[2][8];                                    // pa[s][qq] = p[row 8 s + m of the group][4 qq + j]
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             const unsigned grow = r0 + 64u * g16 + 16u * qd + 8u * s + m;
@@ -386,32 +389,34 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) pa[s][qq] = ld ? __ldcg(p_new + (size_t)grow * ST_P + 4 * qq + j) : 0.0;
           }
-          double acc[2][2][2];                                // [s][tile tt][c]
+          double acc[2][4];                                   // [tile tt][rows m: c 0,1 ; rows m + 8: c 2,3] (m16n8k16 C layout)
           {
             double out[8];
             recombine_frag16(tacc + ((uint32_t)(16 * g16) << 16), out);
-            acc[0][0][0] = out[0] * sc; acc[0][0][1] = out[1] * sc;
-            acc[1][0][0] = out[2] * sc; acc[1][0][1] = out[3] * sc;
-            acc[0][1][0] = out[4] * sc; acc[0][1][1] = out[5] * sc;
-            acc[1][1][0] = out[6] * sc; acc[1][1][1] = out[7] * sc;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[0][c] = out[c] * sc; acc[1][c] = out[4 + c] * sc; }
           }
           if (g16 == 1 || !own1) {   // both read-backs of the block done: the accumulator set may be overwritten
             tc_fence_before();
             mbar_arrive(&mb[B5_TMEM_EMPTY + (u & 1)]);
           }
           if (tid == 256) TL5(23 + 3 * g16);
+          // W = A p - p S (Ssm holds -S): two 16 x 8 tiles, two k-steps of 16 each (2 chains of 2 large fp64 MMAs)
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq) {                    // W = A p - p S   (Ssm holds -S)
-            const double *Mrow = Ssm + (4 * qq + j) * WS + m + 16 * hc;
-            const double sv0 = Mrow[0], sv1 = Mrow[8];
-            dmma884(acc[0][0][0], acc[0][0][1], pa[0][qq], sv0);
-            dmma884(acc[1][0][0], acc[1][0][1], pa[1][qq], sv0);
-            dmma884(acc[0][1][0], acc[0][1][1], pa[0][qq], sv1);
-            dmma884(acc[1][1][0], acc[1][1][1], pa[1][qq], sv1);
+          for (int ks = 0; ks < 2; ++ks) {
+            double af[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) af[ii] = pa[ii & 1][4 * ks + (ii >> 1)];
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+              double bf[4];
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) bf[ii] = Ssm[(16 * ks + j + 4 * ii) * WS + 16 * hc + 8 * tt + m];
+              dmma16816(acc[tt], af, bf);
+            }
           }
           if (tid == 256) TL5(24 + 3 * g16);
-          // the half's W staging area is free once G has finished the Gram of its previous occupant
-          {
+          {   // the half's W staging area is free once G has finished the Gram of its previous occupant
             const unsigned cnt = (wuse >> (16 * g16)) & 0xffffu;
             if (cnt > 0) mbar_wait_guarded(&mb[B5_W_EMPTY + g16], (cnt - 1) & 1);
           }
@@ -430,7 +435,7 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
               const double a0 = __shfl_sync(0xffffffffu, e0, src0), b0 = __shfl_sync(0xffffffffu, e1, src0);
               const double a1 = __shfl_sync(0xffffffffu, e0, src0 + 1), b1 = __shfl_sync(0xffffffffu, e1, src0 + 1);
               const double px = (j >> 1) ? b0 : a0, py = (j >> 1) ? b1 : a1;
-              const double wx = acc[s][tt][0], wy = acc[s][tt][1];
+              const double wx = acc[tt][2 * s], wy = acc[tt][2 * s + 1];
               pw = fma(px, wx, pw); pw = fma(py, wy, pw);
               ww = fma(wx, wx, ww); ww = fma(wy, wy, ww);
               const double2 wv = make_double2(wx, wy);
@@ -450,7 +455,7 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
       if (ovf) atomicOr((unsigned long long *)(set + ACC_FLAG_OFF), 1ull);
     } else {
       // ===== G: projection Gram Y^T W, one exact unit per owned 64-row half =====
-      const int gw = warp - 16, gt = tid - 512;              // warp gw: Gram rows 8 gw .. 8 gw + 7 (columns of Y), all 32 columns
+      const int gw = warp - 16, gt = tid - 512, mp = gw >> 1, np = gw & 1;   // warp gw: 16 x 16 quadrant (mp, np) of the Gram
       unsigned ovf = 0;
       i64 gfix[4][4];
 #pragma unroll
@@ -480,28 +485,41 @@ __device__ __forceinline__ void v5_run(const TcgCommon &a, const StiefelArgs &st
         if (hh + 1 < h1) fetch_y(hh + 1);
         mbar_wait_guarded(&mb[B5_W_FULL + hsel], (wuse >> (16 * hsel)) & 1);
         const double *Yh = Ysm + 64u * hsel * WS, *Wh = Wsm + 64u * hsel * WS;
-        // 4 tiles (gw, nt) x 2 k-halves = 8 independent accumulator chains of 8 steps
-        double ga[4][2][2];
+        // G[16 mp .. +15][16 np .. +15] over the 64 rows: A = Y^T (16 x 16 per k-step), B = W (16 x 8 per tile);
+        // two n-tiles x two k-halves = 4 independent chains of 2 large fp64 MMAs
+        double ga[2][2][4];                                   // [n-tile][k-half][c]
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) ga[nt][0][0] = ga[nt][0][1] = ga[nt][1][0] = ga[nt][1][1] = 0.0;
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
+          for (int kh = 0; kh < 2; ++kh) ga[nt][kh][0] = ga[nt][kh][1] = ga[nt][kh][2] = ga[nt][kh][3] = 0.0;
 #pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
-            const int krow = 4 * (8 * kh + qq) + j;
-            const double x = Yh[krow * WS + 8 * gw + m];
+        for (int ks = 0; ks < 4; ++ks) {
+          double af[8];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) dmma884(ga[nt][kh][0], ga[nt][kh][1], x, Wh[krow * WS + 8 * nt + m]);
+          for (int ii = 0; ii < 8; ++ii) af[ii] = Yh[(16 * ks + j + 4 * (ii >> 1)) * WS + 16 * mp + m + 8 * (ii & 1)];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            double bf[4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) bf[ii] = Wh[(16 * ks + j + 4 * ii) * WS + 16 * np + 8 * nt + m];
+            dmma16816(ga[nt][ks >> 1], af, bf);
           }
         }
         mbar_arrive(&mb[B5_W_EMPTY + hsel]);                  // M may stage the next occupant of this half
         wuse += 1u << (16 * hsel);
+        // c[0], c[1]: Gram row 16 mp + m, columns 16 np + 8 nt + 2 j + {0, 1};  c[2], c[3]: row + 8
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-          gram_accumulate(ga[nt][0][0] + ga[nt][1][0], ga[nt][0][1] + ga[nt][1][1], inv_q, gfix[nt], &ovf);
+        for (int nt = 0; nt < 2; ++nt) {
+          gram_accumulate(ga[nt][0][0] + ga[nt][1][0], ga[nt][0][1] + ga[nt][1][1], inv_q, gfix[2 * nt], &ovf);
+          gram_accumulate(ga[nt][0][2] + ga[nt][1][2], ga[nt][0][3] + ga[nt][1][3], inv_q, gfix[2 * nt + 1], &ovf);
+        }
       }
+      // gfix[2 nt + hrow] <-> 8 x 8 Gram tile (row tile 2 mp + hrow, column tile 2 np + nt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) gram_flush(set, 4 * gw + nt, lane, gfix[nt], nt == 0 ? ovf : 0);
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow)
+          gram_flush(set, 4 * (2 * mp + hrow) + 2 * np + nt, lane, gfix[2 * nt + hrow], (nt | hrow) == 0 ? ovf : 0);
     }
     use += (unsigned)nb_local;
     if (tid == 0) TL5B(40);     // S done
@@ -811,18 +829,18 @@ tcg_stiefel_v5_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   __syncthreads();
   tc_fence_after();
   // register budgets per warp group: 640 threads are launched with 96 registers each (61440 in the CTA's pool)
-  //   S 24 x 128 + L 96 x 128 + M 136 x 256 + G 88 x 128 = 61440
+  //   S 24 x 128 + L 88 x 128 + M 128 x 256 + G 112 x 128 = 61440
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     v5_run<0>(a, st, planes, plane_exp, base);
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     v5_run<1>(a, st, planes, plane_exp, base);
   } else if (warp < 16) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     v5_run<2>(a, st, planes, plane_exp, base);
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     v5_run<3>(a, st, planes, plane_exp, base);
   }
 }
