@@ -42,7 +42,9 @@ cudaError_t launch_stiefel_checksum(const unsigned short *A, unsigned long long 
                                     int sm_count, cudaStream_t st);
 cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
-                                  const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm);
+                                  const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm,
+                                  int hvp_mode = 0, const unsigned long long *planes_sum_dev = nullptr,
+                                  unsigned long long planes_sum_expected = 0);
 cudaError_t launch_tcg_stiefel_v5(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
                                   const unsigned char *planes, const int *plane_exp, int sm_count, cudaStream_t stm);
@@ -119,6 +121,8 @@ struct ob200_context {
   uint64_t planes_n = 0;
   size_t planes_cap = 0;
   bool planes_ok = false;
+  double S_cache[1024];                    // last S uploaded to dmat[0..1023] (skip the pageable H2D copy when unchanged)
+  bool S_cache_valid = false;
   unsigned long long *blk_stats = nullptr; // per-block maxima of r / p for the v5 Stiefel kernel (10 words per block)
   size_t blk_stats_cap = 0;
   unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
@@ -510,6 +514,7 @@ static int sphere_Av(ob200_context *ctx, uint64_t n, uint64_t k, const double *d
   if (!ldu) ldu = n;
   cudaStream_t st = ctx->stream;
   double *st_dev = ctx->dmat;   // k doubles
+  ctx->S_cache_valid = false;   // (dmat[0..] is also where the Stiefel HVP keeps S)
   if (k) {
     CK(cudaMemsetAsync(ctx->acc + ACC_GRAM_OFF, 0, sizeof(u64) * 16 * KUL_STRIDE, st));
     CK(launch_sphere_tdot(n, Ut, ldu, sigma_host, (int)k, v, ctx->acc, ctx->sm_count, st));
@@ -601,8 +606,10 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   ctx->launches += 2;
   CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));  // set 0 is reused by the loop
-  if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG)
+  if (H->kind == OB200_OP_STIEFEL_BLOCKDIAG) {
     CK(cudaMemcpyAsync(ctx->dmat, H->S_host, sizeof(double) * 32 * 32, cudaMemcpyHostToDevice, st));
+    ctx->S_cache_valid = false;
+  }
   CK(cudaStreamSynchronize(st));
   if (want_tc) {
     if ((rc = planes_validate(ctx, H->A_bf16_dev, H->n))) return rc;
@@ -827,16 +834,70 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
     return OB200_OK;
   }
   if (H->kind != OB200_OP_STIEFEL_BLOCKDIAG || H->p != 32) return fail(ctx, OB200_UNSUPPORTED, "operator kind");
+  if (!H->A_bf16_dev || !H->Y_dev || !H->S_host) return fail(ctx, OB200_INVALID_ARGUMENT, "incomplete Stiefel operator");
   int rc = ensure_vectors(ctx, N);
   if (rc) return rc;
   const unsigned long long nblk = (H->n + 127) / 128;
   int grid = ctx->sm_count;
   if ((unsigned long long)grid > nblk) grid = (int)nblk;
-  double vv = 0.0;
+  // <V,V> stays on the device: it bounds the exact fixed-point Gram of the projection
   const double *aa[1] = {v}, *bb[1] = {v};
-  if ((rc = dots_sync(ctx, N, 1, aa, bb, &vv))) return rc;
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SCAL_WORDS, st));
+  CK(launch_dots(N, 1, aa, bb, ctx->acc, ctx->sm_count, st));
+  if ((rc = exchange(ctx, ctx->acc, 0, KUL_STRIDE))) return rc;
+  CK(launch_finalize_many(ctx->acc, 1, ctx->dscal, st));
+  ctx->launches += 2;
+  if (!(ctx->S_cache_valid && !memcmp(ctx->S_cache, H->S_host, sizeof(ctx->S_cache)))) {
+    memcpy(ctx->S_cache, H->S_host, sizeof(ctx->S_cache));
+    CK(cudaMemcpyAsync(ctx->dmat, ctx->S_cache, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
+    ctx->S_cache_valid = true;
+  }
+  if (ctx->opt_tcgen05) {
+    // One persistent launch (the two fused phases of a CG step: contraction + Gram | projection), no host round trip:
+    // the digit planes are validated ON THE DEVICE against the content checksum of A (stale: rebuild and relaunch).
+    if (!(ctx->planes_key == H->A_bf16_dev && ctx->planes_n == H->n)) {
+      if ((rc = ensure_planes(ctx, H->A_bf16_dev, H->n))) return rc;
+    }
+    for (int attempt = 0; attempt < 2 && ctx->planes_ok; ++attempt) {
+      CK(cudaMemsetAsync(ctx->dsum, 0, 8, st));
+      CK(launch_stiefel_checksum(H->A_bf16_dev, nblk, ctx->dsum, ctx->sm_count, st));
+      CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SETS * ACC_WORDS, st));
+      CK(cudaMemsetAsync(ctx->barrier, 0, 64, st));
+      TcgCommon a;
+      memset(&a, 0, sizeof(a));
+      a.N = N;
+      a.g = ctx->dscal;             // device scalar <V,V>
+      a.s = out;
+      a.r = const_cast<double *>(v);
+      a.p0 = ctx->p0; a.p1 = ctx->p1;
+      a.Hp = ctx->Hp;
+      a.Delta = 1.0; a.epsilon = 1e-8;
+      a.acc = ctx->acc;
+      a.barrier = ctx->barrier;
+      a.abort_flag = reinterpret_cast<int *>(ctx->barrier + 1);
+      a.result = ctx->dres;
+      a.cm = ctx->cm;
+      CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
+                               ctx->plane_exp, grid, st, 1, ctx->dsum, ctx->planes_sum));
+      ctx->launches += 2;
+      CK(cudaMemcpyAsync(ctx->hres, ctx->dres, sizeof(TcgDeviceResult), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (ctx->hres->status == 6) {                 // A changed under the cached planes: rebuild, once
+        ctx->planes_key = nullptr;
+        if ((rc = ensure_planes(ctx, H->A_bf16_dev, H->n))) return rc;
+        continue;
+      }
+      ctx->cm.epoch += ctx->hres->phases;
+      if (ctx->hres->status == OB200_NUMERIC_RANGE) return fail(ctx, OB200_NUMERIC_RANGE, "fixed-point Gram bound exceeded or non-finite data");
+      if (ctx->hres->status == OB200_ABORTED) return fail(ctx, OB200_ABORTED, "device grid barrier watchdog fired");
+      return OB200_OK;
+    }
+  }
+  // A not block-fixed-point (or tcgen05 switched off): fp64 tensor-core kernels, Gram symmetrised by the host
+  double vv = 0.0;
+  CK(cudaMemcpyAsync(&vv, ctx->dscal, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   const int e = gram_exponent_host(H->op_norm_bound * std::sqrt(vv) * 4.0);
-  CK(cudaMemcpyAsync(ctx->dmat, H->S_host, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));
   CK(launch_stiefel_apply(H->n, H->A_bf16_dev, v, ctx->dmat, H->Y_dev, ctx->Hp, ctx->acc,
                           std::ldexp(1.0, 90 - e), grid, st));

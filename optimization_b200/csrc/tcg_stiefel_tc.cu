@@ -169,6 +169,18 @@ __device__ __forceinline__ void strip_fetch(unsigned char *slot, uint64_t *bar, 
   bulk_g2s(slot + 4 * STRIP_TILE, Y + off, bytes, bar);
 }
 
+// stand-alone HVP mode: only the W and Y tiles of the strip
+__device__ __forceinline__ void strip_fetch_wy(unsigned char *slot, uint64_t *bar, int sidx, unsigned n_rows,
+                                               const double *W, const double *Y) {
+  const unsigned row0 = (unsigned)sidx * 8u;
+  const unsigned rows = n_rows - row0 < 8u ? n_rows - row0 : 8u;
+  const uint32_t bytes = rows * ST_P * (uint32_t)sizeof(double);
+  const size_t off = (size_t)row0 * ST_P;
+  mbar_expect_tx(bar, 2 * bytes);
+  bulk_g2s(slot, W + off, bytes, bar);
+  bulk_g2s(slot + 4 * STRIP_TILE, Y + off, bytes, bar);
+}
+
 extern __shared__ __align__(16) unsigned char v3_smem_raw[];
 
 // debug timeline (CTA 0, third block of an iteration): slot <- globaltimer
@@ -181,8 +193,15 @@ extern __shared__ __align__(16) unsigned char v3_smem_raw[];
 #define TLB(slot) do { } while (0)
 #endif
 
+// MODE 0: the whole Steihaug-Toint solve.  MODE 1: ONE stand-alone Hessian-vector product out = Hess f(Y)[V]
+// (reference call sites IterativeSolvers.h:294, TNT.h:512) with the same two fused phases and no host round trip:
+// a.r = V (input), a.Hp = W workspace, a.s = out, a.g -> device scalar <V,V> (bound for the exact fixed-point Gram),
+// `planes_sum_dev` / `planes_sum_expected`: the content checksum of A the digit planes were built from (a mismatch
+// ends the launch with status 6: the host rebuilds the planes and relaunches).
+template <int MODE>
 __global__ void __launch_bounds__(V3_THREADS, 1)
-tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, const int *plane_exp) {
+tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, const int *plane_exp,
+                      const unsigned long long *planes_sum_dev, unsigned long long planes_sum_expected) {
   __shared__ CgShared sh;
   __shared__ double s_part[16];
   __shared__ double s_invq, s_q;
@@ -206,6 +225,15 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   const int m = lane >> 2, j = lane & 3;
   const bool is_L = warp < 8;
   const int mw = warp - 8;
+  if (MODE == 1) {
+    a.rv0 = __ldcg(a.g);
+    a.target = -1.0;                                         // never "converged": the single pass always runs
+    a.max_iterations = 1;
+    if (__ldcg(planes_sum_dev) != planes_sum_expected) {     // uniform over the grid: stale digit planes
+      if (blockIdx.x == 0 && tid == 0) { a.result->status = 6; a.result->exit_reason = -1; a.result->phases = 0; }
+      return;
+    }
+  }
   for (int i = tid; i < ACC_NSCAL * KUL_STRIDE; i += blockDim.x) sacc[i] = 0;
   for (int e = tid; e < ST_P * ST_P; e += blockDim.x) Ssm[(e >> 5) * WS + (e & 31)] = -st.S[e];
   if (tid == 0) {
@@ -331,7 +359,9 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           for (int ii = 0; ii < 8; ++ii) {
             const unsigned grow = r0 + 8 * g + ii;
             double2 pv;
-            if (k) {
+            if (MODE == 1) {
+              pv = rv[ii];                                  // stand-alone HVP: the operand itself
+            } else if (k) {
               pv.x = fma(beta, po[ii].x, -rv[ii].x);        // l.420
               pv.y = fma(beta, po[ii].y, -rv[ii].y);
             } else {
@@ -339,7 +369,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
               pv.y = -rv[ii].y;
             }
             if (grow < n_rows32) {
-              stcg2(p_new + (size_t)grow * ST_P + 2 * cp, pv);
+              if (MODE == 0) stcg2(p_new + (size_t)grow * ST_P + 2 * cp, pv);
               pp = fma(pv.x, pv.x, pp); pp = fma(pv.y, pv.y, pp);
               pr = fma(pv.x, rv[ii].x, pr); pr = fma(pv.y, rv[ii].y, pr);
             }
@@ -437,8 +467,9 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           const bool l0 = g0 < n_rows32, l1 = g1 < n_rows32;
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {
-            pa0[qq] = l0 ? __ldcg(p_new + (size_t)g0 * ST_P + 4 * qq + j) : 0.0;
-            pa1[qq] = l1 ? __ldcg(p_new + (size_t)g1 * ST_P + 4 * qq + j) : 0.0;
+            const double *psrc = MODE == 1 ? a.r : p_new;
+            pa0[qq] = l0 ? __ldcg(psrc + (size_t)g0 * ST_P + 4 * qq + j) : 0.0;
+            pa1[qq] = l1 ? __ldcg(psrc + (size_t)g1 * ST_P + 4 * qq + j) : 0.0;
           }
         }
 #ifdef OB200_TIMELINE_BUILD
@@ -479,7 +510,8 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     cur = __shfl_sync(0xffffffffu, cur, 0);
     if (cur >= s_lo && lane == 0) {
       fence_proxy_async_smem();
-      strip_fetch(slot, &s_bmb[warp], cur, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
+      if (MODE == 1) strip_fetch_wy(slot, &s_bmb[warp], cur, n_rows32, a.Hp, st.Y);
+      else strip_fetch(slot, &s_bmb[warp], cur, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
     }
     {
       const u64 flag = rvw.load(ACC_FLAG_OFF);
@@ -523,7 +555,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
         exit_reason = -3;
         break;
       }
-      if (warp == 0) {
+      if (MODE == 0 && warp == 0) {
         // lanes 0..2 evaluate the long-latency operations concurrently, lane 0 takes the decisions
         double nG2 = 0.0;
 #pragma unroll
@@ -547,6 +579,49 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     ++phase;
     TLB(1);
     const double step = sh.step;
+    if (MODE == 1) {
+      // ---- stand-alone HVP, second phase: out = W - Y sym(G), strips as in phase B ----
+      while (cur >= s_lo) {
+        const int sidx = cur;
+        int nxt = 0;
+        if (lane == 0) nxt = atomicSub(&s_next_strip, 1);
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        const unsigned grow = (unsigned)sidx * 8u + m;
+        const bool valid = grow < n_rows32;
+        mbar_wait(&s_bmb[warp], bpar);
+        bpar ^= 1;
+        double acc[4][2];
+        double2 yx[4];
+        const double *tW = reinterpret_cast<const double *>(slot) + m * ST_P, *tY = tW + 4 * 8 * ST_P;
+        unsigned tok = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (valid) {
+            const double2 w = *reinterpret_cast<const double2 *>(tW + 8 * t + 2 * j);
+            acc[t][0] = w.x; acc[t][1] = w.y;
+            yx[t] = *reinterpret_cast<const double2 *>(tY + 8 * j + 2 * t);
+          } else {
+            acc[t][0] = acc[t][1] = 0.0;
+            yx[t] = make_double2(0.0, 0.0);
+          }
+          tok |= __double2hiint(acc[t][0]) | __double2hiint(yx[t].x);
+        }
+        tok = __reduce_or_sync(0xffffffffu, tok);
+        if (nxt >= s_lo && lane == 0 && (tok | 1u)) {
+          fence_proxy_async_smem();
+          strip_fetch_wy(slot, &s_bmb[warp], nxt, n_rows32, a.Hp, st.Y);
+        }
+        strip_rightmul_v(yx, Gsm, lane, acc);
+        if (valid) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            stcg2(a.s + (size_t)grow * ST_P + 8 * t + 2 * j, make_double2(acc[t][0], acc[t][1]));
+        }
+        cur = nxt;
+      }
+      exit_reason = 0;
+      break;
+    }
     if (sh.action != ACT_CONTINUE) {
       if (cur >= s_lo) mbar_wait(&s_bmb[warp], bpar);      // drain the outstanding fetch before leaving
       const size_t e0 = (size_t)row_lo * ST_P, e1 = (size_t)row_hi * ST_P;
@@ -688,10 +763,14 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
 
 cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
-                                  const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm) {
+                                  const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm,
+                                  int hvp_mode, const unsigned long long *planes_sum_dev,
+                                  unsigned long long planes_sum_expected) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tcg_stiefel_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(tcg_stiefel_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_TOTAL);
+    if (e) return e;
+    e = cudaFuncSetAttribute(tcg_stiefel_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_TOTAL);
     if (e) return e;
     attr = true;
   }
@@ -699,9 +778,11 @@ cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows,
   StiefelArgs sa{n_rows, A, Y, S_dev, op_norm_bound};
   const unsigned char *pl = planes;
   const int *pe = plane_exp;
-  void *args[] = {(void *)&ac, (void *)&sa, (void *)&pl, (void *)&pe};
-  return cudaLaunchCooperativeKernel((const void *)tcg_stiefel_tc_kernel, dim3(grid), dim3(V3_THREADS), args,
-                                     V3_TOTAL, stm);
+  const unsigned long long *sd = planes_sum_dev;
+  unsigned long long se = planes_sum_expected;
+  void *args[] = {(void *)&ac, (void *)&sa, (void *)&pl, (void *)&pe, (void *)&sd, (void *)&se};
+  const void *fn = hvp_mode ? (const void *)tcg_stiefel_tc_kernel<1> : (const void *)tcg_stiefel_tc_kernel<0>;
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(V3_THREADS), args, V3_TOTAL, stm);
 }
 
 }  // namespace ob200

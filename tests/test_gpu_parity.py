@@ -259,7 +259,7 @@ def test_stiefel_full_size_vs_reference(ctx, build_oracle, which):
         else:
             s_ref, mn_ref, it_ref, _ = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
         out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
-        assert ctx.last_path == "tcgen05"
+        assert ctx.last_path.startswith("tcgen05")
         assert out.num_iterations == it_ref
         assert rel(out.s.cpu().numpy(), s_ref) < RTOL
         assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
@@ -331,9 +331,34 @@ def test_planes_cache_follows_the_matrix(ctx, port):
         H = ctx.stiefel_operator(A, Y)
         out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
         s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
-        assert ctx.last_path == "tcgen05"
+        assert ctx.last_path.startswith("tcgen05")
         assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
         assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+    # the stand-alone HVP validates its planes on the device: rewrite A again and call it FIRST
+    A.copy_(torch.from_numpy(p2.A_bf16.astype(np.int16)))
+    H2 = ctx.stiefel_operator(A, ctx.to_device(p2.Y0))
+    hv = ctx.hvp(H2, ctx.to_device(p2.g)).cpu().numpy()
+    assert rel(hv, P.stiefel_hess_numpy(p2, p2.Y0, p2.g)) < 1e-12
+
+
+@pytest.mark.parametrize("n", [64, 128, 300, 1000, 20000])
+def test_stiefel_hvp_fused_vs_numpy(ctx, n):
+    """ob200_hvp for the Stiefel operator: ONE persistent launch (contraction + Gram | projection), against the dense
+    numpy Hessian and against the fp64 tensor-core path (ob200_set_option('tcgen05', 0))."""
+    for prob in (P.make_stiefel(n, 32, y_noise=.2), P.make_stiefel_critical(n, 32)):
+        A, Y, H = stiefel_setup(ctx, prob)
+        V = ctx.to_device(prob.g)
+        hv = ctx.hvp(H, V).cpu().numpy()
+        want = P.stiefel_hess_numpy(prob, prob.Y0, prob.g)
+        assert rel(hv, want) < 1e-12
+        ctx.set_option("tcgen05", 0)
+        try:
+            hv0 = ctx.hvp(H, V).cpu().numpy()
+        finally:
+            ctx.set_option("tcgen05", 2)
+        assert rel(hv0, want) < 1e-12
+        z = ctx.hvp(H, ctx.to_device(np.zeros_like(prob.g))).cpu().numpy()
+        assert np.all(z == 0.0)
 
 
 # ---- sphere Rayleigh-quotient Hessian, A = diag + low rank (configs C1 / C2) ------------------
@@ -436,14 +461,17 @@ def test_stiefel_fp64_mma_path_vs_oracle(ctx, port, n):
     kw = dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.)
     s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
     o_tc = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+    assert ctx.last_path == "tcgen05_v4"
+    ctx.set_option("tcgen05", 1)            # the warp-specialised generation of the kernel (kept as an option)
+    o_v5 = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
     assert ctx.last_path == "tcgen05"
     ctx.set_option("tcgen05", 0)
     try:
         o_mm = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
         assert ctx.last_path == "dmma"
     finally:
-        ctx.set_option("tcgen05", 1)
-    for o in (o_tc, o_mm):
+        ctx.set_option("tcgen05", 2)
+    for o in (o_tc, o_v5, o_mm):
         assert (o.num_iterations, o.exit_reason) == (it_ref, why_ref)
         assert rel(o.s.cpu().numpy(), s_ref) < RTOL
         assert abs(o.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
