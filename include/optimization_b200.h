@@ -102,6 +102,13 @@ int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A_bf
                                         A block-diagonal dense (bf16 storage), p == 32  */
 #define OB200_OP_SPHERE_LOWRANK 3   /* H v = 2 P_x(A v) - 2 (x^T A x) v, P_x(z) = z - x (x^T z),
                                         A = diag(d) + U diag(sigma) U^T, k <= 16, p == 1 */
+#define OB200_OP_BLOCK_CSR3 4       /* rotation synchronisation on SO(3)^N relaxed to St(3,r)^N (SE-Sync's Hessian shape,
+                                        BASELINE config C5): X (= Y_dev) is 3N x r row-major, pose i = rows 3i..3i+2 with
+                                        X_i X_i^T = I_3;  H V = Proj_X(2 Q V - Lambda V), Proj_X(Z)_i = Z_i - sym(Z_i X_i^T) X_i,
+                                        Q symmetric with 3 x 3 blocks in block-CSR, Lambda_i = sym((2 Q X)_i X_i^T)
+                                        (ob200_csr3_model fills it); n == 3 N, 3 <= p == r <= 8 */
+#define OB200_OP_STENCIL7 5         /* H V = 7-point Dirichlet Laplacian on a gx x gy x gz grid (x fastest) applied to each
+                                        of the p columns of V; n == gx gy gz (BASELINE config C4's operator as a Hessian) */
 
 typedef struct {
   int kind;
@@ -122,6 +129,14 @@ typedef struct {
   double xAx;              /* x^T A x   (ob200_sphere_model returns it) */
   const double *Ax_dev;    /* n, A x    (ob200_sphere_model fills it)   */
   uint64_t ldu;            /* row stride of U_dev in doubles: even and >= n; 0 means n (n must then be even) */
+  /* OB200_OP_BLOCK_CSR3 (X in Y_dev) */
+  const uint64_t *csr_rowptr_dev; /* N + 1 */
+  const uint32_t *csr_colidx_dev; /* nnz block columns (pose indices), ascending within a row */
+  const double *csr_blocks_dev;   /* nnz x 9, row-major 3 x 3 */
+  const double *csr_lambda_dev;   /* N x 9 */
+  uint64_t csr_nnz;               /* number of stored 3 x 3 blocks (for the byte counts) */
+  /* OB200_OP_STENCIL7 */
+  uint32_t gx, gy, gz;
 } ob200_operator;
 
 /* Replaces the optional preconditioner functor (reference
@@ -177,7 +192,8 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v_dev, 
  * operator (the roofline numerator; definition in DESIGN.md section 4):
  *   step = 10 N e + B_op (+ 2 N e with Jacobi),  hvp = 2 N e + B_op,  e = 8;
  *   B_op: DIAG N e; STIEFEL_BLOCKDIAG 2 N e (Y twice) + 2 bytes per stored entry of A;
- *   SPHERE_LOWRANK (2k + 4) N e (U twice, d, x, A x, p re-read by the second pass). */
+ *   SPHERE_LOWRANK (2k + 4) N e (U twice, d, x, A x, p re-read by the second pass);
+ *   BLOCK_CSR3 N e (p re-read by the operator pass) + nnz (72 + 4) + N_poses (8 + 72) + N e (X); STENCIL7 N e. */
 uint64_t ob200_stpcg_step_bytes(const ob200_operator *H, const ob200_precon *P);
 uint64_t ob200_hvp_bytes(const ob200_operator *H);
 
@@ -213,6 +229,16 @@ int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16
 /* Cholesky-QR retraction  out = qf(Y + V) */
 int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y_dev,
                           const double *V_dev, double *out_dev);
+
+/* ---- rotation synchronisation f(X) = tr(X^T Q X) on St(3,r)^N (BASELINE config C5) -----------------------------
+ * Replace the Objective / QuadraticModel / Retraction functors of that model (reference call sites TNT.h:377,380,505,
+ * 508,573).  ob200_csr3_model: lambda_dev <- Lambda (N x 9, the `csr_lambda_dev` field of the Hessian descriptor),
+ * *f <- f(X), optional grad_dev <- (2 Q X) - Lambda X.  ob200_csr3_retract: out_i = rows of X_i + V_i re-orthonormalised
+ * (Gram-Schmidt in row order = Q factor of the QR decomposition of (X_i + V_i)^T). */
+int ob200_csr3_model(ob200_context *ctx, uint64_t N, uint64_t r, const uint64_t *rowptr_dev, const uint32_t *colidx_dev,
+                     const double *blocks_dev, const double *X_dev, double *lambda_dev, double *f, double *grad_dev);
+int ob200_csr3_retract(ob200_context *ctx, uint64_t N, uint64_t r, const double *X_dev, const double *V_dev,
+                       double *out_dev);
 
 /* ---- Rayleigh quotient on the sphere, f(x) = x^T A x, A = diag(d) + U diag(sigma) U^T ----
  * Replace the Objective / QuadraticModel / Retraction functors of the sphere model

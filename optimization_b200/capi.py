@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("OB200_LIB") or os.path.join(_HERE, "liboptimization_b
 OK, INVALID_ARGUMENT, CUDA_ERROR, UNSUPPORTED, NUMERIC_RANGE, ABORTED = range(6)
 EXIT_RESIDUAL, EXIT_MAX_ITERATIONS, EXIT_KERNEL, EXIT_BOUNDARY = range(4)
 EXIT_NAMES = {0: "residual", 1: "max_iterations", 2: "kernel", 3: "boundary"}
-OP_DIAG, OP_STIEFEL_BLOCKDIAG, OP_SPHERE_LOWRANK = 1, 2, 3
+OP_DIAG, OP_STIEFEL_BLOCKDIAG, OP_SPHERE_LOWRANK, OP_BLOCK_CSR3, OP_STENCIL7 = 1, 2, 3, 4, 5
 PRECON_NONE, PRECON_JACOBI = 0, 1
 
 # every symbol include/optimization_b200.h declares (checked by the CPU test-suite)
@@ -31,7 +31,7 @@ EXPORTS = [
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
-    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path", "ob200_div",
+    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path", "ob200_div", "ob200_csr3_model", "ob200_csr3_retract",
 ]
 
 
@@ -40,7 +40,10 @@ class Operator(C.Structure):
                 ("diag_dev", C.c_void_p), ("A_bf16_dev", C.c_void_p), ("Y_dev", C.c_void_p),
                 ("S_host", C.c_void_p), ("op_norm_bound", C.c_double), ("x_dev", C.c_void_p),
                 ("U_dev", C.c_void_p), ("sigma_host", C.c_void_p), ("k", C.c_uint64),
-                ("xAx", C.c_double), ("Ax_dev", C.c_void_p), ("ldu", C.c_uint64)]
+                ("xAx", C.c_double), ("Ax_dev", C.c_void_p), ("ldu", C.c_uint64),
+                ("csr_rowptr_dev", C.c_void_p), ("csr_colidx_dev", C.c_void_p), ("csr_blocks_dev", C.c_void_p),
+                ("csr_lambda_dev", C.c_void_p), ("csr_nnz", C.c_uint64), ("gx", C.c_uint32), ("gy", C.c_uint32),
+                ("gz", C.c_uint32)]
 
 
 class BlockOperator(C.Structure):
@@ -122,6 +125,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_stiefel_retract.argtypes = [vp, u64, u64, vp, vp, vp]
     lib.ob200_sphere_model.argtypes = [vp, u64, u64, vp, vp, u64, vp, vp, vp, C.POINTER(dbl), vp]
     lib.ob200_sphere_retract.argtypes = [vp, u64, vp, vp, vp]
+    lib.ob200_csr3_model.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp, C.POINTER(dbl), vp]
+    lib.ob200_csr3_retract.argtypes = [vp, u64, u64, vp, vp, vp]
     bo = C.POINTER(BlockOperator)
     lib.ob200_lobpcg.argtypes = [vp, bo, bo, bo, u64, u64, vp, u64, u64, dbl, vp, C.POINTER(dbl), C.POINTER(u64),
                                  C.POINTER(u64)]

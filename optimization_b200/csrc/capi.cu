@@ -57,6 +57,22 @@ cudaError_t launch_sphere_apply(unsigned long long N, const double *d, const dou
                                 const double *st_dev, const double *v, double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_sphere_combine(unsigned long long N, const double *Av, const double *x, const double *v, double c,
                                   double lambda, double *out, int sm_count, cudaStream_t st);
+struct SparseArgs {
+  int kind;
+  int r;
+  unsigned long long units;
+  const unsigned long long *rowptr;
+  const unsigned *colidx;
+  const double *blocks, *lambda, *X;
+  unsigned gx, gy, gz;
+};
+cudaError_t launch_tcg_sparse(const TcgCommon &a, const SparseArgs &sp, int sm_count, cudaStream_t st);
+cudaError_t launch_sparse_apply(unsigned long long N, const SparseArgs &sp, const double *V, double *out, int sm_count,
+                                cudaStream_t st);
+cudaError_t launch_csr3_model(const SparseArgs &sp, const double *X, double *lambda_out, double *grad, u64 *set,
+                              int sm_count, cudaStream_t st);
+cudaError_t launch_csr3_retract(unsigned long long N, int r, const double *X, const double *V, double *out, int *bad,
+                                cudaStream_t st);
 cudaError_t launch_blk_diag(unsigned long long m, int k, const double *d, double alpha, const double *in, int ldi, double *out,
                             int ldo, int sm_count, cudaStream_t st);
 cudaError_t launch_blk_stencil7(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
@@ -529,6 +545,31 @@ static int sphere_Av(ob200_context *ctx, uint64_t n, uint64_t k, const double *d
   return OB200_OK;
 }
 
+static int sparse_args(ob200_context *ctx, const ob200_operator *H, SparseArgs *sp) {
+  memset(sp, 0, sizeof(*sp));
+  sp->kind = H->kind;
+  sp->r = (int)H->p;
+  if (H->kind == OB200_OP_BLOCK_CSR3) {
+    if (H->p < 3 || H->p > 8) return fail(ctx, OB200_UNSUPPORTED, "block-CSR operator requires 3 <= p = r <= 8");
+    if (H->n % 3) return fail(ctx, OB200_INVALID_ARGUMENT, "block-CSR operator: n must be 3 x (number of poses)");
+    if (!H->csr_rowptr_dev || !H->csr_colidx_dev || !H->csr_blocks_dev || !H->csr_lambda_dev || !H->Y_dev)
+      return fail(ctx, OB200_INVALID_ARGUMENT, "incomplete block-CSR operator");
+    sp->units = H->n / 3;
+    sp->rowptr = reinterpret_cast<const unsigned long long *>(H->csr_rowptr_dev);
+    sp->colidx = H->csr_colidx_dev;
+    sp->blocks = H->csr_blocks_dev;
+    sp->lambda = H->csr_lambda_dev;
+    sp->X = H->Y_dev;
+  } else {
+    if (!H->gx || !H->gy || !H->gz || (uint64_t)H->gx * H->gy * H->gz != H->n)
+      return fail(ctx, OB200_INVALID_ARGUMENT, "stencil operator: gx gy gz must equal n");
+    if (H->p > 0xffffu) return fail(ctx, OB200_UNSUPPORTED, "stencil operator: too many columns");
+    sp->units = H->n;
+    sp->gx = H->gx; sp->gy = H->gy; sp->gz = H->gz;
+  }
+  return OB200_OK;
+}
+
 static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
                         const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
   int rc = check_params(ctx, prm);
@@ -552,6 +593,10 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     if (!H->diag_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "diag operator without diagonal");
   } else if (H->kind == OB200_OP_SPHERE_LOWRANK) {
     if ((rc = check_sphere(ctx, H))) return rc;
+  } else if (H->kind == OB200_OP_BLOCK_CSR3 || H->kind == OB200_OP_STENCIL7) {
+    SparseArgs chk;
+    if ((rc = sparse_args(ctx, H, &chk))) return rc;
+    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "sparse operators are single-GPU in this version (no halo exchange yet)");
   } else {
     return fail(ctx, OB200_UNSUPPORTED, "operator kind not supported by the fused tCG path");
   }
@@ -628,6 +673,10 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   } else if (H->kind == OB200_OP_SPHERE_LOWRANK) {
     CK(launch_tcg_sphere(a, H->diag_dev, H->U_dev, H->ldu ? H->ldu : H->n, H->x_dev, H->Ax_dev, H->sigma_host,
                          (int)H->k, H->xAx, ctx->sm_count, st));
+  } else if (H->kind == OB200_OP_BLOCK_CSR3 || H->kind == OB200_OP_STENCIL7) {
+    SparseArgs sp;
+    if ((rc = sparse_args(ctx, H, &sp))) return rc;
+    CK(launch_tcg_sparse(a, sp, ctx->sm_count, st));
   } else {
     const unsigned long long nblk = (H->n + 127) / 128;
     int grid = ctx->sm_count;
@@ -691,6 +740,9 @@ static uint64_t op_bytes(const ob200_operator *H) {
     case OB200_OP_STIEFEL_BLOCKDIAG:                                    // A (bf16) + Y read twice
       return ((H->n + 127) / 128) * 128 * 128 * 2 + 2 * 8 * N;
     case OB200_OP_SPHERE_LOWRANK: return 8 * H->n * (4 + 2 * H->k);     // U twice, d, x, w = A x, p re-read
+    case OB200_OP_BLOCK_CSR3:                                           // p re-read + X; blocks + indices; row pointer + Lambda
+      return 2 * 8 * N + H->csr_nnz * (72 + 4) + (H->n / 3) * (8 + 72);
+    case OB200_OP_STENCIL7: return 8 * N;                               // p re-read by the operator pass
     default: return 0;
   }
 }
@@ -833,6 +885,15 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
     CK(cudaStreamSynchronize(st));
     return OB200_OK;
   }
+  if (H->kind == OB200_OP_BLOCK_CSR3 || H->kind == OB200_OP_STENCIL7) {
+    SparseArgs sp;
+    int rc = sparse_args(ctx, H, &sp);
+    if (rc) return rc;
+    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "sparse operators are single-GPU in this version");
+    CK(launch_sparse_apply(N, sp, v, out, ctx->sm_count, st));
+    ctx->launches += 1;
+    return OB200_OK;
+  }
   if (H->kind != OB200_OP_STIEFEL_BLOCKDIAG || H->p != 32) return fail(ctx, OB200_UNSUPPORTED, "operator kind");
   if (!H->A_bf16_dev || !H->Y_dev || !H->S_host) return fail(ctx, OB200_INVALID_ARGUMENT, "incomplete Stiefel operator");
   int rc = ensure_vectors(ctx, N);
@@ -910,6 +971,47 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
   CK(launch_stiefel_rowgemm(H->n, ctx->Hp, 1.0, H->Y_dev, ctx->dmat + 1024, out, grid, st));
   ctx->launches += 1;
   CK(cudaStreamSynchronize(st));
+  return OB200_OK;
+}
+
+int ob200_csr3_model(ob200_context *ctx, uint64_t N, uint64_t r, const uint64_t *rowptr, const uint32_t *colidx,
+                     const double *blocks, const double *X, double *lambda_dev, double *f, double *grad_dev) {
+  if (!ctx || !rowptr || !colidx || !blocks || !X || !lambda_dev) return OB200_INVALID_ARGUMENT;
+  if (r < 3 || r > 8) return fail(ctx, OB200_UNSUPPORTED, "rotation-synchronisation model requires 3 <= r <= 8");
+  if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "sparse operators are single-GPU in this version");
+  CK(cudaSetDevice(ctx->device));
+  SparseArgs sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.kind = OB200_OP_BLOCK_CSR3;
+  sp.r = (int)r;
+  sp.units = N;
+  sp.rowptr = reinterpret_cast<const unsigned long long *>(rowptr);
+  sp.colidx = colidx;
+  sp.blocks = blocks;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SCAL_WORDS, st));
+  CK(launch_csr3_model(sp, X, lambda_dev, grad_dev, ctx->acc, ctx->sm_count, st));
+  CK(launch_finalize_many(ctx->acc, 1, ctx->dscal, st));
+  ctx->launches += 2;
+  CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (f) *f = ctx->hscal[0];
+  return OB200_OK;
+}
+
+int ob200_csr3_retract(ob200_context *ctx, uint64_t N, uint64_t r, const double *X, const double *V, double *out) {
+  if (!ctx || !X || !V || !out) return OB200_INVALID_ARGUMENT;
+  if (r < 3 || r > 8) return fail(ctx, OB200_UNSUPPORTED, "retraction on St(3,r)^N requires 3 <= r <= 8");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int *bad_dev = reinterpret_cast<int *>(ctx->dbits);
+  CK(cudaMemsetAsync(bad_dev, 0, sizeof(int), st));
+  CK(launch_csr3_retract(N, (int)r, X, V, out, bad_dev, st));
+  ctx->launches += 1;
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (bad) return fail(ctx, OB200_NUMERIC_RANGE, "retraction: a pose block X_i + V_i is rank deficient or not finite");
   return OB200_OK;
 }
 

@@ -61,6 +61,9 @@ class Context:
             raise capi.Ob200Error(rc, "ob200_create failed (no usable GPU?)")
         self.h = h
         self._keep = []
+        import os
+        if os.environ.get("OB200_TCGEN05"):      # developer override: which Stiefel kernel generation to run (see set_option)
+            self.set_option("tcgen05", int(os.environ["OB200_TCGEN05"]))
 
     def close(self):
         if getattr(self, "h", None):
@@ -177,6 +180,45 @@ class Context:
         h = OperatorHandle(self, op, [d, Ut, sigma, x, Ax])
         h.f, h.Ut, h.Ax = f, Ut, Ax
         return h
+
+    def csr3_model(self, rowptr, colidx, blocks, X, want_grad=True):
+        """(Lambda [N x 9], f = tr(X^T Q X), Riemannian gradient) of the rotation-synchronisation cost on the device."""
+        N, r = X.shape[0] // 3, X.shape[1]
+        lam = torch.empty((N, 9), dtype=torch.float64, device=X.device)
+        grad = torch.empty_like(X) if want_grad else None
+        f = C.c_double(0)
+        self._check(self.lib.ob200_csr3_model(self.h, N, r, _ptr(rowptr), _ptr(colidx), _ptr(blocks), _ptr(X), _ptr(lam),
+                                              C.byref(f), _ptr(grad)))
+        return lam, f.value, grad
+
+    def csr3_retract(self, X, V, out=None):
+        if out is None:
+            out = torch.empty_like(X)
+        self._check(self.lib.ob200_csr3_retract(self.h, X.shape[0] // 3, X.shape[1], _ptr(X), _ptr(V), _ptr(out)))
+        return out
+
+    def csr3_operator(self, rowptr, colidx, blocks, X) -> "OperatorHandle":
+        """Hess f(X)[V] = Proj_X(2 Q V - Lambda V) on St(3, r)^N (BASELINE config C5).  rowptr: int64/uint64 [N + 1],
+        colidx: int32/uint32 [nnz], blocks: float64 [nnz, 9], X: float64 [3N, r] (all on the device)."""
+        lam, f, _ = self.csr3_model(rowptr, colidx, blocks, X, want_grad=False)
+        op = capi.Operator()
+        op.kind = capi.OP_BLOCK_CSR3
+        op.n, op.p = X.shape
+        op.Y_dev = X.data_ptr()
+        op.csr_rowptr_dev, op.csr_colidx_dev = rowptr.data_ptr(), colidx.data_ptr()
+        op.csr_blocks_dev, op.csr_lambda_dev = blocks.data_ptr(), lam.data_ptr()
+        op.csr_nnz = int(colidx.numel())
+        h = OperatorHandle(self, op, [rowptr, colidx, blocks, X, lam])
+        h.f, h.Lambda, h.nnz = f, lam, int(colidx.numel())
+        return h
+
+    def stencil7_operator(self, gx: int, gy: int, gz: int, p: int) -> "OperatorHandle":
+        """H V = 7-point Dirichlet Laplacian on the gx x gy x gz grid applied to the p columns of V (n = gx gy gz)."""
+        op = capi.Operator()
+        op.kind = capi.OP_STENCIL7
+        op.n, op.p = gx * gy * gz, p
+        op.gx, op.gy, op.gz = gx, gy, gz
+        return OperatorHandle(self, op, [])
 
     def sphere_model(self, d, Ut, sigma, x, want_grad=True):
         """(A x, f = x^T A x, grad = 2 (A x - f x)) on the device."""

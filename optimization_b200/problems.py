@@ -364,3 +364,113 @@ def make_diag(n: int, seed: int = 5, lo: float = 1000.0, hi: float = 3000.0) -> 
     h = lo + (hi - lo) * uniform01(seed + 1, 0, n)
     m = lo + (hi - lo) * uniform01(seed + 2, 0, n)
     return DiagProblem(n, g, h, 1.0 / m)
+
+
+# ---- BASELINE config C5: rotation synchronisation on SO(3)^N (SE-Sync's relaxation) ----------------------------
+@dataclasses.dataclass
+class PoseGraphProblem:
+    """min tr(X^T Q X) over X in St(3, r)^N (row-major 3N x r, pose i = rows 3i..3i+2, X_i X_i^T = I_3);
+    Q = connection Laplacian of the rotation graph in block-CSR with 3 x 3 blocks (symmetric)."""
+    N: int
+    r: int
+    rowptr: np.ndarray      # (N+1,) uint64
+    colidx: np.ndarray      # (nnz,) uint32, sorted within a row
+    blocks: np.ndarray      # (nnz, 9) float64, row-major 3 x 3
+    X0: np.ndarray          # (3N, r)
+    g: np.ndarray           # (3N, r) tangent at X0 (right-hand side of stand-alone tCG runs)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.colidx.size)
+
+
+def _rot_from_axis_angle(w: np.ndarray) -> np.ndarray:
+    """Rodrigues: (m, 3) rotation vectors -> (m, 3, 3) rotation matrices."""
+    th = np.linalg.norm(w, axis=1)
+    k = w / np.maximum(th, 1e-300)[:, None]
+    K = np.zeros((w.shape[0], 3, 3))
+    K[:, 0, 1], K[:, 0, 2] = -k[:, 2], k[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = k[:, 2], -k[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -k[:, 1], k[:, 0]
+    s, c = np.sin(th)[:, None, None], np.cos(th)[:, None, None]
+    return np.eye(3)[None] + s * K + (1.0 - c) * (K @ K)
+
+
+def _tangent_project_poses(X: np.ndarray, Z: np.ndarray, r: int) -> np.ndarray:
+    """Proj_X(Z)_i = Z_i - sym(Z_i X_i^T) X_i for every pose."""
+    N = X.shape[0] // 3
+    Xb, Zb = X.reshape(N, 3, r), Z.reshape(N, 3, r)
+    M = Zb @ Xb.transpose(0, 2, 1)
+    S = 0.5 * (M + M.transpose(0, 2, 1))
+    return (Zb - S @ Xb).reshape(3 * N, r)
+
+
+def make_posegraph(dims=(10, 10, 10), r: int = 4, seed: int = 41, sigma: float = 0.05, x_noise: float = 0.1,
+                   closures: int = 1) -> PoseGraphProblem:
+    """Synthetic pose graph: poses on a gx x gy x gz grid (x fastest) with odometry edges to the
+    +x, +y, +z neighbours and `closures` random loop closures per pose; relative rotations measured with isotropic
+    noise of `sigma` radians, unit weights.  sigma = 0 gives consistent measurements: the ground truth is then an exact
+    minimiser (f = 0, Lambda = 0) and the Hessian is positive semidefinite -- the stand-alone tCG throughput workload
+    (x_noise = 0 to start there).  X0 = ground truth perturbed by rotations of x_noise radians, embedded in r columns."""
+    gx, gy, gz = dims
+    N = gx * gy * gz
+    idx = np.arange(N, dtype=np.int64)
+    x, y, z = idx % gx, (idx // gx) % gy, idx // (gx * gy)
+    ei, ej = [], []
+    for cond, step in ((x + 1 < gx, 1), (y + 1 < gy, gx), (z + 1 < gz, gx * gy)):
+        ei.append(idx[cond]); ej.append(idx[cond] + step)
+    for c in range(closures):
+        tgt = (splitmix64(seed + 3 + c, idx.astype(np.uint64)) % np.uint64(N)).astype(np.int64)
+        keep = tgt != idx
+        ei.append(idx[keep]); ej.append(tgt[keep])
+    ei, ej = np.concatenate(ei), np.concatenate(ej)
+    m = ei.size
+    Rgt = _rot_from_axis_angle(2.0 * gaussish(seed, 0, 3 * N).reshape(N, 3))                 # ground-truth rotations
+    noise = _rot_from_axis_angle(sigma * gaussish(seed + 1, 0, 3 * m).reshape(m, 3)) if sigma > 0 else np.eye(3)[None]
+    Rij = Rgt[ei].transpose(0, 2, 1) @ Rgt[ej] @ noise                                      # measured R_i^T R_j
+    # COO assembly: Q_ii += I, Q_jj += I, Q_ij -= R_ij, Q_ji -= R_ij^T
+    rows = np.concatenate([ei, ej, ei, ej])
+    cols = np.concatenate([ei, ej, ej, ei])
+    eye = np.broadcast_to(np.eye(3), (m, 3, 3))
+    vals = np.concatenate([eye, eye, -Rij, -Rij.transpose(0, 2, 1)]).reshape(-1, 9)
+    key = rows * N + cols
+    order = np.argsort(key, kind="stable")
+    key, vals = key[order], vals[order]
+    first = np.concatenate([[True], key[1:] != key[:-1]])
+    starts = np.flatnonzero(first)
+    blocks = np.add.reduceat(vals, starts, axis=0)
+    ukey = key[starts]
+    urow, ucol = ukey // N, ukey % N
+    rowptr = np.zeros(N + 1, dtype=np.uint64)
+    np.add.at(rowptr, urow + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.uint64)
+    # X0: rows of (R_gt * Exp(x_noise))^T in the first three columns, small fill in the others, rows re-orthonormalised
+    Rp = Rgt @ _rot_from_axis_angle(x_noise * gaussish(seed + 2, 0, 3 * N).reshape(N, 3)) if x_noise > 0 else Rgt
+    Xb = np.zeros((N, 3, r))
+    Xb[:, :, :3] = Rp.transpose(0, 2, 1)
+    if r > 3 and x_noise > 0:
+        Xb[:, :, 3:] = 0.1 * x_noise * gaussish(seed + 4, 0, 3 * N * (r - 3)).reshape(N, 3, r - 3)
+    for a in range(3):                                                                       # Gram-Schmidt on the 3 rows
+        for b in range(a):
+            Xb[:, a] -= np.sum(Xb[:, a] * Xb[:, b], axis=1)[:, None] * Xb[:, b]
+        Xb[:, a] /= np.linalg.norm(Xb[:, a], axis=1)[:, None]
+    X0 = np.ascontiguousarray(Xb.reshape(3 * N, r))
+    g = _tangent_project_poses(X0, gaussish(seed + 5, 0, 3 * N * r).reshape(3 * N, r), r)
+    return PoseGraphProblem(N, r, rowptr, ucol.astype(np.uint32), np.ascontiguousarray(blocks), X0,
+                            np.ascontiguousarray(g))
+
+
+def posegraph_hess_numpy(prob: PoseGraphProblem, X: np.ndarray, V: np.ndarray):
+    """Dense-free numpy Hess f(X)[V] = Proj_X(2 Q V - Lambda V), Lambda_i = sym(G_i X_i^T), G = 2 Q X (small N only).
+    Returns (HV, Lambda (N, 3, 3), f, grad)."""
+    import scipy.sparse as sp
+    N, r = prob.N, prob.r
+    Q = sp.bsr_matrix((prob.blocks.reshape(-1, 3, 3), prob.colidx.astype(np.int64), prob.rowptr.astype(np.int64)),
+                      shape=(3 * N, 3 * N)).tocsr()
+    G = 2.0 * (Q @ X)
+    M = G.reshape(N, 3, r) @ X.reshape(N, 3, r).transpose(0, 2, 1)
+    L = 0.5 * (M + M.transpose(0, 2, 1))
+    f = 0.5 * float(np.sum(X * G))
+    grad = G - (L @ X.reshape(N, 3, r)).reshape(3 * N, r)
+    W = 2.0 * (Q @ V) - (L @ V.reshape(N, 3, r)).reshape(3 * N, r)
+    return _tangent_project_poses(X, W, r), L, f, grad

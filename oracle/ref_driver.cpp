@@ -316,6 +316,50 @@ Riemannian::TNTParams<double> make_params(const double *prm) {
 
 } // namespace
 
+// ---- STPCG over an operator given as a plain C callback (sparse Hessian families of configs C5 / C4) -------------
+// The reference's STPCG (IterativeSolvers.h:166-426) with HostMat vectors; the Hessian functor calls the shared
+// C restatement of the operator (oracle/sparse_ops.h), the preconditioner is the optional pointwise Jacobi scaling.
+extern "C" {
+#include "sparse_ops.h"
+}
+namespace {
+template <class Apply>
+int ref_stpcg_callback(uint64_t n, const double *g, const double *minv, Apply apply, double Delta,
+                       uint64_t max_iterations, double kappa_fgr, double theta, double epsilon, double *s_out,
+                       double *update_step_M_norm, uint64_t *num_iterations) {
+  using V = HostMat;
+  using M = std::nullptr_t;
+  V G(g, n);
+  LinearAlgebra::SymmetricLinearOperator<V> H = [&](const V &x) {
+    V out(n);
+    apply(x.data(), out.data());
+    return out;
+  };
+  LinearAlgebra::InnerProduct<V> ip = [](const V &a, const V &b) { return oracle::dot(a, b); };
+  std::optional<LinearAlgebra::STPCGPreconditioner<V, M>> P;
+  if (minv)
+    P = [&](const V &x) {
+      V out(n);
+      const double *xd = x.data();
+      double *o = out.data();
+      for (size_t i = 0; i < n; ++i) o[i] = minv[i] * xd[i];
+      return std::make_pair(std::move(out), M());
+    };
+  try {
+    size_t iters = 0;
+    double mnorm = 0;
+    V s = LinearAlgebra::STPCG<V, M>(G, H, ip, mnorm, iters, Delta, size_t(max_iterations), kappa_fgr, theta, P,
+                                     NoAt(), NoUser(), epsilon);
+    std::memcpy(s_out, s.data(), n * sizeof(double));
+    *update_step_M_norm = mnorm;
+    *num_iterations = iters;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 void ref_set_threads(int t) { oracle::threads() = t < 1 ? 1 : t; }
@@ -375,6 +419,22 @@ int ref_stpcg_diag(uint64_t n, const double *g, const double *hdiag,
     return 1;
   }
   return 0;
+}
+
+int ref_csr3_stpcg(uint64_t N, uint64_t r, const uint64_t *rowptr, const uint32_t *colidx,
+                              const double *blocks, const double *lambda, const double *X, const double *g,
+                              const double *minv, double Delta, uint64_t max_iterations, double kappa_fgr,
+                              double theta, double epsilon, double *s_out, double *mnorm, uint64_t *iters) {
+  return ref_stpcg_callback(3 * N * r, g, minv, [&](const double *v, double *out) {
+    csr3_hess_apply(N, int(r), rowptr, colidx, blocks, lambda, X, v, out);
+  }, Delta, max_iterations, kappa_fgr, theta, epsilon, s_out, mnorm, iters);
+}
+int ref_stencil7_stpcg(uint32_t gx, uint32_t gy, uint32_t gz, uint64_t p, const double *g,
+                                  const double *minv, double Delta, uint64_t max_iterations, double kappa_fgr,
+                                  double theta, double epsilon, double *s_out, double *mnorm, uint64_t *iters) {
+  return ref_stpcg_callback(uint64_t(gx) * gy * gz * p, g, minv, [&](const double *v, double *out) {
+    stencil7_apply(gx, gy, gz, int(p), v, out);
+  }, Delta, max_iterations, kappa_fgr, theta, epsilon, s_out, mnorm, iters);
 }
 
 // ---- Stiefel problem handle -------------------------------------------------

@@ -143,6 +143,34 @@ class RefOracle:
             raise ValueError("std::invalid_argument from reference STPCG")
         return s, float(mn.value), int(it.value)
 
+    def csr3_stpcg(self, prob, X, lam, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
+                   epsilon=1e-8):
+        """The reference's STPCG on the rotation-synchronisation Hessian (operator restated in oracle/sparse_ops.h)."""
+        L = self.lib
+        L.ref_csr3_stpcg.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double,
+                                     C.c_uint64, C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
+        s = np.zeros_like(g)
+        mn, it = C.c_double(0), C.c_uint64(0)
+        rc = L.ref_csr3_stpcg(prob.N, prob.r, prob.rowptr.ctypes.data, prob.colidx.ctypes.data, _d(prob.blocks), _d(lam),
+                              _d(X), _d(g), _d(minv), Delta, max_iterations, kappa_fgr, theta, epsilon, _d(s),
+                              C.byref(mn), C.byref(it))
+        if rc:
+            raise ValueError("std::invalid_argument from reference STPCG")
+        return s, float(mn.value), int(it.value)
+
+    def stencil7_stpcg(self, dims, p, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
+                       epsilon=1e-8):
+        L = self.lib
+        L.ref_stencil7_stpcg.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _dp, _dp, C.c_double, C.c_uint64,
+                                         C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
+        s = np.zeros_like(g)
+        mn, it = C.c_double(0), C.c_uint64(0)
+        rc = L.ref_stencil7_stpcg(dims[0], dims[1], dims[2], p, _d(g), _d(minv), Delta, max_iterations, kappa_fgr, theta,
+                                  epsilon, _d(s), C.byref(mn), C.byref(it))
+        if rc:
+            raise ValueError("std::invalid_argument from reference STPCG")
+        return s, float(mn.value), int(it.value)
+
     def sphere_tnt(self, prob, x0, params=None, cap=2048):
         p = params or default_tnt_params()
         tb = _TraceBufs(cap)
@@ -376,6 +404,59 @@ class PortOracle:
         rc = self.lib.port_stpcg_stiefel(prob.n, prob.p, prob.nb, _d(A), _d(Y), _d(g), _d(minv),
                                          Delta, max_iterations, kappa_fgr, theta, epsilon, _d(s),
                                          C.byref(mn), C.byref(it))
+        if rc < 0:
+            raise ValueError("invalid argument")
+        return s, float(mn.value), int(it.value), self.EXIT[rc]
+
+    # -- sparse Hessian families (configs C5 / C4) ------------------------------------------------------
+    def csr3_model(self, prob, X):
+        L = self.lib
+        L.port_csr3_model.restype = C.c_double
+        L.port_csr3_model.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp]
+        lam = np.zeros((prob.N, 9))
+        grad = np.zeros_like(X)
+        f = L.port_csr3_model(prob.N, prob.r, prob.rowptr.ctypes.data, prob.colidx.ctypes.data, _d(prob.blocks), _d(X),
+                              _d(lam), _d(grad))
+        return lam, float(f), grad
+
+    def csr3_hess(self, prob, X, lam, v):
+        L = self.lib
+        L.port_csr3_hess.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp, _dp]
+        out = np.zeros_like(v)
+        L.port_csr3_hess(prob.N, prob.r, prob.rowptr.ctypes.data, prob.colidx.ctypes.data, _d(prob.blocks), _d(lam),
+                         _d(X), _d(v), _d(out))
+        return out
+
+    def stpcg_csr3(self, prob, X, lam, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
+                   epsilon=1e-8):
+        L = self.lib
+        L.port_stpcg_csr3.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double,
+                                      C.c_uint64, C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
+        s = np.zeros_like(g)
+        mn, it = C.c_double(0), C.c_uint64(0)
+        rc = L.port_stpcg_csr3(prob.N, prob.r, prob.rowptr.ctypes.data, prob.colidx.ctypes.data, _d(prob.blocks), _d(lam),
+                               _d(X), _d(g), _d(minv), Delta, max_iterations, kappa_fgr, theta, epsilon, _d(s),
+                               C.byref(mn), C.byref(it))
+        if rc < 0:
+            raise ValueError("invalid argument")
+        return s, float(mn.value), int(it.value), self.EXIT[rc]
+
+    def stencil7_apply(self, dims, p, v):
+        L = self.lib
+        L.port_stencil7_apply.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _dp, _dp]
+        out = np.zeros_like(v)
+        L.port_stencil7_apply(dims[0], dims[1], dims[2], p, _d(v), _d(out))
+        return out
+
+    def stpcg_stencil7(self, dims, p, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
+                       epsilon=1e-8):
+        L = self.lib
+        L.port_stpcg_stencil7.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _dp, _dp, C.c_double, C.c_uint64,
+                                          C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
+        s = np.zeros_like(g)
+        mn, it = C.c_double(0), C.c_uint64(0)
+        rc = L.port_stpcg_stencil7(dims[0], dims[1], dims[2], p, _d(g), _d(minv), Delta, max_iterations, kappa_fgr, theta,
+                                   epsilon, _d(s), C.byref(mn), C.byref(it))
         if rc < 0:
             raise ValueError("invalid argument")
         return s, float(mn.value), int(it.value), self.EXIT[rc]

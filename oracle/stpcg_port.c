@@ -478,3 +478,52 @@ int port_s2_tnt(const double *x0, const double *Ppt, int use_precon, const doubl
   return port_tnt(&M, x0, prm, x_out, status, n_outer, n_trace, scalars, cap, inner_iterations,
                   radius, rho, fvals, gradnorms, step_norms, step_M_norms);
 }
+
+/* ---- sparse Hessian families (configs C5 / C4; operator definitions in sparse_ops.h) ------------------- */
+#include "sparse_ops.h"
+
+typedef struct {
+  uint64_t N; int r;
+  const uint64_t *rowptr; const uint32_t *colidx; const double *blocks, *lambda, *X;
+} port_csr3;
+static void csr3_apply_cb(void *c, const double *v, double *out) {
+  const port_csr3 *P = (const port_csr3 *)c;
+  csr3_hess_apply(P->N, P->r, P->rowptr, P->colidx, P->blocks, P->lambda, P->X, v, out);
+}
+/* f = tr(X^T Q X); lambda: N x 9; grad: 3N x r (nullable) */
+double port_csr3_model(uint64_t N, uint64_t r, const uint64_t *rowptr, const uint32_t *colidx, const double *blocks,
+                       const double *X, double *lambda, double *grad) {
+  return csr3_model(N, (int)r, rowptr, colidx, blocks, X, lambda, grad);
+}
+void port_csr3_hess(uint64_t N, uint64_t r, const uint64_t *rowptr, const uint32_t *colidx, const double *blocks,
+                    const double *lambda, const double *X, const double *v, double *out) {
+  csr3_hess_apply(N, (int)r, rowptr, colidx, blocks, lambda, X, v, out);
+}
+int port_stpcg_csr3(uint64_t N, uint64_t r, const uint64_t *rowptr, const uint32_t *colidx, const double *blocks,
+                    const double *lambda, const double *X, const double *g, const double *minv, double Delta,
+                    uint64_t max_iterations, double kappa_fgr, double theta, double epsilon, double *s,
+                    double *mnorm, uint64_t *iters) {
+  if (r < 3 || r > 8) return PORT_EXIT_BADARG;
+  port_csr3 P = {N, (int)r, rowptr, colidx, blocks, lambda, X};
+  port_diag Pd = {3 * N * r, minv};
+  return port_stpcg(3 * N * r, g, csr3_apply_cb, &P, minv ? diag_apply : NULL, &Pd, Delta, max_iterations,
+                    kappa_fgr, theta, epsilon, s, mnorm, iters);
+}
+
+typedef struct { uint32_t gx, gy, gz; int p; } port_stencil;
+static void stencil_apply_cb(void *c, const double *v, double *out) {
+  const port_stencil *P = (const port_stencil *)c;
+  stencil7_apply(P->gx, P->gy, P->gz, P->p, v, out);
+}
+void port_stencil7_apply(uint32_t gx, uint32_t gy, uint32_t gz, uint64_t p, const double *v, double *out) {
+  stencil7_apply(gx, gy, gz, (int)p, v, out);
+}
+int port_stpcg_stencil7(uint32_t gx, uint32_t gy, uint32_t gz, uint64_t p, const double *g, const double *minv,
+                        double Delta, uint64_t max_iterations, double kappa_fgr, double theta, double epsilon,
+                        double *s, double *mnorm, uint64_t *iters) {
+  port_stencil P = {gx, gy, gz, (int)p};
+  const uint64_t n = (uint64_t)gx * gy * gz * p;
+  port_diag Pd = {n, minv};
+  return port_stpcg(n, g, stencil_apply_cb, &P, minv ? diag_apply : NULL, &Pd, Delta, max_iterations, kappa_fgr,
+                    theta, epsilon, s, mnorm, iters);
+}

@@ -581,3 +581,73 @@ def test_lobpcg_full_size_properties(ctx):
     assert np.all(dist <= rn * (1 + 1e-9))                                                # |theta - lambda| <= |r| / |x|
     G = (Xc.T @ Xc).cpu().numpy()
     assert np.linalg.norm(G - np.eye(nev)) < 1e-9                                         # X^T B X = I (B = I)
+
+
+# ---- sparse Hessian families: rotation synchronisation on St(3,r)^N (config C5), 7-point Laplacian (config C4) --------
+def _pose_dev(ctx, prob):
+    import torch
+    rp = torch.from_numpy(prob.rowptr.astype(np.int64)).cuda()
+    ci = torch.from_numpy(prob.colidx.astype(np.int32)).cuda()
+    bl = ctx.to_device(prob.blocks)
+    X = ctx.to_device(prob.X0)
+    return rp, ci, bl, X
+
+
+@pytest.mark.parametrize("dims,r,consistent", [((8, 7, 6), 4, False), ((8, 7, 6), 3, True), ((6, 6, 6), 5, False),
+                                               ((3, 1, 1), 8, False), ((20, 20, 25), 4, False), ((50, 50, 40), 4, True)])
+def test_csr3_model_hvp_stpcg_vs_oracle(ctx, port, dims, r, consistent):
+    """Block-CSR 3x3 Hessian of the rotation-synchronisation cost (SE-Sync shape): model (Lambda, f, gradient), stand-alone
+    HVP and the fused tCG against the C restatement (itself bit-identical to the reference's STPCG on the same operator,
+    tests/test_oracle.py), N = 3 ... 1e5 poses, r = 3 ... 8, with and without the Jacobi preconditioner."""
+    prob = P.make_posegraph(dims, r, sigma=0.0, x_noise=0.0) if consistent else P.make_posegraph(dims, r)
+    rp, ci, bl, X = _pose_dev(ctx, prob)
+    lam_ref, f_ref, grad_ref = port.csr3_model(prob, prob.X0)
+    lam, f, grad = ctx.csr3_model(rp, ci, bl, X)
+    assert abs(f - f_ref) <= 1e-12 * max(abs(f_ref), float(prob.N))
+    assert np.abs(lam.cpu().numpy() - lam_ref).max() <= 1e-13 * max(1.0, np.abs(lam_ref).max())
+    assert rel(grad.cpu().numpy(), grad_ref) < 1e-13 or np.linalg.norm(grad_ref) < 1e-10
+    H = ctx.csr3_operator(rp, ci, bl, X)
+    lam_h = H.Lambda.cpu().numpy()
+    hv_ref = port.csr3_hess(prob, prob.X0, lam_h, prob.g)
+    hv = ctx.hvp(H, ctx.to_device(prob.g)).cpu().numpy()
+    assert rel(hv, hv_ref) < 1e-13
+    # right-hand side: in the range of H for the consistent problem (the gauge directions X_i Omega are its kernel)
+    g = hv_ref if consistent else prob.g
+    gn = float(np.linalg.norm(g))
+    minv = 1.0 / (1.0 + P.uniform01(77, 0, g.size)).reshape(g.shape)
+    for kw, mv in ((dict(Delta=1e6 * gn, max_iterations=40, kappa_fgr=1e-9, theta=0.), None),
+                   (dict(Delta=.3 * gn, max_iterations=40, kappa_fgr=1e-3, theta=.5), None),
+                   (dict(Delta=1e6 * gn, max_iterations=25, kappa_fgr=1e-9, theta=0.), minv)):
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_csr3(prob, prob.X0, lam_h, g, mv, **kw)
+        out = ctx.stpcg(ctx.to_device(g), H, minv=None if mv is None else ctx.to_device(mv), **kw)
+        assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+    # retraction: every pose block has orthonormal rows, first-order agreement with X + V
+    V = ctx.to_device(0.01 * prob.g)
+    Xr = ctx.csr3_retract(X, V).cpu().numpy().reshape(prob.N, 3, r)
+    assert np.abs(Xr @ Xr.transpose(0, 2, 1) - np.eye(3)).max() < 1e-13
+    Z = (prob.X0 + 0.01 * prob.g).reshape(prob.N, 3, r)
+    Qn = np.stack([np.linalg.qr(z.T)[0] * np.sign(np.diag(np.linalg.qr(z.T)[1]))[None, :] for z in Z[:50]])
+    assert np.abs(Xr[:50] - Qn.transpose(0, 2, 1)).max() < 1e-12
+
+
+@pytest.mark.parametrize("dims,p", [((9, 8, 7), 3), ((1, 1, 5), 1), ((32, 32, 32), 4), ((64, 48, 40), 8)])
+def test_stencil7_operator_stpcg_vs_oracle(ctx, port, dims, p):
+    """The 7-point Dirichlet Laplacian (config C4's operator) as a tCG Hessian descriptor, with the Jacobi
+    preconditioner 1/6 of that configuration."""
+    n = dims[0] * dims[1] * dims[2]
+    g = (2.0 * P.uniform01(5, 0, n * p) - 1.0).reshape(n, p)
+    H = ctx.stencil7_operator(*dims, p)
+    hv = ctx.hvp(H, ctx.to_device(g)).cpu().numpy()
+    assert np.array_equal(hv, port.stencil7_apply(dims, p, g))
+    assert rel(hv, P.laplacian3d_apply(g, *dims)) < 1e-14
+    minv = np.full((n, p), 1.0 / 6.0)
+    for kw, mv in ((dict(Delta=1e9, max_iterations=60, kappa_fgr=1e-9, theta=0.), None),
+                   (dict(Delta=1e9, max_iterations=60, kappa_fgr=1e-9, theta=0.), minv),
+                   (dict(Delta=.5, max_iterations=60, kappa_fgr=1e-3, theta=.5), minv)):
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_stencil7(dims, p, g, mv, **kw)
+        out = ctx.stpcg(ctx.to_device(g), H, minv=None if mv is None else ctx.to_device(mv), **kw)
+        assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)

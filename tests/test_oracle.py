@@ -210,3 +210,35 @@ def test_ref_matches_port_live_sphere(port, ref):
             a = ref.sphere_stpcg(prob, prob.x0, prob.g, **kw)
             b = port.stpcg_sphere(prob, prob.x0, prob.g, **kw)
             assert a[2] == b[2] and a[1] == b[1] and np.array_equal(a[0], b[0])
+
+
+# ---- sparse Hessian families (configs C5 / C4): the C restatement against the reference's STPCG on the same operator ----
+def test_sparse_operator_ports_match_the_reference_header(build_oracle):
+    import numpy as np
+    from optimization_b200 import problems as P
+    from oracle import refapi
+    port = refapi.PortOracle()
+    try:
+        R = refapi.RefOracle()
+    except (FileNotFoundError, OSError):
+        import pytest
+        pytest.skip("oracle/_ref not built here")
+    R.set_threads(1)
+    for pr in (P.make_posegraph((8, 7, 6), 4), P.make_posegraph((8, 7, 6), 3, sigma=0., x_noise=0.), P.make_posegraph((6, 6, 6), 5)):
+        lam, f, grad = port.csr3_model(pr, pr.X0)
+        hv, L, f_np, grad_np = P.posegraph_hess_numpy(pr, pr.X0, pr.g)
+        assert abs(f - f_np) <= 1e-12 * max(1.0, abs(f_np)) and np.abs(lam.reshape(-1, 3, 3) - L).max() < 1e-12
+        assert np.linalg.norm(port.csr3_hess(pr, pr.X0, lam, pr.g) - hv) <= 1e-13 * np.linalg.norm(hv)
+        for kw in (dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-8, theta=0.), dict(Delta=0.5, max_iterations=60, kappa_fgr=1e-3, theta=.5)):
+            s, mn, it, why = port.stpcg_csr3(pr, pr.X0, lam, pr.g, **kw)
+            s2, mn2, it2 = R.csr3_stpcg(pr, pr.X0, lam, pr.g, **kw)
+            assert it == it2 and mn == mn2 and np.array_equal(s, s2)
+    dims, p = (9, 8, 7), 3
+    n = dims[0] * dims[1] * dims[2]
+    g = (2 * P.uniform01(5, 0, n * p) - 1).reshape(n, p)
+    for mv in (None, np.full((n, p), 1 / 6.)):
+        kw = dict(Delta=1e6, max_iterations=200, kappa_fgr=1e-8, theta=0.)
+        s, mn, it, why = port.stpcg_stencil7(dims, p, g, mv, **kw)
+        s2, mn2, it2 = R.stencil7_stpcg(dims, p, g, mv, **kw)
+        assert it == it2 and mn == mn2 and np.array_equal(s, s2) and why == "residual"
+        assert np.linalg.norm(P.laplacian3d_apply(s, *dims) + g) <= 1e-7 * np.linalg.norm(g)
