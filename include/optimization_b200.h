@@ -137,6 +137,15 @@ typedef struct {
   uint64_t csr_nnz;               /* number of stored 3 x 3 blocks (for the byte counts) */
   /* OB200_OP_STENCIL7 */
   uint32_t gx, gy, gz;
+  /* OB200_OP_BLOCK_CSR3, row-sharded over the ranks of ob200_comm_connect (each rank owns a contiguous range of poses,
+   * a multiple of 256; n = 3 x local poses).  Column indices are LOCAL: [0, local poses) own poses, then `csr_n_halo`
+   * halo poses (rows of other ranks that local rows refer to); X (Y_dev) holds own poses followed by the halo poses.
+   * Before each operator apply every rank pushes the rows of p its peers need straight into their halo buffers
+   * (ob200_halo_create / ob200_halo_connect) over NVLink from inside the kernel. */
+  uint64_t csr_n_halo;                 /* halo poses of this rank (0: not sharded) */
+  const uint32_t *halo_send_idx_dev;   /* own pose indices to push, grouped by destination rank */
+  uint64_t halo_send_ptr[9];           /* entries [ptr[q], ptr[q+1]) of halo_send_idx_dev go to rank q */
+  uint64_t halo_dst_off[8];            /* first halo slot (in poses) of my rows inside rank q's halo buffer */
 } ob200_operator;
 
 /* Replaces the optional preconditioner functor (reference
@@ -296,6 +305,11 @@ int ob200_free_host(ob200_context *ctx, void *ptr_host);
  * torch.distributed all_gather), every rank connects.  All ranks must then issue
  * the same sequence of library calls. */
 #define OB200_COMM_HANDLE_BYTES 64
+/* Halo buffer of a row-sharded sparse operator (peers store the rows of p this rank needs into it): allocate `bytes`
+ * on this rank and export its 64-byte IPC handle; connect to the peers' buffers (handles in rank order, after
+ * ob200_comm_connect). */
+int ob200_halo_create(ob200_context *ctx, uint64_t bytes, void *handle_out /* 64 bytes */);
+int ob200_halo_connect(ob200_context *ctx, const void *handles /* world_size x 64 bytes, rank order */);
 int ob200_comm_export(ob200_context *ctx, void *handle_out /* 64 bytes */);
 int ob200_comm_connect(ob200_context *ctx, int rank, int world_size,
                        const void *handles /* world_size x 64 bytes, rank order */);

@@ -31,7 +31,7 @@ EXPORTS = [
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
-    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path", "ob200_div", "ob200_csr3_model", "ob200_csr3_retract",
+    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path", "ob200_div", "ob200_csr3_model", "ob200_csr3_retract", "ob200_halo_create", "ob200_halo_connect",
 ]
 
 
@@ -43,7 +43,8 @@ class Operator(C.Structure):
                 ("xAx", C.c_double), ("Ax_dev", C.c_void_p), ("ldu", C.c_uint64),
                 ("csr_rowptr_dev", C.c_void_p), ("csr_colidx_dev", C.c_void_p), ("csr_blocks_dev", C.c_void_p),
                 ("csr_lambda_dev", C.c_void_p), ("csr_nnz", C.c_uint64), ("gx", C.c_uint32), ("gy", C.c_uint32),
-                ("gz", C.c_uint32)]
+                ("gz", C.c_uint32), ("csr_n_halo", C.c_uint64), ("halo_send_idx_dev", C.c_void_p),
+                ("halo_send_ptr", C.c_uint64 * 9), ("halo_dst_off", C.c_uint64 * 8)]
 
 
 class BlockOperator(C.Structure):
@@ -137,6 +138,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     lib.ob200_malloc_host.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.ob200_free_host.argtypes = [vp, vp]
+    lib.ob200_halo_create.argtypes = [vp, u64, vp]
+    lib.ob200_halo_connect.argtypes = [vp, vp]
     lib.ob200_comm_export.argtypes = [vp, vp]
     lib.ob200_comm_connect.argtypes = [vp, i, i, vp]
     lib.ob200_comm_rank.argtypes = [vp]

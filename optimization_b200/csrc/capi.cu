@@ -65,6 +65,12 @@ struct SparseArgs {
   const unsigned *colidx;
   const double *blocks, *lambda, *X;
   unsigned gx, gy, gz;
+  // row-sharded CSR3: halo exchange of p
+  unsigned long long n_halo;
+  const double *halo;                        // this rank's halo buffer (n_halo poses x 3 r)
+  const unsigned *send_idx;
+  unsigned long long send_ptr[MAX_RANKS + 1];
+  double *peer_halo[MAX_RANKS];              // rank q's halo buffer, already offset to where this rank's rows go
 };
 cudaError_t launch_tcg_sparse(const TcgCommon &a, const SparseArgs &sp, int sm_count, cudaStream_t st);
 cudaError_t launch_sparse_apply(unsigned long long N, const SparseArgs &sp, const double *V, double *out, int sm_count,
@@ -150,6 +156,9 @@ struct ob200_context {
   CommDev cm;                     // rank, world, epoch, peer pointers
   u64 *comm_buf = nullptr;        // own inbox + flags
   void *peer_base[MAX_RANKS] = {nullptr};
+  double *halo_buf = nullptr;     // halo buffer of a row-sharded sparse operator (peers store into it)
+  size_t halo_bytes = 0;
+  void *halo_peer[MAX_RANKS] = {nullptr};
 };
 
 static const size_t COMM_INBOX_WORDS = (size_t)ACC_SLOTS * MAX_RANKS * ACC_WORDS;
@@ -229,6 +238,9 @@ int ob200_destroy(ob200_context *ctx) {
   for (int r = 0; r < MAX_RANKS; ++r)
     if (ctx->peer_base[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
   cudaFree(ctx->comm_buf);
+  for (int r = 0; r < MAX_RANKS; ++r)
+    if (ctx->halo_peer[r] && r != ctx->cm.rank) cudaIpcCloseMemHandle(ctx->halo_peer[r]);
+  cudaFree(ctx->halo_buf);
   cudaFree(ctx->dbg);
   cudaFree(ctx->planes);
   cudaFree(ctx->plane_exp);
@@ -334,6 +346,40 @@ int ob200_comm_connect(ob200_context *ctx, int rank, int world, const void *hand
   ctx->cm.rank = rank;
   ctx->cm.world = world;
   ctx->cm.epoch = 0;
+  return OB200_OK;
+}
+
+int ob200_halo_create(ob200_context *ctx, uint64_t bytes, void *handle_out) {
+  if (!ctx || !handle_out) return OB200_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < MAX_RANKS; ++r) {
+    if (ctx->halo_peer[r] && r != ctx->cm.rank) cudaIpcCloseMemHandle(ctx->halo_peer[r]);
+    ctx->halo_peer[r] = nullptr;
+  }
+  cudaFree(ctx->halo_buf);
+  ctx->halo_buf = nullptr;
+  ctx->halo_bytes = 0;
+  CK(cudaMalloc(&ctx->halo_buf, bytes ? bytes : 256));
+  CK(cudaMemset(ctx->halo_buf, 0, bytes ? bytes : 256));
+  CK(cudaDeviceSynchronize());
+  ctx->halo_bytes = bytes;
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->halo_buf));
+  memcpy(handle_out, &h, sizeof(h));
+  return OB200_OK;
+}
+int ob200_halo_connect(ob200_context *ctx, const void *handles) {
+  if (!ctx || !handles) return OB200_INVALID_ARGUMENT;
+  if (!ctx->halo_buf) return fail(ctx, OB200_INVALID_ARGUMENT, "halo_connect before halo_create");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->cm.world; ++r) {
+    if (r == ctx->cm.rank) { ctx->halo_peer[r] = ctx->halo_buf; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)r * OB200_COMM_HANDLE_BYTES, sizeof(h));
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->halo_peer[r] = p;
+  }
   return OB200_OK;
 }
 
@@ -560,6 +606,20 @@ static int sparse_args(ob200_context *ctx, const ob200_operator *H, SparseArgs *
     sp->blocks = H->csr_blocks_dev;
     sp->lambda = H->csr_lambda_dev;
     sp->X = H->Y_dev;
+    if (ctx->cm.world > 1) {
+      if (!ctx->halo_buf || !ctx->halo_peer[ctx->cm.world - 1])
+        return fail(ctx, OB200_INVALID_ARGUMENT, "row-sharded block-CSR operator: call ob200_halo_create / ob200_halo_connect first");
+      if (ctx->cm.rank + 1 < ctx->cm.world && (uint64_t)(H->n / 3) % 256)   // (the last rank takes the ragged end)
+        return fail(ctx, OB200_INVALID_ARGUMENT, "row-sharded block-CSR operator: local pose count must be a multiple of 256");
+      if (H->csr_n_halo * 3 * H->p * sizeof(double) > ctx->halo_bytes) return fail(ctx, OB200_INVALID_ARGUMENT, "halo buffer too small");
+      if (H->halo_send_ptr[ctx->cm.world] && !H->halo_send_idx_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "missing halo send list");
+      sp->n_halo = H->csr_n_halo;
+      sp->halo = ctx->halo_buf;
+      sp->send_idx = H->halo_send_idx_dev;
+      for (int q = 0; q <= ctx->cm.world; ++q) sp->send_ptr[q] = H->halo_send_ptr[q];
+      for (int q = 0; q < ctx->cm.world; ++q)
+        sp->peer_halo[q] = static_cast<double *>(ctx->halo_peer[q]) + H->halo_dst_off[q] * 3 * H->p;
+    }
   } else {
     if (!H->gx || !H->gy || !H->gz || (uint64_t)H->gx * H->gy * H->gz != H->n)
       return fail(ctx, OB200_INVALID_ARGUMENT, "stencil operator: gx gy gz must equal n");
@@ -596,7 +656,8 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   } else if (H->kind == OB200_OP_BLOCK_CSR3 || H->kind == OB200_OP_STENCIL7) {
     SparseArgs chk;
     if ((rc = sparse_args(ctx, H, &chk))) return rc;
-    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "sparse operators are single-GPU in this version (no halo exchange yet)");
+    if (ctx->cm.world > 1 && H->kind == OB200_OP_STENCIL7)
+      return fail(ctx, OB200_UNSUPPORTED, "the stencil tCG operator is single-GPU in this version");
   } else {
     return fail(ctx, OB200_UNSUPPORTED, "operator kind not supported by the fused tCG path");
   }
@@ -889,7 +950,7 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
     SparseArgs sp;
     int rc = sparse_args(ctx, H, &sp);
     if (rc) return rc;
-    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "sparse operators are single-GPU in this version");
+    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "stand-alone HVP of a sparse operator is single-GPU in this version");
     CK(launch_sparse_apply(N, sp, v, out, ctx->sm_count, st));
     ctx->launches += 1;
     return OB200_OK;
@@ -978,7 +1039,6 @@ int ob200_csr3_model(ob200_context *ctx, uint64_t N, uint64_t r, const uint64_t 
                      const double *blocks, const double *X, double *lambda_dev, double *f, double *grad_dev) {
   if (!ctx || !rowptr || !colidx || !blocks || !X || !lambda_dev) return OB200_INVALID_ARGUMENT;
   if (r < 3 || r > 8) return fail(ctx, OB200_UNSUPPORTED, "rotation-synchronisation model requires 3 <= r <= 8");
-  if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "sparse operators are single-GPU in this version");
   CK(cudaSetDevice(ctx->device));
   SparseArgs sp;
   memset(&sp, 0, sizeof(sp));
@@ -991,6 +1051,10 @@ int ob200_csr3_model(ob200_context *ctx, uint64_t N, uint64_t r, const uint64_t 
   cudaStream_t st = ctx->stream;
   CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SCAL_WORDS, st));
   CK(launch_csr3_model(sp, X, lambda_dev, grad_dev, ctx->acc, ctx->sm_count, st));
+  {   // row-sharded: X holds own poses followed by the halo poses, f is the sum over the ranks
+    int rc = exchange(ctx, ctx->acc, 0, KUL_STRIDE);
+    if (rc) return rc;
+  }
   CK(launch_finalize_many(ctx->acc, 1, ctx->dscal, st));
   ctx->launches += 2;
   CK(cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -374,7 +374,8 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
   if (threadIdx.x == leader) {
     gen += 1;
     const unsigned target = gen * gridDim.x;
-    __threadfence();
+    if (cm.world > 1) __threadfence_system();   // this CTA's peer stores (halo rows) are ordered before the machine-wide flag
+    else __threadfence();
     if (stamps) stamps[0] = globaltimer_ns();
     const unsigned old = atom_add_acqrel_u32(counter, 1u);
     int ok = 1;

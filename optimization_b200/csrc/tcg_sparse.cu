@@ -33,6 +33,13 @@ struct SparseArgs {
   const unsigned *colidx;
   const double *blocks, *lambda, *X;
   unsigned gx, gy, gz;               // STENCIL7
+  // row-sharded CSR3 (one process per GPU): column indices >= units address the halo buffer, which the owning
+  // ranks fill with plain stores over NVLink in phase A1 (before the machine-wide barrier)
+  unsigned long long n_halo;
+  const double *halo;
+  const unsigned *send_idx;
+  unsigned long long send_ptr[MAX_RANKS + 1];
+  double *peer_halo[MAX_RANKS];
 };
 
 template <int CNT>
@@ -83,7 +90,8 @@ __device__ __forceinline__ void csr3_pose_apply(const SparseArgs &sp, unsigned l
     const unsigned long long e0 = __ldg(sp.rowptr + pose), e1 = __ldg(sp.rowptr + pose + 1);
     for (unsigned long long e = e0; e < e1; ++e) {
       const double *B = sp.blocks + 9 * e;
-      const double *Vj = V + (size_t)3 * __ldg(sp.colidx + e) * r + c;
+      const unsigned long long jcol = __ldg(sp.colidx + e);
+      const double *Vj = (jcol < sp.units ? V + (size_t)3 * jcol * r : sp.halo + (size_t)3 * (jcol - sp.units) * r) + c;
       const double v0 = __ldcg(Vj), v1 = __ldcg(Vj + r), v2 = __ldcg(Vj + 2 * r);
       const double b0 = __ldg(B), b1 = __ldg(B + 1), b2 = __ldg(B + 2), b3 = __ldg(B + 3), b4 = __ldg(B + 4),
                    b5 = __ldg(B + 5), b6 = __ldg(B + 6), b7 = __ldg(B + 7), b8 = __ldg(B + 8);
@@ -253,6 +261,23 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
       pp = warp_sum(pp); pr = warp_sum(pr);
       if (lane == 0) kul_add_atomic(sacc + SC_PP * KUL_STRIDE, pp);
       if (lane == 1) kul_add_atomic(sacc + SC_PR * KUL_STRIDE, pr);
+    }
+    if (sp.kind == 4 && a.cm.world > 1) {
+      // halo push: the rows of p that other ranks' rows refer to, recomputed from r / p_old (no dependence on other
+      // CTAs) and stored straight into the peers' halo buffers over NVLink
+      const unsigned long long per = 3ull * sp.r, total = sp.send_ptr[a.cm.world] * per;
+      const unsigned long long t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1ull) / gridDim.x;
+      for (unsigned long long t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const unsigned long long entry = t / per, el = t % per;
+        int q = 0;
+        while (entry >= sp.send_ptr[q + 1]) ++q;
+        const size_t src = (size_t)3 * __ldg(sp.send_idx + entry) * sp.r + el;
+        const double rr = __ldcg(a.r + src);
+        const double v = a.minv ? __ldg(a.minv + src) * rr : rr;
+        const double pv = k ? fma(beta, __ldcg(p_old + src), -v) : -v;
+        sp.peer_halo[q][(entry - sp.send_ptr[q]) * per + el] = pv;
+      }
+      __threadfence_system();
     }
     __syncthreads();
     // <p,p>, <p,r> ride in the set of phase A2 (same reduction); this barrier only orders p

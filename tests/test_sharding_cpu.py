@@ -109,3 +109,32 @@ def test_two_rank_exact_reduction_matches_single_rank():
         # integer limb sums need not be limb-wise equal (carries are not normalised), the VALUE is
         assert kulisch_value(np.array(limbs, dtype=np.int64)) == kulisch_value(single) == want
         assert handles == [0, 1]
+
+
+def test_posegraph_sharding_plan_is_consistent():
+    """Host-side plan of the row-sharded pose-graph operator (config C5): local column indices address own poses then halo
+    poses, entry order inside a row is unchanged, every halo pose is pushed by its owner into the right slot."""
+    import numpy as np
+    from optimization_b200 import problems as P
+    from optimization_b200.sharded import halo_send_plan, pose_partition, shard_posegraph
+    prob = P.make_posegraph((16, 16, 8), 4)
+    for world in (1, 2, 3, 8):
+        lo, hi = pose_partition(prob.N, world)
+        assert lo[0] == 0 and hi[-1] == prob.N and all(a % 256 == 0 for a in lo) and lo[1:] == hi[:-1]
+        plans = [shard_posegraph(prob, q, world) for q in range(world)]
+        sends = [halo_send_plan(prob, q, world) for q in range(world)]
+        for q, pl in enumerate(plans):
+            n_loc = pl["hi"] - pl["lo"]
+            e0 = int(prob.rowptr[pl["lo"]])
+            glob = prob.colidx[e0:e0 + pl["colidx"].size].astype(np.int64)
+            back = np.where(pl["colidx"] < n_loc, pl["colidx"].astype(np.int64) + pl["lo"],
+                            pl["halo"][np.maximum(pl["colidx"].astype(np.int64) - n_loc, 0)] if pl["halo"].size else 0)
+            assert np.array_equal(back, glob)                         # same entries, same order
+            assert np.all((pl["halo"] < pl["lo"]) | (pl["halo"] >= pl["hi"]))
+            # emulate the pushes of every owner into q's halo buffer
+            got = np.full(pl["halo"].size, -1, dtype=np.int64)
+            for src in range(world):
+                idx, ptr, off = sends[src]
+                mine = idx[int(ptr[q]):int(ptr[q + 1])].astype(np.int64) + plans[src]["lo"]
+                got[int(off[q]):int(off[q]) + mine.size] = mine
+            assert np.array_equal(got, pl["halo"])
