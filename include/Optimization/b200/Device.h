@@ -6,6 +6,7 @@
 #pragma once
 #include <cstring>
 #include <memory>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -414,11 +415,29 @@ struct DeviceLOBPCG<std::vector<double>, b200::DeviceMatrix, double> {
     M X = X0;
     std::vector<double> theta(nev, 0.0);
     uint64_t it = 0, conv = 0;
+    // the Gaussian probe block of the operator-norm estimates: same generator and draw order as the reference
+    // (LOBPCG.h:203-210), so the convergence tolerances -- and with them num_iters / nc -- are the reference's
+    M Omega;
+    {
+      const size_t m = X0.rows(), nx = X0.cols();
+      std::vector<double> h(m * nx);
+      std::default_random_engine engine;
+      std::normal_distribution<double> gauss(0, 1.0);
+      for (size_t i = 0; i < m; ++i)
+        for (size_t j = 0; j < nx; ++j) h[i * nx + j] = gauss(engine);
+      Omega = M(a->ctx, m, nx, h.data());
+    }
     b200::check(a->ctx, ob200_lobpcg(a->ctx, &a->op, b ? &b->op : nullptr, t ? &t->op : nullptr, X.rows(), X.cols(), X.data(),
-                                     nev, max_iters, tau, nullptr, theta.data(), &it, &conv));
+                                     nev, max_iters, tau, Omega.data(), theta.data(), &it, &conv));
     num_iters = it;
     nc = conv;
-    out = std::make_pair(std::move(theta), std::move(X));   // X: m x nx, the first nev columns are the eigenvector estimates
+    // hand back the nev eigenvector estimates only (m x nev), like the reference's conservativeResize (l.334)
+    M Xnev(a->ctx, X.rows(), nev);
+    ob200_block_operator ident{};
+    ident.kind = OB200_BLK_SCALAR;
+    ident.alpha = 1.0;
+    b200::check(a->ctx, ob200_block_apply(a->ctx, &ident, X.rows(), nev, X.data(), X.cols(), Xnev.data(), nev));
+    out = std::make_pair(std::move(theta), std::move(Xnev));
     return true;
   }
 };

@@ -471,3 +471,53 @@ class PortOracle:
         if rc:
             raise ValueError("invalid argument")
         return tb.result(x)
+
+
+class RefLobpcg:
+    """oracle/_ref/libref_lobpcg.so: the reference's own LOBPCG.h compiled against oracle/eigen_shim (see
+    oracle/ref_lobpcg_driver.cpp).  Operators are descriptors: None | ("diag", array) | ("scalar", alpha) |
+    ("laplacian", (gx, gy, gz))."""
+
+    def __init__(self, path=os.path.join(_HERE, "_ref", "libref_lobpcg.so")):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle ref` in the dev container)")
+        self.lib = C.CDLL(path)
+        self.lib.ref_lobpcg.argtypes = [C.c_int, _dp, C.c_double, C.POINTER(C.c_uint32), C.c_int, _dp, C.c_double, C.c_int,
+                                        _dp, C.c_double, C.c_uint64, C.c_uint64, _dp, C.c_uint64, C.c_uint64, C.c_double,
+                                        _dp, _dp, _u64p, _u64p, _dp]
+        self.lib.ref_lobpcg_omega.argtypes = [C.c_uint64, C.c_uint64, _dp]
+
+    @staticmethod
+    def _op(op):
+        if op is None:
+            return 0, None, 0.0, None, None
+        kind, val = op
+        if kind == "diag":
+            a = np.ascontiguousarray(val, dtype=np.float64)
+            return 1, _d(a), 0.0, None, a
+        if kind == "scalar":
+            return 2, None, float(val), None, None
+        g = (C.c_uint32 * 3)(*val)
+        return 3, None, 0.0, g, g
+
+    def omega(self, m, nx):
+        out = np.zeros((m, nx))
+        self.lib.ref_lobpcg_omega(m, nx, _d(out))
+        return out
+
+    def lobpcg(self, A, B, T, X0, nev, max_iters, tau=1e-6, trace=False):
+        m, nx = X0.shape
+        ka, da, aa, ga, keep_a = self._op(A)
+        kb, db, ab, _, keep_b = self._op(B)
+        kt, dt, at, _, keep_t = self._op(T)
+        theta, X = np.zeros(nev), np.zeros((m, nev))
+        it, nc = C.c_uint64(0), C.c_uint64(0)
+        tr = np.zeros((max_iters, nx)) if trace else None
+        rc = self.lib.ref_lobpcg(ka, da, aa, ga, kb, db, ab, kt, dt, at, m, nx, _d(np.ascontiguousarray(X0)), nev,
+                                 max_iters, tau, _d(theta), _d(X), C.byref(it), C.byref(nc), _d(tr))
+        if rc == 1:
+            raise ValueError("std::invalid_argument from reference LOBPCG")
+        if rc:
+            raise RuntimeError("reference LOBPCG failed")
+        out = (theta, X, int(it.value), int(nc.value))
+        return out + (tr[:int(it.value) + 1],) if trace else out

@@ -282,13 +282,56 @@ def test_device_lobpcg_header_entry_point(tmp_path):
         for a in (ad, bd, X0):
             fh.write(np.ascontiguousarray(a).tobytes())
     got = _lines(subprocess.run([exe, str(f)], check=True, capture_output=True, text=True).stdout)
-    A, B, T = (lambda X: ad[:, None] * X), (lambda X: bd[:, None] * X), (lambda X: np.abs(ad)[:, None] * X)
-    for name, Bop, exact in (("diag", None, ad[:nev]), ("diag_generalized", B, np.sort(ad / bd)[:nev])):
-        th_ref, _, it_ref, nc_ref = L.lobpcg(A, Bop, T, X0, nev, n, 1e-8, Omega=X0)
+    # the reference's own header (compiled against the Eigen stand-in) on the same X0; the header layer draws the
+    # reference's Gaussian probe block itself, so iteration counts are pinned exactly
+    from oracle import refapi
+    R = refapi.RefLobpcg()
+    for name, Bop, exact in (("diag", None, ad[:nev]), ("diag_generalized", ("diag", bd), np.sort(ad / bd)[:nev])):
+        th_ref, _, it_ref, nc_ref = R.lobpcg(("diag", ad), Bop, ("diag", np.abs(ad)), X0, nev, n, 1e-8)
         g = got[name]
-        assert g["nc"] == nc_ref == nev and g["x_cols"] == nx
+        assert g["nc"] == nc_ref == nev and g["x_cols"] == nev                         # m x nev, like the reference
         assert np.linalg.norm(np.array(g["theta"]) - exact) < 1e-4                     # the reference tests' bar
         assert np.allclose(g["theta"], th_ref, rtol=1e-9, atol=1e-9)
-        assert abs(g["num_iters"] - it_ref) <= max(2, it_ref // 10)
+        assert abs(g["num_iters"] - it_ref) <= 1        # (Gram rounding on a different machine may move the test by one)
     assert got["apply"]["max_err"] == 0.0
+    assert got["invalid_argument"]["thrown"] == 2
+
+
+def test_host_lobpcg_header_matches_reference_header(tmp_path):
+    """OUR LOBPCG.h (dense path: RayleighRitz, soft locking, user function, random-start overload) against the
+    reference's own LOBPCG.h, both compiled against the same Eigen stand-in (oracle/eigen_shim): iteration counts,
+    converged counts, eigenvalues and eigenvectors bit for bit on the four problems of the reference's
+    tests/LOBPCG_unit_test.cpp:123-208."""
+    from oracle import refapi
+    try:
+        R = refapi.RefLobpcg()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built here")
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "lobpcg_host_check")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "oracle", "eigen_shim"),
+                    os.path.join(ROOT, "tests", "host", "lobpcg_host_check.cpp"), "-o", exe], check=True)
+    n, nx, nev = 1000, 10, 5
+    ad, bd = np.linspace(-.5 * n, .5 * n, n), np.linspace(1.0, n, n)
+    X0 = (2.0 * P.uniform01(91, 0, n * nx) - 1.0).reshape(n, nx)
+    f = tmp_path / "lob.bin"
+    with open(f, "wb") as fh:
+        fh.write(struct.pack("<QQ", n, nx))
+        for a in (ad, bd, X0):
+            fh.write(np.ascontiguousarray(a).tobytes())
+    got = _lines(subprocess.run([exe, str(f), str(tmp_path) + "/x_"], check=True, capture_output=True, text=True).stdout)
+    for name, (gen, pre) in {"plain": (False, False), "precon": (False, True), "generalized_precon": (True, True),
+                             "generalized": (True, False)}.items():
+        th, X, it, nc = R.lobpcg(("diag", ad), ("diag", bd) if gen else None, ("diag", np.abs(ad)) if pre else None, X0,
+                                 nev, 10 * n, 1e-8)
+        g = got[name]
+        assert (g["num_iters"], g["nc"], g["hook_calls"]) == (it, nc, it)
+        assert np.array_equal(np.array(g["theta"]), th)
+        assert np.array_equal(np.fromfile(str(tmp_path) + f"/x_{name}.bin").reshape(n, nev), X)
+        exact = np.sort(ad / bd)[:nev] if gen else ad[:nev]
+        assert np.linalg.norm(th - exact) < 1e-4                                       # the reference tests' bar
+    assert got["hook_stop"]["num_iters"] == 7 and got["hook_stop"]["hook_calls"] == 7
+    assert got["random_start"]["nc"] == 3 and got["random_start"]["x_cols"] == 3
+    assert np.linalg.norm(np.array(got["random_start"]["theta"]) - ad[:3]) < 1e-4
     assert got["invalid_argument"]["thrown"] == 2

@@ -64,3 +64,28 @@ def test_laplacian_spectrum_with_jacobi():
     A = lambda X: P.laplacian3d_apply(X, g, g, g)
     theta, X, it, nc = L.lobpcg(A, None, lambda R: R / 6.0, _x0(g ** 3, 8, seed=31), 4, 300, 1e-8)
     assert nc == 4 and np.allclose(theta, exact[:4], rtol=1e-6)
+
+
+def test_numpy_restatement_is_pinned_to_the_reference_header():
+    """oracle/lobpcg_port.py (numpy) against the reference's own LOBPCG.h compiled with the Eigen stand-in
+    (oracle/_ref/libref_lobpcg.so): same probe block, iteration counts within one, eigenvalues to 1e-9."""
+    import numpy as np
+    import pytest
+    from optimization_b200 import problems as P
+    from oracle import lobpcg_port as L, refapi
+    try:
+        R = refapi.RefLobpcg()
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built here")
+    n, nx, nev = 1000, 10, 5
+    ad, bd = np.linspace(-.5 * n, .5 * n, n), np.linspace(1.0, n, n)
+    X0 = (2.0 * P.uniform01(91, 0, n * nx) - 1.0).reshape(n, nx)
+    Om = R.omega(n, nx)
+    for gen, pre in ((False, False), (False, True), (True, True), (True, False)):
+        th, X, it, nc = R.lobpcg(("diag", ad), ("diag", bd) if gen else None, ("diag", np.abs(ad)) if pre else None, X0, nev,
+                                 10 * n, 1e-8)
+        th2, _, it2, nc2 = L.lobpcg(lambda V: ad[:, None] * V, (lambda V: bd[:, None] * V) if gen else None,
+                                    (lambda V: np.abs(ad)[:, None] * V) if pre else None, X0, nev, 10 * n, 1e-8, Omega=Om)
+        assert nc == nc2 == nev and abs(it - it2) <= 1 and np.allclose(th, th2, rtol=1e-9, atol=1e-9)
+        exact = np.sort(ad / bd)[:nev] if gen else ad[:nev]
+        assert np.linalg.norm(th - exact) < 1e-4          # the bar of the reference's tests/LOBPCG_unit_test.cpp
