@@ -83,6 +83,13 @@ cudaError_t launch_blk_diag(unsigned long long m, int k, const double *d, double
                             int ldo, int sm_count, cudaStream_t st);
 cudaError_t launch_blk_stencil7(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
                                 int sm_count, cudaStream_t st);
+cudaError_t launch_blk_stencil7_slab(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
+                                     int has_lo, int has_hi, int sm_count, cudaStream_t st);
+cudaError_t launch_lob_allreduce(const CommDev &cm, unsigned long long gphase, double *const *peer_region, size_t slot_stride,
+                                 double *buf, int count, int *abort_flag, cudaStream_t st);
+cudaError_t launch_lob_plane_exchange(const PlaneXchg &px, double *interior, int ld, int k, unsigned long long plane_rows,
+                                      unsigned long long planes, int has_lo, int has_hi, int *abort_flag, int sm_count,
+                                      cudaStream_t st);
 cudaError_t launch_blk_gram(unsigned long long m, const double *A, int lda, int k1, const double *B, int ldb, int k2,
                             double *partial, int nb, double *G, cudaStream_t st);
 cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int k, const double *C, int ldc, int n2, double *out,
@@ -156,6 +163,8 @@ struct ob200_context {
   CommDev cm;                     // rank, world, epoch, peer pointers
   u64 *comm_buf = nullptr;        // own inbox + flags
   void *peer_base[MAX_RANKS] = {nullptr};
+  unsigned long long plane_seq = 0;   // ghost-plane exchanges issued so far (row-sharded LOBPCG; same on every rank)
+  unsigned long long ar_seq = 0;      // all-reduces through the halo buffer issued so far
   double *halo_buf = nullptr;     // halo buffer of a row-sharded sparse operator (peers store into it)
   size_t halo_bytes = 0;
   void *halo_peer[MAX_RANKS] = {nullptr};
@@ -359,6 +368,8 @@ int ob200_halo_create(ob200_context *ctx, uint64_t bytes, void *handle_out) {
   cudaFree(ctx->halo_buf);
   ctx->halo_buf = nullptr;
   ctx->halo_bytes = 0;
+  ctx->plane_seq = 0;
+  ctx->ar_seq = 0;
   CK(cudaMalloc(&ctx->halo_buf, bytes ? bytes : 256));
   CK(cudaMemset(ctx->halo_buf, 0, bytes ? bytes : 256));
   CK(cudaDeviceSynchronize());
@@ -1248,6 +1259,63 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   const int nx = (int)nx64, nsmax = 3 * nx, nb = ctx->sm_count;
   const size_t mnx = (size_t)m * nx;
   int rc;
+  // Row sharding (one process per GPU, ob200_comm_connect + ob200_halo_create / ob200_halo_connect): every rank holds a
+  // contiguous block of rows (for the Laplacian: a slab of z-planes, A->gz = LOCAL planes); Grams, norms and residual
+  // norms are all-reduced in rank order through the halo buffers, the Rayleigh-Ritz step runs replicated on identical
+  // data, the stencil exchanges one ghost plane with each neighbouring rank before every apply.
+  const int world = ctx->cm.world, rank = ctx->cm.rank;
+  const bool sharded = world > 1;
+  const bool slab = sharded && A->kind == OB200_BLK_STENCIL7;
+  const size_t plane_rows = slab ? (size_t)A->gx * A->gy : 0;
+  const size_t ghost = plane_rows * (size_t)nsmax;                         // doubles of one ghost plane of a basis buffer
+  const size_t AR_MAX = (size_t)nsmax * nsmax + 64;
+  const size_t HDR = 512;                                                  // doubles reserved for flags at the buffer head
+  if (sharded) {
+    if ((B && B->kind == OB200_BLK_STENCIL7) || (T && T->kind == OB200_BLK_STENCIL7))
+      return fail(ctx, OB200_UNSUPPORTED, "row-sharded LOBPCG: only A may be the stencil operator");
+    const size_t need = sizeof(double) * (HDR + 2 * (size_t)world * AR_MAX + 4 * plane_rows * (size_t)nsmax);
+    if (!ctx->halo_buf || ctx->halo_bytes < need || !ctx->halo_peer[world - 1]) {
+      ctx->err = "row-sharded LOBPCG: halo buffer of at least " + std::to_string(need) +
+                 " bytes required (ob200_halo_create / ob200_halo_connect)";
+      return OB200_INVALID_ARGUMENT;
+    }
+  }
+  int *abort_dev = reinterpret_cast<int *>(ctx->barrier + 1);
+  auto allreduce = [&](double *buf, int count) -> int {                    // sum over the ranks, in rank order, in place
+    if (!sharded) return OB200_OK;
+    double *regions[MAX_RANKS];
+    const size_t par = (size_t)(ctx->ar_seq & 1ull);
+    for (int q = 0; q < world; ++q) regions[q] = static_cast<double *>(ctx->halo_peer[q]) + HDR + par * world * AR_MAX;
+    CK(launch_lob_allreduce(ctx->cm, ctx->cm.epoch, regions, AR_MAX, buf, count, abort_dev, st));
+    ctx->cm.epoch += 1;
+    ctx->ar_seq += 1;
+    ctx->launches += 1;
+    return OB200_OK;
+  };
+  auto apply_A = [&](int k, double *in, int ldi, double *out, int ldo) -> int {   // `in`: a basis buffer (ghost planes around it)
+    if (!slab) return block_apply(ctx, A, m, k, in, ldi, out, ldo);
+    const int has_lo = rank > 0, has_hi = rank + 1 < world;
+    ctx->plane_seq += 1;
+    const size_t par = (size_t)(ctx->plane_seq & 1ull), plane = plane_rows * (size_t)nsmax;
+    auto region = [&](int q, int dir) {   // dir 0: "from below" (filled by q-1), 1: "from above" (filled by q+1)
+      return static_cast<double *>(ctx->halo_peer[q]) + HDR + 2 * (size_t)world * AR_MAX + (2 * par + dir) * plane;
+    };
+    auto flag = [&](int q, int dir) { return reinterpret_cast<unsigned long long *>(ctx->halo_peer[q]) + 8 + dir; };
+    PlaneXchg px;
+    px.lo_dst = has_lo ? region(rank - 1, 1) : nullptr;
+    px.hi_dst = has_hi ? region(rank + 1, 0) : nullptr;
+    px.lo_flag = has_lo ? flag(rank - 1, 1) : nullptr;
+    px.hi_flag = has_hi ? flag(rank + 1, 0) : nullptr;
+    px.from_below = region(rank, 0);
+    px.from_above = region(rank, 1);
+    px.my_flags = flag(rank, 0);
+    px.seq = ctx->plane_seq;
+    px.counter = reinterpret_cast<unsigned *>(ctx->halo_buf) + 0;            // first word of my own header
+    CK(launch_lob_plane_exchange(px, in, ldi, k, plane_rows, A->gz, has_lo, has_hi, abort_dev, ctx->sm_count, st));
+    CK(launch_blk_stencil7_slab(A->gx, A->gy, A->gz, k, in, ldi, out, ldo, has_lo, has_hi, ctx->sm_count, st));
+    ctx->launches += 3;
+    return OB200_OK;
+  };
 
   double *S = nullptr, *S2 = nullptr, *AS = nullptr, *BS = nullptr, *AX = nullptr, *BX = nullptr, *R = nullptr, *P = nullptr,
          *tmp = nullptr;
@@ -1262,8 +1330,8 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   for (int pass = 0; pass < 2; ++pass) {
     Slab mem;
     mem.base = pass ? ctx->lob_ws : nullptr;
-    mem.get(&S, (size_t)m * nsmax);
-    mem.get(&S2, (size_t)m * nsmax);     // the update writes the new X straight into the next basis (no copies of X)
+    mem.get(&S, (size_t)m * nsmax + 2 * ghost);      // (+ one ghost plane below and above when the grid is sharded in z)
+    mem.get(&S2, (size_t)m * nsmax + 2 * ghost);     // the update writes the new X straight into the next basis (no copies of X)
     mem.get(&AS, (size_t)m * nsmax);
     if (B) mem.get(&BS, (size_t)m * nsmax);
     mem.get(&AX, mnx);
@@ -1285,11 +1353,15 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
       ctx->lob_cap = mem.off;
     }
   }
+  S += ghost;      // interior of the basis buffers
+  S2 += ghost;
+  const size_t rowX = sizeof(double) * nx, rowS = sizeof(double) * nsmax;
 
   std::vector<double> h(2 * nx + 8), th(nsmax);
   auto frob = [&](const double *V, double *out) -> int {   // ||V||_F of an m x nx block
     CK(launch_blk_sumsq(mnx, V, partial, nb, norms2, st));
     ctx->launches += 2;
+    { int rca = allreduce(norms2, 1); if (rca) return rca; }
     CK(cudaMemcpyAsync(h.data(), norms2, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *out = std::sqrt(h[0]);
@@ -1300,7 +1372,8 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   const double *Om = Omega ? Omega : X;
   double nOm = 0, nA = 0, nB = 0;
   if ((rc = frob(Om, &nOm))) return rc;
-  if ((rc = block_apply(ctx, A, m, nx, Om, nx, tmp, nx))) return rc;
+  CK(cudaMemcpy2DAsync(S, rowS, Om, rowX, rowX, m, cudaMemcpyDeviceToDevice, st));        // (the stencil reads a basis buffer)
+  if ((rc = apply_A(nx, S, nsmax, tmp, nx))) return rc;
   if ((rc = frob(tmp, &nA))) return rc;
   const double A2normest = nA / nOm;
   double B2normest = 1.0;
@@ -1311,12 +1384,15 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   }
 
   // initial Rayleigh-Ritz on span(X0) (l.186-198)
-  if ((rc = block_apply(ctx, A, m, nx, X, nx, AX, nx))) return rc;
+  CK(cudaMemcpy2DAsync(S, rowS, X, rowX, rowX, m, cudaMemcpyDeviceToDevice, st));            // l.210 (first iteration)
+  if ((rc = apply_A(nx, S, nsmax, AX, nx))) return rc;
   const double *BXp = X;
   if (B) { if ((rc = block_apply(ctx, B, m, nx, X, nx, BX, nx))) return rc; BXp = BX; }
   CK(launch_blk_gram(m, X, nx, nx, AX, nx, nx, partial, nb, GA, st));
   CK(launch_blk_gram(m, X, nx, nx, BXp, nx, nx, partial, nb, GB, st));
   ctx->launches += 4;
+  if ((rc = allreduce(GA, nx * nx))) return rc;
+  if ((rc = allreduce(GB, nx * nx))) return rc;
   if ((rc = rayleigh_ritz(ctx, nx, GA, GB, EA, EB, D, theta, C, work, lwork, info_dev))) return rc;
   CK(launch_blk_gemm(m, AX, nx, nx, C, nx, nx, tmp, nx, nb, st));           // AX <- AX C
   CK(cudaMemcpyAsync(AX, tmp, sizeof(double) * mnx, cudaMemcpyDeviceToDevice, st));
@@ -1328,9 +1404,7 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
   ctx->launches += 2;
 
   uint64_t nc = 0, it = 1;
-  const size_t rowX = sizeof(double) * nx, rowS = sizeof(double) * nsmax;
   // the current eigenvector block lives in the first nx columns of the current basis buffer (leading dimension nsmax)
-  CK(cudaMemcpy2DAsync(S, rowS, X, rowX, rowX, m, cudaMemcpyDeviceToDevice, st));            // l.210 (first iteration)
   for (it = 1; it < max_iters; ++it) {
     const int act = nx - (int)nc;                                                           // soft locking
     if (T) {   // l.207 + l.213: W = T(R), active columns written straight into the basis
@@ -1343,22 +1417,25 @@ extern "C" int ob200_lobpcg(ob200_context *ctx, const ob200_block_operator *A, c
       CK(cudaMemcpy2DAsync(S + ns, rowS, P + nc, rowX, sizeof(double) * act, m, cudaMemcpyDeviceToDevice, st));  // l.217
       ns = 3 * nx - 2 * (int)nc;
     }
-    if ((rc = block_apply(ctx, A, m, ns, S, nsmax, AS, nsmax))) return rc;                  // l.225
+    if ((rc = apply_A(ns, S, nsmax, AS, nsmax))) return rc;                                 // l.225
     const double *BSp = S;
     if (B) { if ((rc = block_apply(ctx, B, m, ns, S, nsmax, BS, nsmax))) return rc; BSp = BS; }   // l.226
     CK(launch_blk_gram(m, S, nsmax, ns, AS, nsmax, ns, partial, nb, GA, st));               // l.229
     CK(launch_blk_gram(m, S, nsmax, ns, BSp, nsmax, ns, partial, nb, GB, st));              // l.230
     ctx->launches += 4;
+    if ((rc = allreduce(GA, ns * ns))) return rc;
+    if ((rc = allreduce(GB, ns * ns))) return rc;
     if ((rc = rayleigh_ritz(ctx, ns, GA, GB, EA, EB, D, theta, C, work, lwork, info_dev))) return rc;   // l.233
     CK(launch_blk_update(m, S, nsmax, ns, nx, C, ns, S2, nsmax, P, nx, nb, st));   // l.239 X = S C(:, 1:nx) -> next basis; l.249 P
     ctx->launches += 1;
     std::swap(S, S2);                                                                       // X = S[:, 0:nx] from here on
-    if ((rc = block_apply(ctx, A, m, nx, S, nsmax, AX, nx))) return rc;                     // l.242
+    if ((rc = apply_A(nx, S, nsmax, AX, nx))) return rc;                                    // l.242
     const double *BXq = S;
     int ldbx = nsmax;
     if (B) { if ((rc = block_apply(ctx, B, m, nx, S, nsmax, BX, nx))) return rc; BXq = BX; ldbx = nx; }   // l.243
     CK(launch_blk_residual(m, nx, AX, BXq, ldbx, S, nsmax, theta, R, partial, nb, norms2, st));   // l.246, 254
     ctx->launches += 2;
+    if ((rc = allreduce(norms2, 2 * nx))) return rc;
     CK(cudaMemcpyAsync(h.data(), norms2, sizeof(double) * 2 * nx, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(th.data(), theta, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -346,6 +346,16 @@ struct CommDev {
   int words_per_set;
 };
 
+// ghost-plane exchange of a z-slab between neighbouring ranks (row-sharded LOBPCG, lobpcg.cu)
+struct PlaneXchg {
+  double *lo_dst, *hi_dst;                    // (r-1)'s "from above" region, (r+1)'s "from below" region (or null)
+  unsigned long long *lo_flag, *hi_flag;      // the flags to raise there
+  const double *from_below, *from_above;      // my receive regions
+  const unsigned long long *my_flags;         // [0] from below (rank r-1), [1] from above (rank r+1)
+  unsigned long long seq;
+  unsigned *counter;                          // CTA completion counter (zeroed before the push)
+};
+
 struct RedView {   // reduced word j = sum_r base0[r * stride + j]
   const u64 *base0;
   size_t stride;

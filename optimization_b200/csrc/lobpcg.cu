@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace ob200 {
 
 constexpr int LB_THREADS = 256;
@@ -25,8 +27,10 @@ __global__ void __launch_bounds__(LB_THREADS) blk_diag_kernel(unsigned long long
   }
 }
 // 7-point Laplacian, Dirichlet boundary, grid gx x gy x gz (x fastest): out = 6 in - sum of existing neighbours
+// has_lo / has_hi: the block vector is one z-slab of a row-sharded grid and carries a ghost plane below / above its
+// first / last plane (filled from the neighbouring rank before the call); otherwise the slab ends at the Dirichlet boundary.
 __global__ void __launch_bounds__(LB_THREADS) blk_stencil7_kernel(unsigned gx, unsigned gy, unsigned gz, int k, const double *in,
-                                                                  int ldi, double *out, int ldo) {
+                                                                  int ldi, double *out, int ldo, int has_lo, int has_hi) {
   const unsigned long long m = (unsigned long long)gx * gy * gz, total = m * (unsigned long long)k;
   const unsigned long long sx = 1, sy = gx, sz = (unsigned long long)gx * gy;
   for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < total;
@@ -40,8 +44,8 @@ __global__ void __launch_bounds__(LB_THREADS) blk_stencil7_kernel(unsigned gx, u
     if (x + 1 < gx) v -= p[sx * ldi];
     if (y > 0) v -= p[-(long long)(sy * ldi)];
     if (y + 1 < gy) v -= p[sy * ldi];
-    if (z > 0) v -= p[-(long long)(sz * ldi)];
-    if (z + 1 < gz) v -= p[sz * ldi];
+    if (z > 0 || has_lo) v -= p[-(long long)(sz * ldi)];
+    if (z + 1 < gz || has_hi) v -= p[sz * ldi];
     out[r * ldo + c] = v;
   }
 }
@@ -341,7 +345,116 @@ cudaError_t launch_blk_diag(unsigned long long m, int k, const double *d, double
 }
 cudaError_t launch_blk_stencil7(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
                                 int sm_count, cudaStream_t st) {
-  blk_stencil7_kernel<<<lb_grid((unsigned long long)gx * gy * gz * k, sm_count), LB_THREADS, 0, st>>>(gx, gy, gz, k, in, ldi, out, ldo);
+  blk_stencil7_kernel<<<lb_grid((unsigned long long)gx * gy * gz * k, sm_count), LB_THREADS, 0, st>>>(gx, gy, gz, k, in, ldi, out, ldo, 0, 0);
+  return cudaGetLastError();
+}
+cudaError_t launch_blk_stencil7_slab(unsigned gx, unsigned gy, unsigned gz, int k, const double *in, int ldi, double *out, int ldo,
+                                     int has_lo, int has_hi, int sm_count, cudaStream_t st) {
+  blk_stencil7_kernel<<<lb_grid((unsigned long long)gx * gy * gz * k, sm_count), LB_THREADS, 0, st>>>(gx, gy, gz, k, in, ldi, out, ldo,
+                                                                                                 has_lo, has_hi);
+  return cudaGetLastError();
+}
+
+// ---- row-sharded LOBPCG (one process per GPU): exchanges through the ranks' halo buffers (NVLink peer stores) ------------
+// All-reduce of `count` doubles: every rank stores its values into slot [rank] of every rank's region, raises a flag per
+// destination, waits for all sources and sums the slots IN RANK ORDER (every rank forms the same sum, bit for bit, so the
+// replicated Rayleigh-Ritz steps stay identical).
+struct LobPeers {
+  double *ar[MAX_RANKS];     // rank q's all-reduce region for the current parity
+  size_t slot_stride;        // doubles per source slot
+};
+__global__ void __launch_bounds__(512) lob_allreduce_kernel(CommDev cm, unsigned long long gphase, LobPeers pe, double *buf,
+                                                            int count, int *abort_flag) {
+  for (int q = 0; q < cm.world; ++q) {
+    double *dst = pe.ar[q] + (size_t)cm.rank * pe.slot_stride;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  const int slot = (int)(gphase % ACC_SLOTS);
+  if ((int)threadIdx.x < cm.world) {
+    st_release_sys_u64(cm.flags[threadIdx.x] + slot * MAX_RANKS + cm.rank, gphase + 1ull);
+    const unsigned long long *f = cm.flags[cm.rank] + slot * MAX_RANKS + threadIdx.x;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys_u64(f) < gphase + 1ull) {
+      if (++spins > (1ull << 26)) { atomicExch(abort_flag, 1); break; }
+      if (spins > 256) __nanosleep(64);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const double *mine = pe.ar[cm.rank];
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    double v = __ldcg(mine + i);
+    for (int q = 1; q < cm.world; ++q) v += __ldcg(mine + (size_t)q * pe.slot_stride + i);
+    buf[i] = v;
+  }
+}
+cudaError_t launch_lob_allreduce(const CommDev &cm, unsigned long long gphase, double *const *peer_region, size_t slot_stride,
+                                 double *buf, int count, int *abort_flag, cudaStream_t st) {
+  LobPeers pe;
+  for (int q = 0; q < MAX_RANKS; ++q) pe.ar[q] = q < cm.world ? peer_region[q] : nullptr;
+  pe.slot_stride = slot_stride;
+  lob_allreduce_kernel<<<1, 512, 0, st>>>(cm, gphase, pe, buf, count, abort_flag);
+  return cudaGetLastError();
+}
+
+// Ghost planes of a z-slab: push my first / last plane (k columns of a row-major block vector with leading dimension ld)
+// into the neighbours' receive regions, the last CTA to finish raises their flags; the pull kernel waits for my own flags
+// and copies the received planes into my ghost planes.
+__global__ void __launch_bounds__(LB_THREADS) lob_plane_push_kernel(PlaneXchg px, const double *interior, int ld, int k,
+                                                                    unsigned long long plane_rows, unsigned long long planes) {
+  const unsigned long long per = plane_rows * (unsigned long long)k;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < 2 * per;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const bool top = e >= per;
+    const unsigned long long i = top ? e - per : e, r = i / k, c = i - r * k;
+    if (!top && px.lo_dst) px.lo_dst[i] = interior[r * ld + c];                                     // my first plane -> rank r-1
+    if (top && px.hi_dst) px.hi_dst[i] = interior[((planes - 1) * plane_rows + r) * ld + c];      // my last plane -> rank r+1
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(px.counter, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence_system();
+      if (px.lo_flag) st_release_sys_u64(px.lo_flag, px.seq);
+      if (px.hi_flag) st_release_sys_u64(px.hi_flag, px.seq);
+    }
+  }
+}
+__global__ void __launch_bounds__(LB_THREADS) lob_plane_pull_kernel(PlaneXchg px, double *interior, int ld, int k,
+                                                                    unsigned long long plane_rows, unsigned long long planes,
+                                                                    int has_lo, int has_hi, int *abort_flag) {
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < 2; ++d) {
+      if (!(d ? has_hi : has_lo)) continue;
+      unsigned long long spins = 0;
+      while (ld_acquire_sys_u64(px.my_flags + d) < px.seq) {
+        if (++spins > (1ull << 26)) { atomicExch(abort_flag, 1); break; }
+        if (spins > 256) __nanosleep(64);
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const unsigned long long per = plane_rows * (unsigned long long)k;
+  for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < 2 * per;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const bool top = e >= per;
+    const unsigned long long i = top ? e - per : e, r = i / k, c = i - r * k;
+    if (!top && has_lo) (interior - plane_rows * ld)[r * ld + c] = __ldcg(px.from_below + i);          // ghost plane below
+    if (top && has_hi) (interior + planes * plane_rows * ld)[r * ld + c] = __ldcg(px.from_above + i);  // ghost plane above
+  }
+}
+cudaError_t launch_lob_plane_exchange(const PlaneXchg &px, double *interior, int ld, int k, unsigned long long plane_rows,
+                                      unsigned long long planes, int has_lo, int has_hi, int *abort_flag, int sm_count,
+                                      cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(px.counter, 0, sizeof(unsigned), st);
+  if (e) return e;
+  const int grid = lb_grid(2 * plane_rows * (unsigned long long)k, sm_count);
+  lob_plane_push_kernel<<<grid, LB_THREADS, 0, st>>>(px, interior, ld, k, plane_rows, planes);
+  lob_plane_pull_kernel<<<grid, LB_THREADS, 0, st>>>(px, interior, ld, k, plane_rows, planes, has_lo, has_hi, abort_flag);
   return cudaGetLastError();
 }
 // G (k1 x k2, row-major) = A^T B ; partial: scratch of nb * k1 * k2 doubles

@@ -231,3 +231,49 @@ class ShardedPoseGraph:
 
     def solve_device(self, **kw):
         return self.ctx.stpcg(self.g, self.H, **kw)
+
+
+# ---- BASELINE config C4 sharded: LOBPCG with block vectors row-sharded over the ranks -----------------------------------
+def lobpcg_halo_bytes(world: int, nx: int, plane_rows: int = 0) -> int:
+    """Size of the halo buffer ob200_lobpcg needs in row-sharded mode (same formula as csrc/capi.cu)."""
+    nsmax = 3 * nx
+    return 8 * (512 + 2 * world * (nsmax * nsmax + 64) + 4 * plane_rows * nsmax)
+
+
+def setup_halo(ctx, world: int, nbytes: int):
+    """Allocate this rank's halo buffer and connect to the peers' (handles exchanged with torch.distributed)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import capi
+    buf = (C.c_ubyte * capi.COMM_HANDLE_BYTES)()
+    ctx._check(ctx.lib.ob200_halo_create(ctx.h, int(nbytes), buf))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(buf))
+    ctx._check(ctx.lib.ob200_halo_connect(ctx.h, b"".join(handles)))
+
+
+def z_partition(gz: int, world: int):
+    """z-planes [lo[q], hi[q]) of rank q (contiguous slabs of the gx x gy x gz grid, x fastest)."""
+    lo = [gz * q // world for q in range(world)]
+    hi = [gz * (q + 1) // world for q in range(world)]
+    return lo, hi
+
+
+class ShardedLaplacianLobpcg:
+    """LOBPCG on the 7-point Laplacian of a gx x gy x gz grid with the block vectors sharded in z-slabs: Grams, norms and
+    residual norms all-reduced in rank order, Rayleigh-Ritz replicated, one ghost plane exchanged with each neighbour
+    before every operator apply -- all through NVLink peer stores (no NCCL call on the data path)."""
+
+    def __init__(self, ctx, gx, gy, gz, nx, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        if getattr(ctx, "world", 1) != world:
+            ctx.connect(rank, world)
+        lo, hi = z_partition(gz, world)
+        self.z0, self.z1 = lo[rank], hi[rank]
+        self.rows = slice(self.z0 * gx * gy, self.z1 * gx * gy)
+        setup_halo(ctx, world, lobpcg_halo_bytes(world, nx, gx * gy))
+        self.A = ctx.block_laplacian3d(gx, gy, self.z1 - self.z0)          # LOCAL planes
+        self.T = ctx.block_scalar(1.0 / 6.0)
+
+    def solve(self, X0_local, nev, max_iters, tau, Omega_local):
+        return self.ctx.lobpcg(self.A, None, self.T, X0_local, nev, max_iters, tau, Omega=Omega_local)
