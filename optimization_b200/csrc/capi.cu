@@ -45,7 +45,7 @@ cudaError_t launch_tcg_stiefel_tc(const TcgCommon &a, unsigned long long n_rows,
                                   const unsigned char *planes, const int *plane_exp, int grid, cudaStream_t stm,
                                   int hvp_mode = 0, const unsigned long long *planes_sum_dev = nullptr,
                                   unsigned long long planes_sum_expected = 0);
-cudaError_t launch_tcg_stiefel_v5(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
+cudaError_t launch_tcg_stiefel_v6(const TcgCommon &a, unsigned long long n_rows, const unsigned short *A,
                                   const double *Y, const double *S_dev, double op_norm_bound,
                                   const unsigned char *planes, const int *plane_exp, int sm_count, cudaStream_t stm);
 cudaError_t launch_tcg_sphere(const TcgCommon &a, const double *d, const double *Ut, unsigned long long ldu, const double *x,
@@ -152,12 +152,12 @@ struct ob200_context {
   bool planes_ok = false;
   double S_cache[1024];                    // last S uploaded to dmat[0..1023] (skip the pageable H2D copy when unchanged)
   bool S_cache_valid = false;
-  unsigned long long *blk_stats = nullptr; // per-block maxima of r / p for the v5 Stiefel kernel (10 words per block)
+  unsigned long long *blk_stats = nullptr; // per-block maxima of r / p for the v6 Stiefel kernel (10 words per block)
   size_t blk_stats_cap = 0;
   unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
   unsigned long long *dsum = nullptr;      // device / pinned-host word for the per-solve checksum of A
   unsigned long long *hsum = nullptr;
-  int opt_tcgen05 = 2;            // 1: tcgen05 kernel v5 (warp-specialised, work in progress), 2: tcgen05 kernel v4, 0: fp64 MMA kernel
+  int opt_tcgen05 = 2;            // 1: tcgen05 kernel v6 (warp-specialised register budgets, work in progress), 2: tcgen05 kernel v4, 0: fp64 MMA kernel
   int last_path = 0;              // 1 = tcgen05 kernel, 0 = fp64 tensor-core kernel
   // multi-GPU exchange (CUDA IPC peer memory)
   CommDev cm;                     // rank, world, epoch, peer pointers
@@ -273,7 +273,7 @@ int ob200_synchronize(ob200_context *ctx) {
 
 int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, uint64_t *out4_min) {
   if (!ctx) return OB200_INVALID_ARGUMENT;
-  const size_t words = 4 * 1024 + 64;
+  const size_t words = 4 * 1024 + 256;
   if (enable && !ctx->dbg) {
     CK(cudaMalloc(&ctx->dbg, words * 8));
     CK(cudaMemset(ctx->dbg, 0, words * 8));
@@ -291,12 +291,17 @@ int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, 
       }
     }
     if (getenv("OB200_TIMELINE")) {
-      if (getenv("OB200_TIMELINE")[0] == '5') {   // v5 kernel: all 48 stamps relative to the end of the previous iteration's phase A loop start
+      if (getenv("OB200_TIMELINE")[0] == '5') {   // v6 kernel: all 48 stamps relative to the end of the previous iteration's phase A loop start
         unsigned long long t0 = ~0ull;
-        for (int k = 0; k < 48; ++k) if (h[4096 + k] && h[4096 + k] < t0) t0 = h[4096 + k];
-        fprintf(stderr, "v5 timeline (ns rel. to the earliest stamp):");
-        for (int k = 0; k < 48; ++k) if (h[4096 + k]) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - t0));
-        fprintf(stderr, "\n");
+        for (int k = 0; k < 192; ++k) if (h[4096 + k] && h[4096 + k] < t0) t0 = h[4096 + k];
+        fprintf(stderr, "v6 timeline (ns rel. to the earliest stamp):");
+        for (int k = 0; k < 64; ++k) if (h[4096 + k]) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - t0));
+        fprintf(stderr, "\nper block [RP_FULL, L done, M frags, MMA done, M read back, M done, G start, G done]:\n");
+        for (int b = 0; b < 8; ++b) {
+          fprintf(stderr, "  blk %d:", b);
+          for (int e = 0; e < 8; ++e) fprintf(stderr, " %6lld", h[4096 + 64 + 8 * b + e] ? (long long)(h[4096 + 64 + 8 * b + e] - t0) : -1ll);
+          fprintf(stderr, "\n");
+        }
       }
       fprintf(stderr, "timeline (ns rel. to L start):");
       for (int k = 0; k < 18; ++k) fprintf(stderr, " [%d]%lld", k, (long long)(h[4096 + k] - h[4096]));
@@ -701,7 +706,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   a.cm = ctx->cm;
   a.blk_stats = nullptr;
   a.nblk_stats = 0;
-  if (want_tc && ctx->opt_tcgen05 == 1) {   // v5 kernel: block maxima of r (seeded by the init kernel) and p
+  if (want_tc && ctx->opt_tcgen05 == 1) {   // v6 kernel: block maxima of r (seeded by the init kernel) and p
     const size_t nblk = (H->n + 127) / 128;
     if (nblk > ctx->blk_stats_cap) {
       cudaFree(ctx->blk_stats);
@@ -757,7 +762,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
       CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
                                ctx->plane_exp, grid, st));
     else if (use_tc)
-      CK(launch_tcg_stiefel_v5(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
+      CK(launch_tcg_stiefel_v6(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
                                ctx->plane_exp, ctx->sm_count, st));
     else
       CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));

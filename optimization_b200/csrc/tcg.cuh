@@ -53,7 +53,7 @@ struct TcgCommon {
   TcgDeviceResult *result;
   CommDev cm;                  // multi-GPU exchange (world == 1: unused)
   unsigned long long *dbg;     // optional: [0..3] ns spent in phase A / A-sync / phase B / B-sync (max over CTAs)
-  // optional (Stiefel v5 kernel): per-128-row-block maxima as bit patterns of non-negative doubles,
+  // optional (Stiefel v6 kernel): per-128-row-block maxima as bit patterns of non-negative doubles,
   // [R0 | R1 : nblk each] max |r| (ping-pong over iterations), [P0 | P1 : 4 nblk each] max |p| per L warp
   unsigned long long *blk_stats;
   unsigned long long nblk_stats;

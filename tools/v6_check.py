@@ -1,4 +1,4 @@
-"""v5 kernel bring-up: parity against the C port at small sizes, then timing against v4 at the BASELINE size."""
+"""v6 kernel bring-up: parity against the C port at small sizes, then timing against v4 at the BASELINE size."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,7 +26,7 @@ for n in sizes:
             good = (o.num_iterations, o.exit_reason) == (it_ref, why_ref) and e < 1e-10 and torch.equal(o.s, o2.s)
             ok &= good
             print(f"n={n} path={ctx.last_path} it={o.num_iterations}/{it_ref} exit={o.exit_reason}/{why_ref} rel={e:.2e} det={torch.equal(o.s, o2.s)} {'OK' if good else 'FAIL'}", flush=True)
-print("V5_CHECK", "PASS" if ok else "FAIL", flush=True)
+print("V6_CHECK", "PASS" if ok else "FAIL", flush=True)
 if "--notime" not in sys.argv:
     n = 100000
     prob = P.make_stiefel_critical(n, 32)
