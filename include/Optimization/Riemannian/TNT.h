@@ -76,6 +76,17 @@ struct InnerViews {
   inner_product(const Variable &x, const RiemannianMetric<Variable, Tangent, Scalar, Args...> &metric) {
     return [&x, &metric](const Tangent &a1, const Tangent &a2, Args &...a) -> Scalar { return metric(x, a1, a2, a...); };
   }
+  // the preconditioner in the form the inner solver takes: (v, lambda) = P(r) with an empty multiplier
+  // (reference TNT.h:413-426)
+  template <typename Multiplier>
+  static std::optional<LinearAlgebra::STPCGPreconditioner<Tangent, Multiplier, Args...>>
+  preconditioner(const Variable &x, const std::optional<LinearOperator<Variable, Tangent, Args...>> &precon) {
+    if (!precon) return std::nullopt;
+    return LinearAlgebra::STPCGPreconditioner<Tangent, Multiplier, Args...>(
+        [&x, &precon](const Tangent &v, Args &...a) -> std::pair<Tangent, Multiplier> {
+          return {(*precon)(x, v, a...), Multiplier()};
+        });
+  }
 };
 
 template <typename Scalar>
@@ -138,11 +149,8 @@ TNT(const Objective<Variable, Scalar, Args...> &f, const QuadraticModel<Variable
   using Views = detail::InnerViews<Variable, Tangent, Scalar, Args...>;
   LA::SymmetricLinearOperator<Tangent, Args...> H = Views::hessian(x, Hess);
   const LA::InnerProduct<Tangent, Scalar, Args...> inner = Views::inner_product(x, metric);
-  std::optional<LA::STPCGPreconditioner<Tangent, Multiplier, Args...>> P;
-  if (precon)
-    P = [&x, &precon](const Tangent &v, Args &...a) -> std::pair<Tangent, Multiplier> {
-      return {(*precon)(x, v, a...), Multiplier()};
-    };
+  const std::optional<LA::STPCGPreconditioner<Tangent, Multiplier, Args...>> P =
+      Views::template preconditioner<Multiplier>(x, precon);
 
   Scalar Delta = params.Delta0;
   const auto t0 = Stopwatch::tick();

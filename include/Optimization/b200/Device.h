@@ -194,6 +194,31 @@ struct BoundJacobi {
   }
 };
 
+// The same scaling in the form TNT takes as its `precon` argument (Riemannian::LinearOperator: precon(x, v), reference
+// TNT.h:247).  TNT's inner views recognise it and hand BoundJacobi to the inner solver, so a Jacobi-preconditioned solve
+// stays on the fused tCG path (operators that admit a pointwise preconditioner: diagonal, sphere, sparse families).
+struct JacobiPreconditioner {
+  std::shared_ptr<const DeviceMatrix> minv;
+  template <typename... Args>
+  DeviceMatrix operator()(const DeviceMatrix &, const DeviceMatrix &v, Args &...a) const {
+    return BoundJacobi{minv}(v, a...).first;
+  }
+};
+// Tangent-space preserving preconditioner for the Stiefel model: precon(Y, V) = P_Y(minv o V), P_Y(Z) = Z - Y sym(Y^T Z).
+// (An elementwise scaling alone leaves T_Y St(n,p), which is why ob200_stpcg refuses OB200_PRECON_JACOBI on the Stiefel
+// operator.)  Runs the generic STPCG loop over the device level-1 kernels: one extra projection per CG iteration.
+struct ProjectedJacobiPreconditioner {
+  ob200_context *ctx = nullptr;
+  std::shared_ptr<const DeviceMatrix> minv;
+  template <typename... Args>
+  DeviceMatrix operator()(const DeviceMatrix &Y, const DeviceMatrix &v, Args &...) const {
+    DeviceMatrix z = v.like(), out = v.like();
+    check(ctx, ob200_hadamard(ctx, v.size(), minv->data(), v.data(), z.data()));
+    check(ctx, ob200_stiefel_project(ctx, Y.rows(), Y.cols(), Y.data(), z.data(), out.data()));
+    return out;
+  }
+};
+
 // One fused tCG solve through the C ABI (ob200_stpcg): the whole STPCG loop in one persistent kernel.
 inline DeviceMatrix fused_stpcg(const OperatorState &st, const DeviceMatrix *minv, const DeviceMatrix &g,
                                 double &update_step_M_norm, size_t &num_iterations, double Delta,
@@ -394,6 +419,17 @@ struct InnerViews<b200::DeviceMatrix, b200::DeviceMatrix, double, Args...> {
     if (const EuclideanFn *fn = metric.template target<EuclideanFn>())
       if (*fn == &EuclideanMetric<M, double, Args...>) return b200::FrobeniusProduct{};
     return [&x, &metric](const M &a1, const M &a2, Args &...a) -> double { return metric(x, a1, a2, a...); };
+  }
+  template <typename Multiplier>
+  static std::optional<LinearAlgebra::STPCGPreconditioner<M, Multiplier, Args...>>
+  preconditioner(const M &x, const std::optional<LinearOperator<M, M, Args...>> &precon) {
+    if (!precon) return std::nullopt;
+    if constexpr (std::is_same<Multiplier, std::nullptr_t>::value) {
+      if (const b200::JacobiPreconditioner *jp = precon->template target<b200::JacobiPreconditioner>())
+        return LinearAlgebra::STPCGPreconditioner<M, Multiplier, Args...>(b200::BoundJacobi{jp->minv});
+    }
+    return LinearAlgebra::STPCGPreconditioner<M, Multiplier, Args...>(
+        [&x, &precon](const M &v, Args &...a) -> std::pair<M, Multiplier> { return {(*precon)(x, v, a...), Multiplier()}; });
   }
 };
 }  // namespace detail

@@ -238,6 +238,11 @@ int ob200_stiefel_model(ob200_context *ctx, uint64_t n, uint64_t p, const uint16
 /* Cholesky-QR retraction  out = qf(Y + V) */
 int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y_dev,
                           const double *V_dev, double *out_dev);
+/* Tangent-space projection  out = Z - Y sym(Y^T Z)  at a point Y with orthonormal columns (p == 32).  Building block of
+ * tangent-space preserving preconditioners for the Stiefel model: the reference hands the user's `precon` functor
+ * (TNT.h:247) to STPCG through the adapter of TNT.h:413-426, and an elementwise scaling alone leaves T_Y St(n,p). */
+int ob200_stiefel_project(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y_dev,
+                          const double *Z_dev, double *out_dev);
 
 /* ---- rotation synchronisation f(X) = tr(X^T Q X) on St(3,r)^N (BASELINE config C5) -----------------------------
  * Replace the Objective / QuadraticModel / Retraction functors of that model (reference call sites TNT.h:377,380,505,

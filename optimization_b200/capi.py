@@ -27,7 +27,7 @@ EXPORTS = [
     "ob200_create", "ob200_destroy", "ob200_last_error", "ob200_version", "ob200_sm_count",
     "ob200_synchronize", "ob200_kernel_launches", "ob200_stpcg", "ob200_stpcg_host", "ob200_hvp",
     "ob200_dot", "ob200_dots", "ob200_axpby", "ob200_hadamard", "ob200_stiefel_model",
-    "ob200_stiefel_retract", "ob200_sphere_model", "ob200_sphere_retract", "ob200_lobpcg", "ob200_block_apply", "ob200_malloc",
+    "ob200_stiefel_retract", "ob200_stiefel_project", "ob200_sphere_model", "ob200_sphere_retract", "ob200_lobpcg", "ob200_block_apply", "ob200_malloc",
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
@@ -124,6 +124,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_stiefel_model.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(dbl), vp,
                                         C.POINTER(dbl)]
     lib.ob200_stiefel_retract.argtypes = [vp, u64, u64, vp, vp, vp]
+    lib.ob200_stiefel_project.argtypes = [vp, u64, u64, vp, vp, vp]
     lib.ob200_sphere_model.argtypes = [vp, u64, u64, vp, vp, u64, vp, vp, vp, C.POINTER(dbl), vp]
     lib.ob200_sphere_retract.argtypes = [vp, u64, vp, vp, vp]
     lib.ob200_csr3_model.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp, C.POINTER(dbl), vp]

@@ -1185,6 +1185,35 @@ int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const doub
   return OB200_OK;
 }
 
+int ob200_stiefel_project(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y, const double *Z, double *out) {
+  if (!ctx || !Y || !Z || !out) return OB200_INVALID_ARGUMENT;
+  if (p != 32) return fail(ctx, OB200_UNSUPPORTED, "Stiefel projection requires p == 32");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t N = n * p;
+  int rc = ensure_vectors(ctx, N);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const unsigned long long nblk = (n + 127) / 128;
+  int grid = ctx->sm_count;
+  if ((unsigned long long)grid > nblk) grid = (int)nblk;
+  double zz = 0.0;
+  const double *aa[1] = {Z}, *bb[1] = {Z};
+  if ((rc = dots_sync(ctx, N, 1, aa, bb, &zz))) return rc;
+  const int e = gram_exponent_host(std::sqrt(zz) * 2.0);       // |(Y^T Z)_ij| <= ||y_i|| ||z_j|| <= ||Z||_F
+  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_WORDS, st));
+  CK(launch_stiefel_gram(n, Y, Z, ctx->acc, std::ldexp(1.0, 90 - e), grid, st));
+  ctx->launches += 1;
+  std::vector<double> G(1024);
+  if ((rc = read_gram(ctx, e, G.data(), nullptr))) return rc;
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j) ctx->hmat[i * 32 + j] = -0.5 * (G[i * 32 + j] + G[j * 32 + i]);
+  CK(cudaMemcpyAsync(ctx->dmat + 1024, ctx->hmat, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
+  CK(launch_stiefel_rowgemm(n, Z, 1.0, Y, ctx->dmat + 1024, out, grid, st));   // Z - Y sym(Y^T Z)
+  ctx->launches += 1;
+  CK(cudaStreamSynchronize(st));
+  return OB200_OK;
+}
+
 }  // extern "C"
 
 // ---- LOBPCG ------------------------------------------------------------------------------------------------

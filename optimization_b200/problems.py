@@ -334,6 +334,27 @@ def tnls_sine_cases(m: int = 100):
     }
 
 
+def device_lsq_case(n: int = 5000):
+    """Inputs of the device LSQR / TNLS checks (tests/host/lsq_device_check.cpp): a diagonal operator d in [0.5, 2],
+    right-hand sides and a start, all from the counter-based generator.  LSQR: min |diag(d) x - b|;
+    TNLS: F(x) = (d o x o x + x) - c  with c = F-consistent data of a known root x* in [0.2, 1.2]."""
+    d = 0.5 + 1.5 * uniform01(91, 0, n)
+    b = 2.0 * uniform01(92, 0, n) - 1.0
+    xstar = 0.2 + uniform01(93, 0, n)
+    c = (d * (xstar * xstar) + xstar)
+    x0 = np.full(n, 0.5)
+    return dict(d=d, b=b, c=c, x0=x0, xstar=xstar,
+                lsqr=dict(max_iterations=200, lam=0.0, btol=1e-12, Atol=1e-12, cond_limit=1e12),
+                tnls=dict(max_iterations=50, root_tol=1e-9, grad_tol=0.0, rel_tol=0.0, step_tol=0.0, Delta_tol=0.0))
+
+
+def stiefel_row_scaling(n: int, p: int = 32) -> np.ndarray:
+    """Elementwise scaling minv (n x p, constant along rows) of the projected Jacobi preconditioner used by the
+    TNT + preconditioner checks: 1 / (1 + ((37 r) mod 64) / 128)."""
+    w = 1.0 / (1.0 + ((37 * np.arange(n)) % 64) / 128.0)
+    return np.ascontiguousarray(np.repeat(w[:, None], p, axis=1))
+
+
 def laplacian3d_apply(X: np.ndarray, gx: int, gy: int, gz: int) -> np.ndarray:
     """7-point Laplacian with Dirichlet boundary on a gx x gy x gz grid (x fastest), applied to the rows of the
     block vector X (m x k, m = gx gy gz): (A X)[i] = 6 X[i] - sum of the existing neighbours (config C4 operator)."""

@@ -534,11 +534,13 @@ int ref_stiefel_stpcg(void *hh, const double *Y, const double *g,
 }
 
 // End-to-end reference TNT on the Stiefel trace-min problem.
-int ref_stiefel_tnt(void *hh, const double *Y0, const double *prm, double *Y_out,
-                    int *status, uint64_t *n_outer, uint64_t *n_trace,
-                    double *scalars, uint64_t cap, uint64_t *inner_iterations,
-                    double *radius, double *rho, double *fvals, double *gradnorms,
-                    double *step_norms, double *step_M_norms) {
+// minv (nullable): elementwise scaling of the tangent-space preserving preconditioner  precon(Y, V) = P_Y(minv o V),
+// P_Y(Z) = Z - Y sym(Y^T Z), handed to the reference's TNT as its `precon` argument (TNT.h:247, adapter l.413-426).
+int ref_stiefel_tnt_precon(void *hh, const double *Y0, const double *minv, const double *prm, double *Y_out,
+                           int *status, uint64_t *n_outer, uint64_t *n_trace,
+                           double *scalars, uint64_t cap, uint64_t *inner_iterations,
+                           double *radius, double *rho, double *fvals, double *gradnorms,
+                           double *step_norms, double *step_M_norms) {
   auto *h = static_cast<RefStiefel *>(hh);
   using V = HostMat;
   const BlockDiag &op = h->op;
@@ -570,10 +572,26 @@ int ref_stiefel_tnt(void *hh, const double *Y0, const double *prm, double *Y_out
       [&](const V &Y, const V &Vt, StiefelCache &) {
         return stiefel_retract(op.n, op.p, Y, Vt);
       };
+  std::optional<Riemannian::LinearOperator<V, V, StiefelCache>> precon;
+  if (minv)
+    precon = [&op, minv, N](const V &Y, const V &Vt, StiefelCache &) {
+      V Z(N);
+      double *z = Z.data();
+      const double *v = Vt.data();
+      oracle::parallel_ranges(N, [&](int, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) z[i] = minv[i] * v[i];
+      });
+      std::vector<double> G(op.p * op.p);
+      gram(Y.data(), Z.data(), op.n, op.p, G.data());
+      symmetrize(G.data(), op.p);
+      V out(N);
+      sub_right_mul(Z.data(), Y.data(), G.data(), op.n, op.p, out.data());
+      return out;
+    };
   try {
     V Y0m(Y0, N);
     auto res = Riemannian::TNT<V, V, double, StiefelCache>(
-        f, QM, metric, retract, Y0m, cache, std::nullopt, make_params(prm));
+        f, QM, metric, retract, Y0m, cache, precon, make_params(prm));
     std::memcpy(Y_out, res.x.data(), N * sizeof(double));
     export_tnt(res, status, n_outer, n_trace, scalars, cap, inner_iterations,
                radius, rho, fvals, gradnorms, step_norms, step_M_norms);
@@ -581,6 +599,15 @@ int ref_stiefel_tnt(void *hh, const double *Y0, const double *prm, double *Y_out
     return 1;
   }
   return 0;
+}
+
+int ref_stiefel_tnt(void *hh, const double *Y0, const double *prm, double *Y_out,
+                    int *status, uint64_t *n_outer, uint64_t *n_trace,
+                    double *scalars, uint64_t cap, uint64_t *inner_iterations,
+                    double *radius, double *rho, double *fvals, double *gradnorms,
+                    double *step_norms, double *step_M_norms) {
+  return ref_stiefel_tnt_precon(hh, Y0, nullptr, prm, Y_out, status, n_outer, n_trace, scalars, cap, inner_iterations,
+                                radius, rho, fvals, gradnorms, step_norms, step_M_norms);
 }
 
 // ---- Sphere Rayleigh quotient (configs C1 / C2) ----------------------------
@@ -627,8 +654,9 @@ int ref_sphere_stpcg(uint64_t n, uint64_t k, const double *d, const double *U,
   return 0;
 }
 
-int ref_sphere_tnt(uint64_t n, uint64_t k, const double *d, const double *U,
-                   const double *sigma, const double *x0, const double *prm,
+// minv (nullable): pointwise Jacobi scaling  precon(x, v) = minv o v  as the reference TNT's `precon` argument
+int ref_sphere_tnt_precon(uint64_t n, uint64_t k, const double *d, const double *U,
+                   const double *sigma, const double *x0, const double *minv, const double *prm,
                    double *x_out, int *status, uint64_t *n_outer,
                    uint64_t *n_trace, double *scalars, uint64_t cap,
                    uint64_t *inner_iterations, double *radius, double *rho,
@@ -689,10 +717,21 @@ int ref_sphere_tnt(uint64_t n, uint64_t k, const double *d, const double *U,
         });
         return z;
       };
+  std::optional<Riemannian::LinearOperator<V, V, SphereCache>> precon;
+  if (minv)
+    precon = [minv, n](const V &, const V &v, SphereCache &) {
+      V out(n);
+      double *o = out.data();
+      const double *vd = v.data();
+      oracle::parallel_ranges(n, [&](int, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) o[i] = minv[i] * vd[i];
+      });
+      return out;
+    };
   try {
     V X0(x0, n);
     auto res = Riemannian::TNT<V, V, double, SphereCache>(
-        f, QM, metric, retract, X0, cache, std::nullopt, make_params(prm));
+        f, QM, metric, retract, X0, cache, precon, make_params(prm));
     std::memcpy(x_out, res.x.data(), n * sizeof(double));
     export_tnt(res, status, n_outer, n_trace, scalars, cap, inner_iterations,
                radius, rho, fvals, gradnorms, step_norms, step_M_norms);
@@ -700,6 +739,17 @@ int ref_sphere_tnt(uint64_t n, uint64_t k, const double *d, const double *U,
     return 1;
   }
   return 0;
+}
+
+int ref_sphere_tnt(uint64_t n, uint64_t k, const double *d, const double *U,
+                   const double *sigma, const double *x0, const double *prm,
+                   double *x_out, int *status, uint64_t *n_outer,
+                   uint64_t *n_trace, double *scalars, uint64_t cap,
+                   uint64_t *inner_iterations, double *radius, double *rho,
+                   double *fvals, double *gradnorms, double *step_norms,
+                   double *step_M_norms) {
+  return ref_sphere_tnt_precon(n, k, d, U, sigma, x0, nullptr, prm, x_out, status, n_outer, n_trace, scalars, cap,
+                               inner_iterations, radius, rho, fvals, gradnorms, step_norms, step_M_norms);
 }
 
 // ---- The reference's own S^2 test problem (tests/TNT_unit_test.cpp:63-122) --
@@ -963,6 +1013,95 @@ int ref_lsqr(uint64_t m, uint64_t n, const double *A, const double *b, uint64_t 
     else std::memset(x_out, 0, n * sizeof(double));
     *xnorm_out = xnorm;
     *num_iterations = iters;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+
+// Reference LSQR on a DIAGONAL operator A = diag(d) (the shape the device check uses: A and A^T are pointwise scalings,
+// ob200_hadamard on the device), n unknowns.
+int ref_lsqr_diag(uint64_t n, const double *d, const double *b, uint64_t max_iterations,
+                  double lambda, double btol, double Atol, double cond_limit, double Delta,
+                  double *x_out, double *xnorm_out, uint64_t *num_iterations) {
+  using V = HostMat;
+  LinearAlgebra::LinearOperator<V, V> Aop = [&](const V &x) {
+    V out(n);
+    for (size_t i = 0; i < n; ++i) out.d[i] = d[i] * x.d[i];
+    return out;
+  };
+  LinearAlgebra::InnerProduct<V> ip = [](const V &a, const V &c) { return oracle::dot(a, c); };
+  try {
+    V B(b, n);
+    double xnorm = 0;
+    size_t iters = 0;
+    V x = LinearAlgebra::LSQR<V>(Aop, Aop, B, ip, xnorm, iters, size_t(max_iterations), lambda, btol,
+                                 Atol, cond_limit, Delta);
+    if (x.size() == n) std::memcpy(x_out, x.data(), n * sizeof(double));
+    else std::memset(x_out, 0, n * sizeof(double));
+    *xnorm_out = xnorm;
+    *num_iterations = iters;
+  } catch (const std::invalid_argument &) {
+    return 1;
+  }
+  return 0;
+}
+
+// Reference EuclideanTNLS (Riemannian/TNLS.h:265-729) on a separable problem every operation of which is a device
+// level-1 kernel:  F(x)_i = (d_i (x_i x_i) + x_i) - b_i,  DF(x) = DF(x)^T = diag(2 (d_i x_i) + 1).
+int ref_tnls_elem(uint64_t n, const double *d, const double *b, const double *x0, uint64_t max_iterations,
+                  double root_tol, double grad_tol, double rel_tol, double step_tol, double Delta_tol,
+                  double *x_out, int *status, uint64_t *n_outer, uint64_t cap, uint64_t *inner_iterations,
+                  double *rho_out, double *radius_out, double *fvals_out, double *f_out, double *gradnorm_out) {
+  using V = HostMat;
+  std::vector<double> jd(n, 0.0);
+  Riemannian::Mapping<V, V> F = [&](const V &x) {
+    V out(n);
+    for (size_t i = 0; i < n; ++i) {
+      const double xx = x.d[i] * x.d[i];
+      const double u = d[i] * xx;
+      out.d[i] = (u + x.d[i]) - b[i];
+    }
+    return out;
+  };
+  Riemannian::JacobianPairFunction<V, V, V> JF = [&](const V &x) {
+    for (size_t i = 0; i < n; ++i) jd[i] = 2.0 * (d[i] * x.d[i]) + 1.0;
+    Riemannian::Jacobian<V, V, V> DF = [&](const V &, const V &v) {
+      V out(n);
+      for (size_t i = 0; i < n; ++i) out.d[i] = jd[i] * v.d[i];
+      return out;
+    };
+    Riemannian::JacobianAdjoint<V, V, V> DFt = [&](const V &, const V &w) {
+      V out(n);
+      for (size_t i = 0; i < n; ++i) out.d[i] = jd[i] * w.d[i];
+      return out;
+    };
+    return std::make_pair(DF, DFt);
+  };
+  Riemannian::TNLSParams<double> params;
+  params.max_iterations = size_t(max_iterations);
+  params.root_tolerance = root_tol;
+  params.gradient_tolerance = grad_tol;
+  params.relative_decrease_tolerance = rel_tol;
+  params.stepsize_tolerance = step_tol;
+  params.Delta_tolerance = Delta_tol;
+  try {
+    V X0(x0, n);
+    const std::optional<Riemannian::TNLSPreconditioner<V, V>> no_precon;
+    auto res = Riemannian::EuclideanTNLS<V>(F, JF, X0, no_precon, params);
+    std::memcpy(x_out, res.x.data(), n * sizeof(double));
+    *status = int(res.status);
+    *n_outer = res.inner_iterations.size();
+    for (size_t i = 0; i < res.inner_iterations.size() && i < cap; ++i) {
+      inner_iterations[i] = res.inner_iterations[i];
+      rho_out[i] = res.rho[i];
+    }
+    for (size_t i = 0; i < res.trust_region_radius.size() && i < cap; ++i) {
+      radius_out[i] = res.trust_region_radius[i];
+      fvals_out[i] = res.objective_values[i];
+    }
+    *f_out = res.f;
+    *gradnorm_out = res.gradfx_norm;
   } catch (const std::invalid_argument &) {
     return 1;
   }

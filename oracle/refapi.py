@@ -171,13 +171,15 @@ class RefOracle:
             raise ValueError("std::invalid_argument from reference STPCG")
         return s, float(mn.value), int(it.value)
 
-    def sphere_tnt(self, prob, x0, params=None, cap=2048):
+    def sphere_tnt(self, prob, x0, params=None, cap=2048, minv=None):
+        """minv: pointwise Jacobi preconditioner precon(x, v) = minv o v (None: no preconditioner)."""
         p = params or default_tnt_params()
         tb = _TraceBufs(cap)
         x = np.zeros(prob.n)
-        rc = self.lib.ref_sphere_tnt(C.c_uint64(prob.n), C.c_uint64(prob.k), _d(prob.d),
-                                     _d(prob.U), _d(prob.sigma), _d(x0), _d(_prm(p)), _d(x),
-                                     *tb.args())
+        mv = None if minv is None else np.ascontiguousarray(minv, dtype=np.float64)
+        rc = self.lib.ref_sphere_tnt_precon(C.c_uint64(prob.n), C.c_uint64(prob.k), _d(prob.d),
+                                            _d(prob.U), _d(prob.sigma), _d(x0), _d(mv), _d(_prm(p)), _d(x),
+                                            *tb.args())
         if rc:
             raise ValueError("std::invalid_argument from reference TNT")
         return tb.result(x)
@@ -261,6 +263,43 @@ class RefOracle:
                     rho=rho[:k].tolist(), trust_region_radius=rad[:nrec].tolist(), objective_values=fv[:nrec].tolist(),
                     f=f.value, gradfx_norm=gn.value)
 
+    def lsqr_diag(self, d, b, max_iterations=1000, lam=0.0, btol=1e-6, Atol=1e-6, cond_limit=1e8, Delta=None):
+        """Reference LSQR on A = diag(d) (the device check's operator shape)."""
+        n = d.size
+        x = np.zeros(n)
+        xn, it = C.c_double(0), C.c_uint64(0)
+        dd = C.c_double
+        self.lib.ref_lsqr_diag.argtypes = [C.c_uint64, _dp, _dp, C.c_uint64, dd, dd, dd, dd, dd, _dp, C.POINTER(dd), _u64p]
+        rc = self.lib.ref_lsqr_diag(n, _d(d), _d(b), max_iterations, lam, btol, Atol, cond_limit,
+                                    np.finfo(np.float64).max if Delta is None else Delta, _d(x), C.byref(xn), C.byref(it))
+        if rc:
+            raise ValueError("std::invalid_argument from reference LSQR")
+        return x, float(xn.value), int(it.value)
+
+    def tnls_elem(self, d, b, x0, max_iterations=100, root_tol=1e-6, grad_tol=1e-6, rel_tol=1e-6, step_tol=1e-6,
+                  Delta_tol=1e-6, cap=256):
+        """Reference EuclideanTNLS on F(x) = (d o x o x + x) - b (separable; every operation a device level-1 kernel)."""
+        n = d.size
+        x = np.zeros(n)
+        st, no = C.c_int(-1), C.c_uint64(0)
+        inner = np.zeros(cap, dtype=np.uint64)
+        rho, rad, fv = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        f, gn = C.c_double(0), C.c_double(0)
+        dd = C.c_double
+        self.lib.ref_tnls_elem.argtypes = [C.c_uint64, _dp, _dp, _dp, C.c_uint64, dd, dd, dd, dd, dd, _dp,
+                                           C.POINTER(C.c_int), _u64p, C.c_uint64, _u64p, _dp, _dp, _dp,
+                                           C.POINTER(dd), C.POINTER(dd)]
+        rc = self.lib.ref_tnls_elem(n, _d(d), _d(b), _d(np.ascontiguousarray(x0, dtype=np.float64)), max_iterations,
+                                    root_tol, grad_tol, rel_tol, step_tol, Delta_tol, _d(x), C.byref(st), C.byref(no), cap,
+                                    inner.ctypes.data_as(_u64p), _d(rho), _d(rad), _d(fv), C.byref(f), C.byref(gn))
+        if rc:
+            raise ValueError("std::invalid_argument from reference TNLS")
+        k = int(no.value)
+        nrec = min(cap, k + 1)
+        return dict(x=x, status_code=st.value, inner_iterations=inner[:k].astype(int).tolist(), rho=rho[:k].tolist(),
+                    trust_region_radius=rad[:nrec].tolist(), objective_values=fv[:nrec].tolist(), f=f.value,
+                    gradfx_norm=gn.value)
+
     def sphere_gd(self, prob, x0, max_iterations=100, gradient_tolerance=1e-6):
         x = np.zeros(prob.n)
         st, it, ls = C.c_int(-1), C.c_uint64(0), C.c_uint64(0)
@@ -319,12 +358,15 @@ class RefStiefel:
             raise ValueError("std::invalid_argument from reference STPCG")
         return s, float(mn.value), int(it.value)
 
-    def tnt(self, Y0, params=None, cap=2048):
+    def tnt(self, Y0, params=None, cap=2048, minv=None):
+        """minv: elementwise scaling of the projected Jacobi preconditioner precon(Y, V) = P_Y(minv o V) (None: no
+        preconditioner)."""
         p = params or default_tnt_params()
         tb = _TraceBufs(cap)
         Y = np.zeros_like(Y0)
-        rc = self.ora.lib.ref_stiefel_tnt(C.c_void_p(self.h), _d(Y0), _d(_prm(p)), _d(Y),
-                                          *tb.args())
+        mv = None if minv is None else np.ascontiguousarray(minv, dtype=np.float64)
+        rc = self.ora.lib.ref_stiefel_tnt_precon(C.c_void_p(self.h), _d(Y0), _d(mv),
+                                                 _d(_prm(p)), _d(Y), *tb.args())
         if rc:
             raise ValueError("std::invalid_argument from reference TNT")
         return tb.result(Y)

@@ -130,6 +130,24 @@ def main():
     r = R.sphere_gd(prob, prob.x0, max_iterations=60, gradient_tolerance=1e-6)      # prob = make_sphere(100, 16)
     arrays["sphere100_gd_x"] = r.pop("x")
     out["sphere100_gd"] = r
+    # --- TNT with a preconditioner (reference TNT.h:247, adapter l.413-426) on the device model shapes ----------
+    prob = P.make_sphere(100, 16)
+    r = R.sphere_tnt(prob, prob.x0, default_tnt_params(), minv=1.0 / (2.0 * prob.d))      # pointwise Jacobi
+    arrays["sphere100_tnt_jacobi_x"] = r.pop("x")
+    out["sphere100_tnt_jacobi"] = r
+    prob = P.make_stiefel(512, 32, y_noise=.1)
+    r = R.stiefel(prob).tnt(prob.Y0, default_tnt_params(), minv=P.stiefel_row_scaling(512, 32))   # P_Y(minv o V)
+    arrays["stiefel512_yn1_tnt_pjacobi_x"] = r.pop("x")
+    out["stiefel512_yn1_tnt_pjacobi"] = r
+    # --- LSQR / TNLS on device-shaped (pointwise) operators: tests/host/lsq_device_check.cpp ---------------------
+    case = P.device_lsq_case(5000)
+    x, xn, it = R.lsqr_diag(case["d"], case["b"], **case["lsqr"])
+    out["lsqr_diag5000"] = dict(xnorm=xn, num_iterations=it, args=case["lsqr"])
+    arrays["lsqr_diag5000_x"] = x
+    r = R.tnls_elem(case["d"], case["c"], case["x0"], **case["tnls"])
+    arrays["tnls_elem5000_x"] = r.pop("x")
+    r["args"] = case["tnls"]
+    out["tnls_elem5000"] = r
     with open(os.path.join(HERE, "golden.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "golden_arrays.npz"), **arrays)
