@@ -205,7 +205,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   __shared__ CgShared sh;
   __shared__ double s_part[16];
   __shared__ double s_invq, s_q;
-  __shared__ double s_lmax[16];
+  __shared__ int s_lmax[16];
   __shared__ int s_next_strip;
   __shared__ __align__(8) uint64_t s_bmb[16];   // phase B: one mbarrier per warp (strip staging)
   __shared__ int s_fe[5];      // fixacc exponents: <p,W>, <W,W>, <p,p>, <p,r>, <r,r>
@@ -319,7 +319,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
       int E_prev = 0;
       for (int i = 0; i <= nb_local; ++i) {
         const unsigned u = use + i;
-        int E_cur = 0;
+        int E_cur = 0, pe_cur = 0;
         if (i < nb_local) {
           const unsigned b = bfirst + i, r0 = b * ST_NB;
           TL(0);
@@ -342,6 +342,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
             mbar_expect_tx(&mb[MB_A_FULL], TC_ABLOCK);
             bulk_g2s(Asm, planes + b * (size_t)TC_ABLOCK, TC_ABLOCK, &mb[MB_A_FULL]);
           }
+          pe_cur = __ldg(plane_exp + b);        // (with the loads below: its L2 round trip is hidden, not in the read-back)
           double2 rv[8], po[8];
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) {      // all 16 loads of this thread in flight at once
@@ -354,7 +355,8 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
             }
           }
           double p[8][2];
-          double pp = 0.0, pr = 0.0, mx = 0.0;
+          double pp = 0.0, pr = 0.0;
+          int mxh = 0;                          // block maximum of |p| through the (ordered) high words
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) {
             const unsigned grow = r0 + 8 * g + ii;
@@ -375,7 +377,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
             }
             p[ii][0] = pv.x;
             p[ii][1] = pv.y;
-            mx = fmax(mx, fmax(fabs(pv.x), fabs(pv.y)));
+            mxh = max(mxh, max(__double2hiint(pv.x) & 0x7fffffff, __double2hiint(pv.y) & 0x7fffffff));
           }
           TL(1);
           // next block's r, p_old, Y and A digit planes -> L2, issued AFTER this block's demand loads have
@@ -383,16 +385,16 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           // exact-reduction unit: this lane's 8 x 2 elements
           fixacc_add(fa0, pp, fq0, ovf);
           fixacc_add(fa1, pr, fq1, ovf);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          if (lane == 0) s_lmax[(u & 1) * 8 + warp] = mx;
+          mxh = __reduce_max_sync(0xffffffffu, mxh);
+          if (lane == 0) s_lmax[(u & 1) * 8 + warp] = mxh;
           nbar_sync(NB_LSYNC, 256);
-          mx = s_lmax[(u & 1) * 8];
+          mxh = s_lmax[(u & 1) * 8];
 #pragma unroll
-          for (int w = 1; w < 8; ++w) mx = fmax(mx, s_lmax[(u & 1) * 8 + w]);
-          // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums)
-          const int E = (mx > 0.0) ? (int)((__double_as_longlong(mx) >> 52) & 0x7ff) - 1023 + 1 : 0;
-          E_cur = E;
+          for (int w = 1; w < 8; ++w) mxh = max(mxh, s_lmax[(u & 1) * 8 + w]);
+          // |p| < 2^E over the block (non-finite data: the Kulisch accumulators flag the partial sums); a block of
+          // zeros or subnormals (biased exponent 0) takes E = 0
+          const int E = (mxh >> 20) ? (mxh >> 20) - 1023 + 1 : 0;
+          E_cur = E + pe_cur;   // exponent of the block's product scale: block maximum of p + plane exponent of A
           TL(2);
           if (i > 0) {   // MMAs of block u-1 complete: digit image and A image are free again
             mbar_wait(&mb[MB_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);
@@ -429,7 +431,7 @@ tcg_stiefel_tc_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
           double out[16];
           recombine_row16(tmem_base + (v & 1) * TC_TMEM_COLS + ((uint32_t)(32 * q4) << 16) + 16 * chalf, out);
           tc_fence_before();
-          const double sc = scalbn(1.0, __ldg(plane_exp + bfirst + i - 1) + E_prev + 10);
+          const double sc = scalbn(1.0, E_prev + 10);
           double *wrow = Wsm + (v & 1) * (ST_NB * WS) + tc_row_of_lane((uint32_t)(32 * q4 + lane)) * WS + 16 * chalf;
 #pragma unroll
           for (int c = 0; c < 16; c += 2) *reinterpret_cast<double2 *>(wrow + c) = make_double2(out[c] * sc, out[c + 1] * sc);

@@ -41,6 +41,7 @@ constexpr int V6_WORK = 512;                                   // L + M + G thre
 constexpr uint32_t V6_A = 0;                                   // 48 KB int8 digit planes of A
 constexpr uint32_t V6_Q = V6_A + TC_ABLOCK;                    // 28 KB int8 digit image of p
 constexpr uint32_t V6_TILE = ST_NB * ST_P * 8;                 // 32 KB dense fp64 tile
+constexpr uint32_t V6_HALF = V6_TILE / 2;                      // 16 KB: one 64-row half of it
 constexpr uint32_t V6_R = V6_Q + TC_QBYTES;                    // r tile (TMA)
 constexpr uint32_t V6_PO = V6_R + V6_TILE;                     // p_old tile (TMA), overwritten in place with p
 constexpr uint32_t V6_WB = ST_NB * WS * 8;                     // 36 KB padded tile
@@ -50,7 +51,7 @@ constexpr uint32_t V6_S = V6_Y + V6_WB;                        // -S, rows in fr
 constexpr uint32_t V6_ACC = V6_S + ST_P * WS * 8;              // CTA Kulisch accumulators (5 scalars)
 constexpr uint32_t V6_NACC = 5;
 constexpr uint32_t V6_BAR = V6_ACC + V6_NACC * KUL_STRIDE * 8; // mbarriers
-constexpr uint32_t V6_NBAR = 32;
+constexpr uint32_t V6_NBAR = 40;
 constexpr uint32_t V6_MISC = V6_BAR + V6_NBAR * 8;
 constexpr uint32_t V6_MISC_BYTES = 768;
 constexpr uint32_t V6_TOTAL = V6_MISC + V6_MISC_BYTES;
@@ -64,8 +65,10 @@ static_assert(V6_GRAW >= V6_W && V6_GRAW + 8192 <= V6_Y, "G scratch must sit in 
 static_assert(ST_P * GS * 8 <= V6_WB, "G must fit the Y tile region");
 static_assert(V6_TOTAL + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
 
-enum { B6_RP_FULL = 0, B6_R_EMPTY = 1, B6_A_FULL = 2, B6_Q_FULL = 3, B6_MMA_DONE = 4 /*,5*/, B6_TMEM_EMPTY = 6 /*,7*/,
-       B6_SLOT = 8 /* .. 23 */, B6_W_FULL = 24 /*,25*/, B6_W_EMPTY = 26 /*,27*/, B6_PO_EMPTY = 28 };
+// (the stage works in 64-row halves: r / p_old of half h stream in while the other half is being sliced)
+enum { B6_A_FULL = 2, B6_Q_FULL = 3, B6_MMA_DONE = 4 /*,5*/, B6_TMEM_EMPTY = 6 /*,7*/,
+       B6_SLOT = 8 /* .. 23 */, B6_W_FULL = 24 /*,25*/, B6_W_EMPTY = 26 /*,27*/,
+       B6_RP_FULL = 28 /*,29*/, B6_R_EMPTY = 30 /*,31*/, B6_PO_EMPTY = 32 /*,33*/, B6_P_FULL = 34 /*,35*/ };
 
 struct V6Misc {
   CgShared sh;
@@ -273,15 +276,31 @@ __device__ __forceinline__ void v6_run_service(const TcgCommon &a, const Stiefel
       fence_proxy_async_global_v6();   // r / p written with generic stores by other CTAs (ordered by the grid barrier)
       for (int i = 0; i < pt.nb_local; ++i) {
         const unsigned u = use + i, b = pt.bfirst + i, r0 = b * ST_NB;
-        const unsigned rows = n_rows32 - r0 < ST_NB ? n_rows32 - r0 : ST_NB;
-        const uint32_t bytes = rows * ST_P * (uint32_t)sizeof(double);
-        const size_t off = (size_t)r0 * ST_P;
         TL6(0);
-        if (u > 0) mbar_wait_guarded(&mb[B6_R_EMPTY], (u - 1) & 1);           // L has read r of the previous block
-        TL6(1);
-        mbar_expect_tx(&mb[B6_RP_FULL], k ? 2 * bytes : bytes);
-        bulk_g2s(base + V6_R, a.r + off, bytes, &mb[B6_RP_FULL]);
-        if (i + 1 < pt.nb_local) {   // what the next block needs that is not fetched early: A planes, Y; then r / p_old one further
+        // demand loads first (the TMA unit serves its queue in order), half by half: r into the half L has read, p_old
+        // into the half M has taken p from
+#pragma unroll 1
+        for (unsigned h = 0; h < 2; ++h) {
+          const unsigned rh = r0 + 64u * h;
+          const unsigned rows_h = rh < n_rows32 ? (n_rows32 - rh < 64u ? n_rows32 - rh : 64u) : 0u;
+          const uint32_t bytes_h = rows_h * ST_P * (uint32_t)sizeof(double);
+          const size_t off_h = (size_t)rh * ST_P;
+          if (u > 0) mbar_wait_guarded(&mb[B6_R_EMPTY + h], (u - 1) & 1);       // L has read r of this half (previous block)
+          if (h == 0) TL6(1);
+          mbar_expect_tx(&mb[B6_RP_FULL + h], k ? 2 * bytes_h : bytes_h);
+          if (bytes_h) bulk_g2s(base + V6_R + h * V6_HALF, a.r + off_h, bytes_h, &mb[B6_RP_FULL + h]);
+          if (k) {
+            if (u > 0) mbar_wait_guarded(&mb[B6_PO_EMPTY + h], (u - 1) & 1);    // M has taken p of this half (previous block)
+            fence_proxy_async_smem();   // L's generic-proxy stores of p into this half are ordered before the async-proxy write
+            if (bytes_h) bulk_g2s(base + V6_PO + h * V6_HALF, p_old + off_h, bytes_h, &mb[B6_RP_FULL + h]);
+          }
+          if (h == 0) TL6(2);
+        }
+        if (u > 0) mbar_wait_guarded(&mb[B6_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // A image free
+        mbar_expect_tx(&mb[B6_A_FULL], TC_ABLOCK);
+        bulk_g2s(Asm, planes + (size_t)b * TC_ABLOCK, TC_ABLOCK, &mb[B6_A_FULL]);
+        TL6(3);
+        if (i + 1 < pt.nb_local) {   // L2 prefetch of what the next blocks need: A planes, Y; then r / p_old one further
           const unsigned rn = r0 + ST_NB;
           const unsigned rows1 = n_rows32 - rn < ST_NB ? n_rows32 - rn : ST_NB;
           const uint32_t bytes1 = rows1 * ST_P * (uint32_t)sizeof(double);
@@ -294,15 +313,6 @@ __device__ __forceinline__ void v6_run_service(const TcgCommon &a, const Stiefel
             bulk_prefetch_l2_v6(a.r + (size_t)r2 * ST_P, bytes2);
             if (k) bulk_prefetch_l2_v6(p_old + (size_t)r2 * ST_P, bytes2);
           }
-        }
-        TL6(2);
-        if (u > 0) mbar_wait_guarded(&mb[B6_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // A image free
-        mbar_expect_tx(&mb[B6_A_FULL], TC_ABLOCK);
-        bulk_g2s(Asm, planes + (size_t)b * TC_ABLOCK, TC_ABLOCK, &mb[B6_A_FULL]);
-        TL6(3);
-        if (k) {
-          if (u > 0) mbar_wait_guarded(&mb[B6_PO_EMPTY], (u - 1) & 1);        // M has taken p of the previous block
-          bulk_g2s(base + V6_PO, p_old + off, bytes, &mb[B6_RP_FULL]);
         }
         TL6(9);
       }
@@ -397,7 +407,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
       // It is a deterministic function of exactly reduced data (identical on every CTA / GPU that handles the block) and
       // at most a few bits above the true maximum: p is quantised to 2^(E-54), i.e. no coarser than ~2^-52 of the
       // block maximum.
-      const int t = rt, cp = t & 15, g = t >> 4;             // columns cp, cp + 16 ; rows 16g .. 16g+15 of the block
+      const int t = rt, cp = t & 15, g = t >> 4;             // columns cp, cp + 16 ; rows 8g .. 8g+7 of a 64-row half
       // (a half warp reads / writes 16 consecutive doubles of a row: conflict-free shared memory, full HBM sectors)
       FixAcc fa0 = {0, 0}, fa1 = {0, 0};                     // <p,p>, <p,r>
       const int fe0 = ms.s_fe[SC_PP], fe1 = ms.s_fe[SC_PR];
@@ -423,70 +433,71 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
       double bound_next = nb_local > 0 ? block_bound(bfirst) : 0.0;
       for (int i = 0; i < nb_local; ++i) {
         const unsigned u = use + i, b = bfirst + i, r0 = b * ST_NB;
-        const unsigned hh = 2u * b + (unsigned)(g >> 2);     // this thread's half block
-        const bool mine = hh >= h0 && hh < h1;
-        const unsigned char *rrow = Rsm + (16u * g) * 256u + 8u * cp;
-        unsigned char *prow = POsm + (16u * g) * 256u + 8u * cp;
         const double bound = bound_next;
         if (i + 1 < nb_local) bound_next = block_bound(b + 1);
         const int E = (bound > 0.0) ? (int)((__double_as_longlong(bound) >> 52) & 0x7ff) - 1023 + 1 : 0;
         const double scale = scalbn(1.0, 54 - E);
         if (t == 0 && 2u * b >= h0) __stcg(Rnext + b, 0ull);           // max |r| of the NEXT iteration starts from zero
         if (t == 0) TL6(10);
-        mbar_wait_guarded(&mb[B6_RP_FULL], u & 1);
-        if (t == 0) { TL6(11); TLI(0); }
-        if (u > 0) {
-          mbar_wait_guarded(&mb[B6_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // digit image free
-          if (!kk) mbar_wait_guarded(&mb[B6_PO_EMPTY], (u - 1) & 1);   // first iteration: no TMA into the p tile orders this
-        }
-        if (t == 0) TL6(12);
+        if (u > 0) mbar_wait_guarded(&mb[B6_MMA_DONE + ((u - 1) & 1)], ((u - 1) >> 1) & 1);   // digit image free
         int mxb = 0;
 #pragma unroll 1
-        for (int z = 0; z < 2; ++z) {                        // one column of the pair at a time (not unrolled: code size)
-          uint32_t lo[16], hi[16];
-          double pp0 = 0.0, pp1 = 0.0, pr0 = 0.0, pr1 = 0.0;
+        for (unsigned h = 0; h < 2; ++h) {                   // the two 64-row halves of the block, as they arrive
+          const bool mine = 2u * b + h >= h0 && 2u * b + h < h1;
+          const unsigned char *rrow = Rsm + h * V6_HALF + (8u * g) * 256u + 8u * cp;
+          unsigned char *prow = POsm + h * V6_HALF + (8u * g) * 256u + 8u * cp;
+          mbar_wait_guarded(&mb[B6_RP_FULL + h], u & 1);
+          if (t == 0 && h == 0) { TL6(11); TLI(0); }
+          if (!kk && u > 0) mbar_wait_guarded(&mb[B6_PO_EMPTY + h], (u - 1) & 1);   // first iteration: no TMA into the p tile orders this
+          if (t == 0 && h == 0) TL6(12);
+#pragma unroll 1
+          for (int z = 0; z < 2; ++z) {                      // one column of the pair at a time (not unrolled: code size)
+            uint32_t lo[8], hi[8];
+            double pp0 = 0.0, pp1 = 0.0, pr0 = 0.0, pr1 = 0.0;
 #pragma unroll
-          for (int ii = 0; ii < 16; ++ii) {
-            if ((ii & 7) == 0) asm volatile("" ::: "memory");   // at most eight rows' operands in flight (register budget)
-            const unsigned grow = r0 + 16u * g + ii;
-            const bool valid = grow < n_rows32, ok = valid && mine;
-            // branch-free (selects): rows beyond n and, in the first iteration, the p_old tile hold stale shared memory
-            double rv = *reinterpret_cast<const double *>(rrow + ii * 256u + 128u * z);
-            double po = *reinterpret_cast<const double *>(prow + ii * 256u + 128u * z);
-            rv = valid ? rv : 0.0;
-            po = (valid && kk) ? po : 0.0;
-            const double pv = fma(beta, po, -rv);                    // l.420; first iteration: beta = 0, p = -r (l.256)
-            *reinterpret_cast<double *>(prow + ii * 256u + 128u * z) = pv;   // the M role takes its fragments from here
-            if (ok) __stcg(p_new + (size_t)grow * ST_P + cp + 16 * z, pv);
-            const double pm = ok ? pv : 0.0;
-            if (ii & 1) { pp1 = fma(pm, pm, pp1); pr1 = fma(pm, rv, pr1); }
-            else        { pp0 = fma(pm, pm, pp0); pr0 = fma(pm, rv, pr0); }
-            mxb = max(mxb, __double2hiint(pv) & 0x7fffffff);   // high word of |pv|: an ordered integer
-            const unsigned long long uu = ((unsigned long long)__double2ll_rn(pv * scale) + TC_DIGIT_BIAS) ^ TC_DIGIT_BIAS;
-            lo[ii] = (uint32_t)uu;
-            hi[ii] = (uint32_t)(uu >> 32);
-          }
-          if (t == 0) TL6(13 + z);
-          // exact-reduction unit: this thread's 16 elements of one column (inside one half block)
-          fixacc_add(fa0, pp0 + pp1, fq0, ovf);
-          fixacc_add(fa1, pr0 + pr1, fq1, ovf);
-          const uint32_t off = sw128_chunk_off((uint32_t)(cp + 16 * z), (uint32_t)g);
-#pragma unroll
-          for (int sl = 0; sl < TC_SLICES; ++sl) {
-            const int d = 6 - sl;                                   // digit index held by slice sl
-            const uint32_t sel = (d & 3) | (((d & 3) + 4) << 4);    // byte d of a -> pos 0, byte d of b -> pos 1
-            uint32_t wq[4];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint32_t x0 = d < 4 ? lo[4 * q4] : hi[4 * q4], x1 = d < 4 ? lo[4 * q4 + 1] : hi[4 * q4 + 1];
-              const uint32_t x2 = d < 4 ? lo[4 * q4 + 2] : hi[4 * q4 + 2], x3 = d < 4 ? lo[4 * q4 + 3] : hi[4 * q4 + 3];
-              const uint32_t t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
-              wq[q4] = __byte_perm(t01, t23, 0x5410);
+            for (int ii = 0; ii < 8; ++ii) {
+              const unsigned grow = r0 + 64u * h + 8u * g + ii;
+              const bool valid = grow < n_rows32, ok = valid && mine;
+              // branch-free (selects): rows beyond n and, in the first iteration, the p_old tile hold stale shared memory
+              double rv = *reinterpret_cast<const double *>(rrow + ii * 256u + 128u * z);
+              double po = *reinterpret_cast<const double *>(prow + ii * 256u + 128u * z);
+              rv = valid ? rv : 0.0;
+              po = (valid && kk) ? po : 0.0;
+              const double pv = fma(beta, po, -rv);                    // l.420; first iteration: beta = 0, p = -r (l.256)
+              *reinterpret_cast<double *>(prow + ii * 256u + 128u * z) = pv;   // the M role takes its fragments from here
+              if (ok) __stcg(p_new + (size_t)grow * ST_P + cp + 16 * z, pv);
+              const double pm = ok ? pv : 0.0;
+              if (ii & 1) { pp1 = fma(pm, pm, pp1); pr1 = fma(pm, rv, pr1); }
+              else        { pp0 = fma(pm, pm, pp0); pr0 = fma(pm, rv, pr0); }
+              mxb = max(mxb, __double2hiint(pv) & 0x7fffffff);   // high word of |pv|: an ordered integer
+              const unsigned long long uu = ((unsigned long long)__double2ll_rn(pv * scale) + TC_DIGIT_BIAS) ^ TC_DIGIT_BIAS;
+              lo[ii] = (uint32_t)uu;
+              hi[ii] = (uint32_t)(uu >> 32);
             }
-            *reinterpret_cast<uint4 *>(Qsm + sl * TC_QTILE + off) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+            if (t == 0 && h == 0) TL6(13 + z);
+            // exact-reduction unit: this thread's 8 elements of one column
+            fixacc_add(fa0, pp0 + pp1, fq0, ovf);
+            fixacc_add(fa1, pr0 + pr1, fq1, ovf);
+            // rows k = 64 h + 8 g .. + 7 of column n: the 8-byte half (g & 1) of k-chunk 4 h + (g >> 1)
+            const uint32_t off = sw128_chunk_off((uint32_t)(cp + 16 * z), 4u * h + (uint32_t)(g >> 1)) + 8u * (uint32_t)(g & 1);
+#pragma unroll
+            for (int sl = 0; sl < TC_SLICES; ++sl) {
+              const int d = 6 - sl;                                   // digit index held by slice sl
+              const uint32_t sel = (d & 3) | (((d & 3) + 4) << 4);    // byte d of a -> pos 0, byte d of b -> pos 1
+              uint32_t wq[2];
+#pragma unroll
+              for (int q4 = 0; q4 < 2; ++q4) {
+                const uint32_t x0 = d < 4 ? lo[4 * q4] : hi[4 * q4], x1 = d < 4 ? lo[4 * q4 + 1] : hi[4 * q4 + 1];
+                const uint32_t x2 = d < 4 ? lo[4 * q4 + 2] : hi[4 * q4 + 2], x3 = d < 4 ? lo[4 * q4 + 3] : hi[4 * q4 + 3];
+                const uint32_t t01 = __byte_perm(x0, x1, sel), t23 = __byte_perm(x2, x3, sel);
+                wq[q4] = __byte_perm(t01, t23, 0x5410);
+              }
+              *reinterpret_cast<uint2 *>(Qsm + sl * TC_QTILE + off) = make_uint2(wq[0], wq[1]);
+            }
           }
+          mbar_arrive(&mb[B6_R_EMPTY + h]);                   // this half of the r tile may be refilled with the next block
+          mbar_arrive(&mb[B6_P_FULL + h]);                    // p of this half is in the stage: M may take its fragments
         }
-        mbar_arrive(&mb[B6_R_EMPTY]);                         // the r tile may be refilled with the next block
         fence_proxy_async_smem();
         if (t == 0) ms.s_E[u & 3] = E;
         mbar_arrive(&mb[B6_Q_FULL]);
@@ -516,16 +527,16 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
         const unsigned hh = 2u * b + (unsigned)g16;
         const bool own = hh >= h0 && hh < h1;
         if (tid == 256) TL6(21);
-        // L has finished block u: p is in the stage (release / acquire through the Q_FULL mbarrier; L cannot be more
-        // than one block ahead of this role, so the parity is unambiguous)
-        mbar_wait_guarded(&mb[B6_Q_FULL], u & 1);
+        // L has finished this warp's half of block u: p is in the stage (release / acquire through the P_FULL mbarrier;
+        // L cannot be more than one block ahead of this role, so the parity is unambiguous)
+        mbar_wait_guarded(&mb[B6_P_FULL + g16], u & 1);
         if (tid == 256) TL6(22);
         // rows 16 qd + m and + 8 of the half as fp64 MMA A fragments: paf[ks][2 c + s] = p[row 8 s + m][16 ks + 4 j + c]
         double paf[2][8];
         if (own) {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const unsigned char *prow = POsm + (64u * g16 + 16u * qd + 8u * s + m) * 256u + 32u * j;
+            const unsigned char *prow = POsm + g16 * V6_HALF + (16u * qd + 8u * s + m) * 256u + 32u * j;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const double2 v01 = *reinterpret_cast<const double2 *>(prow + 128u * ks);
@@ -534,7 +545,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
             }
           }
         }
-        mbar_arrive(&mb[B6_PO_EMPTY]);                        // the stage's p tile may be refilled (p_old of the next block)
+        mbar_arrive(&mb[B6_PO_EMPTY + g16]);                  // this half of the p tile may be refilled (p_old of the next block)
         if (tid == 256) { TL6(26); TLI(2); }
         if (own) {
           // T = -p S while the tensor cores multiply (Ssm holds -S, rows in fragment order), small fp64 MMAs (m8n8k4: a
@@ -955,9 +966,12 @@ tcg_stiefel_v6_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     ms.s_fe[SC_PP] = fixacc_exponent(a.rv0);                                             // ||p||^2 = pk_M_2 (l.266)
     ms.s_fe[SC_PR] = fixacc_exponent(a.rv0);                                             // |<p,r>| <= ||p|| ||r||
     ms.s_fe[SC_RV] = 0;
-    mbar_init(&mb[B6_RP_FULL], 1);
-    mbar_init(&mb[B6_R_EMPTY], 128);
-    mbar_init(&mb[B6_PO_EMPTY], 256);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&mb[B6_RP_FULL + h], 1);
+      mbar_init(&mb[B6_R_EMPTY + h], 128);
+      mbar_init(&mb[B6_PO_EMPTY + h], 128);
+      mbar_init(&mb[B6_P_FULL + h], 128);
+    }
     mbar_init(&mb[B6_A_FULL], 1);
     mbar_init(&mb[B6_Q_FULL], 128);
     mbar_init(&mb[B6_MMA_DONE], 1);
