@@ -134,6 +134,9 @@ struct ob200_context {
   TcgDeviceResult *dres = nullptr;
   double *dscal = nullptr;        // 8 doubles
   double *dmat = nullptr;         // 2 * 32*32 doubles (S, M)
+  double *drot = nullptr;         // v6 kernel: Q | Q^T | lambda (eigen-decomposition of S), 3 * 32*32 doubles
+  double *yrot = nullptr;         // v6 kernel: Y Q (n x 32)
+  size_t yrot_capacity = 0;
   unsigned long long *dbits = nullptr;
   // pinned host mirrors
   TcgDeviceResult *hres = nullptr;
@@ -219,6 +222,7 @@ int ob200_create(int device, void *stream, ob200_context **out) {
   CK(cudaMalloc(&ctx->dres, sizeof(TcgDeviceResult)));
   CK(cudaMalloc(&ctx->dscal, sizeof(double) * 8));
   CK(cudaMalloc(&ctx->dmat, sizeof(double) * 2 * 32 * 32));
+  CK(cudaMalloc(&ctx->drot, sizeof(double) * 3 * 32 * 32));
   CK(cudaMalloc(&ctx->dbits, 64));
   CK(cudaMalloc(&ctx->dsum, 8));
   CK(cudaMallocHost(&ctx->hsum, 8));
@@ -241,6 +245,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->r); cudaFree(ctx->p0); cudaFree(ctx->p1); cudaFree(ctx->Hp); cudaFree(ctx->gs);
   cudaFree(ctx->acc); cudaFree(ctx->barrier); cudaFree(ctx->dres); cudaFree(ctx->dscal);
+  cudaFree(ctx->drot); cudaFree(ctx->yrot);
   cudaFree(ctx->dmat); cudaFree(ctx->dbits); cudaFree(ctx->dsum); cudaFreeHost(ctx->hsum);
   cudaFreeHost(ctx->hres); cudaFreeHost(ctx->hscal); cudaFreeHost(ctx->hacc); cudaFreeHost(ctx->hmat);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -646,6 +651,44 @@ static int sparse_args(ob200_context *ctx, const ob200_operator *H, SparseArgs *
   return OB200_OK;
 }
 
+// Eigen-decomposition S = Q diag(lam) Q^T of a symmetric 32 x 32 matrix (cyclic Jacobi, host, deterministic): the v6
+// Stiefel kernel solves in the eigenbasis of S, where  p S  is an elementwise shift.
+static void jacobi_eig32(const double *S, double *Q, double *lam) {
+  const int P = 32;
+  double A[32][32];
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j < P; ++j) { A[i][j] = 0.5 * (S[i * P + j] + S[j * P + i]); Q[i * P + j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dia = 0.0;
+    for (int i = 0; i < P; ++i) { dia += A[i][i] * A[i][i]; for (int j = i + 1; j < P; ++j) off += A[i][j] * A[i][j]; }
+    if (off <= 1e-36 * dia || off == 0.0) break;
+    for (int p = 0; p < P - 1; ++p)
+      for (int q = p + 1; q < P; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < P; ++k) {   // A <- A J
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < P; ++k) {   // A <- J^T A
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < P; ++k) {   // Q <- Q J
+          const double qkp = Q[k * P + p], qkq = Q[k * P + q];
+          Q[k * P + p] = c * qkp - sn * qkq;
+          Q[k * P + q] = sn * qkp + c * qkq;
+        }
+      }
+  }
+  for (int i = 0; i < P; ++i) lam[i] = A[i][i];
+}
+
 static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
                         const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
   int rc = check_params(ctx, prm);
@@ -684,10 +727,41 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   if (want_tc && (rc = planes_checksum_async(ctx, H->A_bf16_dev, H->n))) return rc;   // validated after the sync below
   const uint64_t launches0 = ctx->launches;
   cudaStream_t st = ctx->stream;
+  // v6 kernel: the solve runs in the eigenbasis of S = Q Lambda Q^T -- g~ = g Q, Y~ = Y Q, s = s~ Q^T.  The iteration is
+  // the same Steihaug-Toint loop on an orthogonally rotated copy of the problem (Frobenius products, the projection and
+  // the trust-region norm are invariant), with  p S  reduced to an elementwise shift.
+  const bool rotate = want_tc && ctx->opt_tcgen05 == 1;
+  const double *Y_solve = H->Y_dev;
+  if (rotate) {
+    CK(cudaStreamSynchronize(st));
+    if ((rc = planes_validate(ctx, H->A_bf16_dev, H->n))) return rc;
+  }
+  const bool rotated = rotate && ctx->planes_ok;
+  if (rotated) {
+    if (N > ctx->yrot_capacity) {
+      cudaFree(ctx->yrot);
+      ctx->yrot = nullptr; ctx->yrot_capacity = 0;
+      CK(cudaMalloc(&ctx->yrot, sizeof(double) * (N + 64)));
+      ctx->yrot_capacity = N;
+    }
+    std::vector<double> rot(3 * 1024, 0.0);
+    jacobi_eig32(H->S_host, rot.data(), rot.data() + 2048);
+    for (int i = 0; i < 32; ++i)
+      for (int j = 0; j < 32; ++j) rot[1024 + i * 32 + j] = rot[j * 32 + i];
+    CK(cudaMemcpyAsync(ctx->drot, rot.data(), sizeof(double) * 3 * 1024, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));     // `rot` is pageable host memory
+    const unsigned long long nblk_r = (H->n + 127) / 128;
+    int grid_r = ctx->sm_count;
+    if ((unsigned long long)grid_r > nblk_r) grid_r = (int)nblk_r;
+    CK(launch_stiefel_rowgemm(H->n, nullptr, 0.0, H->Y_dev, ctx->drot, ctx->yrot, grid_r, st));      // Y~ = Y Q
+    CK(launch_stiefel_rowgemm(H->n, nullptr, 0.0, g_dev, ctx->drot, ctx->p0, grid_r, st));           // g~ = g Q
+    ctx->launches += 2;
+    Y_solve = ctx->yrot;
+  }
 
   TcgCommon a;
   a.N = N;
-  a.g = g_dev;
+  a.g = rotated ? ctx->p0 : g_dev;      // (p0 is first written by the second CG iteration)
   a.s = s_dev;
   a.r = ctx->r;
   a.p0 = ctx->p0;
@@ -734,7 +808,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   }
   CK(cudaStreamSynchronize(st));
   if (want_tc) {
-    if ((rc = planes_validate(ctx, H->A_bf16_dev, H->n))) return rc;
+    if (!rotate && (rc = planes_validate(ctx, H->A_bf16_dev, H->n))) return rc;
     use_tc = ctx->planes_ok;
   }
   const double rv0 = ctx->hscal[0];
@@ -762,14 +836,21 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
       CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
                                ctx->plane_exp, grid, st));
     else if (use_tc)
-      CK(launch_tcg_stiefel_v6(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
-                               ctx->plane_exp, ctx->sm_count, st));
+      CK(launch_tcg_stiefel_v6(a, H->n, H->A_bf16_dev, Y_solve, ctx->drot + 2048 /* eigenvalues of S */, H->op_norm_bound,
+                               ctx->planes, ctx->plane_exp, ctx->sm_count, st));
     else
       CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
     ctx->last_path = use_tc ? (ctx->opt_tcgen05 == 2 ? 2 : 1) : 0;
   }
   CK(cudaEventRecord(ctx->ev1, st));
   ctx->launches += 1;
+  if (rotated && use_tc) {               // s = s~ Q^T (row-wise, in place)
+    const unsigned long long nblk_r = (H->n + 127) / 128;
+    int grid_r = ctx->sm_count;
+    if ((unsigned long long)grid_r > nblk_r) grid_r = (int)nblk_r;
+    CK(launch_stiefel_rowgemm(H->n, nullptr, 0.0, s_dev, ctx->drot + 1024, s_dev, grid_r, st));
+    ctx->launches += 1;
+  }
   CK(cudaMemcpyAsync(ctx->hres, ctx->dres, sizeof(TcgDeviceResult), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   res->solve_kernel_ms = 0.f;

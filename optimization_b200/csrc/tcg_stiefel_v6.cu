@@ -16,11 +16,11 @@
 //                                   rows this CTA owns and, in place of p_old, to the stage), <p,p>, <p,r>, block
 //                                   maximum, seven balanced int8 digit slices of p straight into the UMMA K-major
 //                                   SWIZZLE_128B operand image -- one pass.
-//   M (warps 8-15, 120 registers) : one 16-row group of one 64-row half block per warp: the rows of p as fp64 MMA A
-//                                   fragments from the stage (then the stage is released: the next block's p_old
-//                                   streams in), TMEM -> registers in the mma.sync accumulator arrangement
-//                                   (tcgen05.ld 16x256b), integer recombination = Z = A p; W = Z - p S on the fp64
-//                                   tensor cores, W written back and staged per 64-row half, <p,W>, <W,W>.
+//   M (warps 8-15, 120 registers) : one 16-row group of one 64-row half block per warp: its elements of p from the
+//                                   stage (then the half is released: the next block's p_old streams in), TMEM ->
+//                                   registers in the mma.sync accumulator arrangement (tcgen05.ld 16x256b), integer
+//                                   recombination = Z = A p; W = Z - p Lambda (the solve runs in the eigenbasis of S:
+//                                   an elementwise shift), W written back and staged per 64-row half, <p,W>, <W,W>.
 //   G (warps 16-19, 120 registers): projection Gram Y^T W of the staged half (fp64 tensor cores, exact fixed-point
 //                                   accumulation), Y of the next half fetched with cp.async meanwhile.
 // Hand-offs through mbarriers only.  Ownership is by 64-row HALF blocks (balanced to 1/11 instead of 1/6 of a CTA's
@@ -47,7 +47,7 @@ constexpr uint32_t V6_PO = V6_R + V6_TILE;                     // p_old tile (TM
 constexpr uint32_t V6_WB = ST_NB * WS * 8;                     // 36 KB padded tile
 constexpr uint32_t V6_W = V6_PO + V6_TILE;                     // W tile (stride WS)
 constexpr uint32_t V6_Y = V6_W + V6_WB;                        // Y tile (stride WS)
-constexpr uint32_t V6_S = V6_Y + V6_WB;                        // -S, rows in fragment order (stride WS)
+constexpr uint32_t V6_S = V6_Y + V6_WB;                        // -lambda: the 32 eigenvalues of S, negated (region kept at p x WS doubles)
 constexpr uint32_t V6_ACC = V6_S + ST_P * WS * 8;              // CTA Kulisch accumulators (5 scalars)
 constexpr uint32_t V6_NACC = 5;
 constexpr uint32_t V6_BAR = V6_ACC + V6_NACC * KUL_STRIDE * 8; // mbarriers
@@ -90,10 +90,6 @@ __device__ __forceinline__ void bulk_prefetch_l2_v6(const void *g, uint32_t byte
 __device__ __forceinline__ void fence_proxy_async_global_v6() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void bar_cta() { asm volatile("bar.sync 0, 640;" ::: "memory"); }    // all five warp groups
 __device__ __forceinline__ void bar_work() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // L + M + G
-
-// slot of row R of S in the staged copy: the fp64 MMA k-index of lane t, step c is the physical column 4 t + c of
-// its 16-column group (so that a lane's four A-fragment elements are 32 contiguous bytes of the dense p tile)
-__host__ __device__ constexpr int v6_srow(int R) { return (R & 16) + ((R >> 2) & 3) + 4 * (R & 3); }
 
 __device__ __forceinline__ void strip_fetch6(unsigned char *slot, uint64_t *bar, int sidx, unsigned n_rows,
                                              const double *W, const double *S, const double *Pn, const double *R,
@@ -161,7 +157,6 @@ __device__ __forceinline__ bool grid_reduce_barrier_w(V6Misc &ms, int rt, unsign
         if (++spins > (1u << 24)) {
           if (*((volatile int *)abort_flag) || spins > (1u << 25)) { ok = 0; break; }
         }
-        if (spins > 64) __nanosleep(64);
       }
       if (stamps) stamps[1] = globaltimer_ns();
       if (!ok) atomicExch(abort_flag, 1);
@@ -300,13 +295,16 @@ __device__ __forceinline__ void v6_run_service(const TcgCommon &a, const Stiefel
         mbar_expect_tx(&mb[B6_A_FULL], TC_ABLOCK);
         bulk_g2s(Asm, planes + (size_t)b * TC_ABLOCK, TC_ABLOCK, &mb[B6_A_FULL]);
         TL6(3);
-        if (i + 1 < pt.nb_local) {   // L2 prefetch of what the next blocks need: A planes, Y; then r / p_old one further
+#ifndef OB200_PF
+#define OB200_PF 0   // bulk L2 prefetches off: measured, the demand loads of the next half queue behind them in the TMA unit
+#endif
+        if (OB200_PF && i + 1 < pt.nb_local) {   // L2 prefetch of what the next blocks need: A planes, Y; then r / p_old one further
           const unsigned rn = r0 + ST_NB;
           const unsigned rows1 = n_rows32 - rn < ST_NB ? n_rows32 - rn : ST_NB;
           const uint32_t bytes1 = rows1 * ST_P * (uint32_t)sizeof(double);
           bulk_prefetch_l2_v6(planes + (size_t)(b + 1) * TC_ABLOCK, TC_ABLOCK);
           bulk_prefetch_l2_v6(st.Y + (size_t)rn * ST_P, bytes1);
-          if (i + 2 < pt.nb_local) {
+          if ((OB200_PF & 2) && i + 2 < pt.nb_local) {
             const unsigned r2 = rn + ST_NB;
             const unsigned rows2 = n_rows32 - r2 < ST_NB ? n_rows32 - r2 : ST_NB;
             const uint32_t bytes2 = rows2 * ST_P * (uint32_t)sizeof(double);
@@ -531,44 +529,32 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
         // L cannot be more than one block ahead of this role, so the parity is unambiguous)
         mbar_wait_guarded(&mb[B6_P_FULL + g16], u & 1);
         if (tid == 256) TL6(22);
-        // rows 16 qd + m and + 8 of the half as fp64 MMA A fragments: paf[ks][2 c + s] = p[row 8 s + m][16 ks + 4 j + c]
-        double paf[2][8];
+        // this thread's elements of p in the accumulator arrangement: pc[s][nt] = p[row 8 s + m][8 nt + 2 j + {0, 1}]
+        double2 pc[2][4];
         if (own) {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const unsigned char *prow = POsm + g16 * V6_HALF + (16u * qd + 8u * s + m) * 256u + 32u * j;
+            const unsigned char *prow = POsm + g16 * V6_HALF + (16u * qd + 8u * s + m) * 256u + 16u * j;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const double2 v01 = *reinterpret_cast<const double2 *>(prow + 128u * ks);
-              const double2 v23 = *reinterpret_cast<const double2 *>(prow + 128u * ks + 16u);
-              paf[ks][0 + s] = v01.x; paf[ks][2 + s] = v01.y; paf[ks][4 + s] = v23.x; paf[ks][6 + s] = v23.y;
-            }
+            for (int nt = 0; nt < 4; ++nt) pc[s][nt] = *reinterpret_cast<const double2 *>(prow + 64u * nt);
           }
         }
         mbar_arrive(&mb[B6_PO_EMPTY + g16]);                  // this half of the p tile may be refilled (p_old of the next block)
         if (tid == 256) { TL6(26); TLI(2); }
         if (own) {
-          // T = -p S while the tensor cores multiply (Ssm holds -S, rows in fragment order), small fp64 MMAs (m8n8k4: a
-          // large one would hold the SM sub-partition's fp64 pipe for > 100 cycles and stall the L role's DFMA stream
-          // behind it): eight independent accumulator chains of eight k-steps
+          // The solve runs in the eigenbasis of S (ob200_stpcg rotates g, Y and s): W = A p - p Lambda, an elementwise
+          // shift by the column's eigenvalue instead of a 128 x 32 x 32 fp64 product (the fp64 pipe is the scarce unit of
+          // phase A: DESIGN.md 4.2b).  T = -lambda o p now, W = Z + T after the read-back.
           double acc[2][4][2];                                // [row tile s][n-tile][c]: row 8 s + m, columns 8 nt + 2 j + c
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) acc[0][nt][0] = acc[0][nt][1] = acc[1][nt][0] = acc[1][nt][1] = 0.0;
-#ifndef OB200_EXP_NO_PS
+          for (int nt = 0; nt < 4; ++nt) {
+            const double2 nl = *reinterpret_cast<const double2 *>(Ssm + 8 * nt + 2 * j);   // -lambda of the two columns
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const double *Srow = Ssm + (16 * ks + j + 4 * c) * WS + m;
-#pragma unroll
-              for (int nt = 0; nt < 4; ++nt) {
-                const double bv = Srow[8 * nt];
-                dmma884(acc[0][nt][0], acc[0][nt][1], paf[ks][2 * c], bv);
-                dmma884(acc[1][nt][0], acc[1][nt][1], paf[ks][2 * c + 1], bv);
-              }
+            for (int s = 0; s < 2; ++s) {
+              acc[s][nt][0] = nl.x * pc[s][nt].x;
+              acc[s][nt][1] = nl.y * pc[s][nt].y;
             }
           }
-#endif
           if (tid == 256) TL6(27);
           // MMAs of block u complete: Z = A p from TMEM in the accumulator arrangement, W = Z + T
           mbar_wait_guarded(&mb[B6_MMA_DONE + (u & 1)], (u >> 1) & 1);
@@ -597,13 +583,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
               const int col = 8 * nt + 2 * j;
-              // p[row][col + e] = paf[nt >> 1][2 (2 (j & 1) + e) + s] of lane (m, 2 (nt & 1) + (j >> 1))
-              const int src = 4 * m + 2 * (nt & 1) + (j >> 1);
-              const double a0 = __shfl_sync(0xffffffffu, paf[nt >> 1][0 + s], src);
-              const double a1 = __shfl_sync(0xffffffffu, paf[nt >> 1][2 + s], src);
-              const double b0 = __shfl_sync(0xffffffffu, paf[nt >> 1][4 + s], src);
-              const double b1 = __shfl_sync(0xffffffffu, paf[nt >> 1][6 + s], src);
-              const double px = (j & 1) ? b0 : a0, py = (j & 1) ? b1 : a1;
+              const double px = pc[s][nt].x, py = pc[s][nt].y;
               const double wx = acc[s][nt][0], wy = acc[s][nt][1];
               pw = fma(px, wx, pw); pw = fma(py, wy, pw);
               ww = fma(wx, wx, ww); ww = fma(wy, wy, ww);
@@ -860,20 +840,21 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
           strip_fetch6(slot, sb, nxt, n_rows32, a.Hp, a.s, p_new, a.r, st.Y);
         }
         strip_rightmul_v(yx, Gsm, lane, acc);   // Hp = W - Y symG
-        double rr = 0.0, rm = 0.0;
+        double rr = 0.0;
+        int rmh = 0;                                      // max |r| of the strip through the (ordered) high words
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int col = 8 * t + 2 * j;
           rv[t].x = fma(step, acc[t][0], rv[t].x); rv[t].y = fma(step, acc[t][1], rv[t].y);   // l.377
           rr = fma(rv[t].x, rv[t].x, rr); rr = fma(rv[t].y, rv[t].y, rr);                      // l.383,408
-          rm = fmax(rm, fmax(fabs(rv[t].x), fabs(rv[t].y)));
+          rmh = max(rmh, max(__double2hiint(rv[t].x) & 0x7fffffff, __double2hiint(rv[t].y) & 0x7fffffff));
           if (valid) stcg2(a.r + rowoff + col, rv[t]);
         }
         fixacc_add(fb, rr, fqb, ovfb);      // exact-reduction unit: this lane's 8 elements of the strip
         // max |r| per 128-row block for the scale bound of the next phase A (order independent)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, __shfl_xor_sync(0xffffffffu, rm, o));
-        if (lane == 0) atomicMax(Rmax + ((unsigned)sidx >> 4), (unsigned long long)__double_as_longlong(rm));
+        rmh = __reduce_max_sync(0xffffffffu, rmh);
+        // (upper bound of the maximum: the largest double with this high word)
+        if (lane == 0) atomicMax(Rmax + ((unsigned)sidx >> 4), ((unsigned long long)(unsigned)rmh << 32) | 0xffffffffull);
         cur = nxt;
       }
       if (tid == 256) TL6B(45);   // phase B strips done (warp 8)
@@ -944,7 +925,7 @@ tcg_stiefel_v6_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   uint64_t *mb = reinterpret_cast<uint64_t *>(base + V6_BAR);
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (int)(V6_NACC * KUL_STRIDE); i += blockDim.x) sacc[i] = 0;
-  for (int e = tid; e < ST_P * ST_P; e += blockDim.x) Ssm[v6_srow(e >> 5) * WS + (e & 31)] = -st.S[e];
+  if (tid < ST_P) Ssm[tid] = -st.S[tid];   // st.S: the 32 eigenvalues of S (the solve runs in its eigenbasis)
   if (tid == 0) {
     CgShared &sh = ms.sh;
     sh.rv = a.rv0;
