@@ -329,7 +329,7 @@ def stiefel_fallbacks(ctx, prob, n):
             out["stiefel_dmma_fallback"] = dict(rate(s0), workload="same workload, ob200_set_option('tcgen05', 0): "
                                                 "tcg_stiefel_kernel (A p on the fp64 tensor cores)")
         finally:
-            ctx.set_option("tcgen05", 2)
+            ctx.set_option("tcgen05", 1)
         del s0
         torch.cuda.empty_cache()
         pg = P.make_stiefel_critical(n, 32, generic_bf16=True)

@@ -137,6 +137,10 @@ struct ob200_context {
   double *drot = nullptr;         // v6 kernel: Q | Q^T | lambda (eigen-decomposition of S), 3 * 32*32 doubles
   double *yrot = nullptr;         // v6 kernel: Y Q (n x 32)
   size_t yrot_capacity = 0;
+  bool rot_valid = false;         // (drot, yrot) belong to the point (rot_Y, rot_S)
+  const double *rot_Y = nullptr;
+  uint64_t rot_n = 0;
+  double rot_S[1024];
   unsigned long long *dbits = nullptr;
   // pinned host mirrors
   TcgDeviceResult *hres = nullptr;
@@ -160,7 +164,7 @@ struct ob200_context {
   unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
   unsigned long long *dsum = nullptr;      // device / pinned-host word for the per-solve checksum of A
   unsigned long long *hsum = nullptr;
-  int opt_tcgen05 = 2;            // 1: tcgen05 kernel v6 (warp-specialised register budgets, work in progress), 2: tcgen05 kernel v4, 0: fp64 MMA kernel
+  int opt_tcgen05 = 1;            // 1: tcgen05 kernel v6 (warp-specialised register budgets, eigenbasis of S), 2: tcgen05 kernel v4, 0: fp64 MMA kernel
   int last_path = 0;              // 1 = tcgen05 kernel, 0 = fp64 tensor-core kernel
   // multi-GPU exchange (CUDA IPC peer memory)
   CommDev cm;                     // rank, world, epoch, peer pointers
@@ -417,6 +421,7 @@ int ob200_malloc(ob200_context *ctx, size_t bytes, void **p) {
 int ob200_free(ob200_context *ctx, void *p) {
   if (!ctx) return OB200_INVALID_ARGUMENT;
   if (p && p == ctx->planes_key) { ctx->planes_key = nullptr; ctx->planes_ok = false; }   // cached digit planes die with their A
+  if (p && p == ctx->rot_Y) { ctx->rot_valid = false; ctx->rot_Y = nullptr; }              // so does the rotated copy of a freed Y
   CK(cudaFree(p));
   return OB200_OK;
 }
@@ -651,42 +656,130 @@ static int sparse_args(ob200_context *ctx, const ob200_operator *H, SparseArgs *
   return OB200_OK;
 }
 
-// Eigen-decomposition S = Q diag(lam) Q^T of a symmetric 32 x 32 matrix (cyclic Jacobi, host, deterministic): the v6
-// Stiefel kernel solves in the eigenbasis of S, where  p S  is an elementwise shift.
-static void jacobi_eig32(const double *S, double *Q, double *lam) {
-  const int P = 32;
-  double A[32][32];
-  for (int i = 0; i < P; ++i)
-    for (int j = 0; j < P; ++j) { A[i][j] = 0.5 * (S[i * P + j] + S[j * P + i]); Q[i * P + j] = (i == j) ? 1.0 : 0.0; }
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0, dia = 0.0;
-    for (int i = 0; i < P; ++i) { dia += A[i][i] * A[i][i]; for (int j = i + 1; j < P; ++j) off += A[i][j] * A[i][j]; }
-    if (off <= 1e-36 * dia || off == 0.0) break;
-    for (int p = 0; p < P - 1; ++p)
-      for (int q = p + 1; q < P; ++q) {
-        const double apq = A[p][q];
-        if (apq == 0.0) continue;
-        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
-        for (int k = 0; k < P; ++k) {   // A <- A J
-          const double akp = A[k][p], akq = A[k][q];
-          A[k][p] = c * akp - sn * akq;
-          A[k][q] = sn * akp + c * akq;
-        }
-        for (int k = 0; k < P; ++k) {   // A <- J^T A
-          const double apk = A[p][k], aqk = A[q][k];
-          A[p][k] = c * apk - sn * aqk;
-          A[q][k] = sn * apk + c * aqk;
-        }
-        for (int k = 0; k < P; ++k) {   // Q <- Q J
-          const double qkp = Q[k * P + p], qkq = Q[k * P + q];
-          Q[k * P + p] = c * qkp - sn * qkq;
-          Q[k * P + q] = sn * qkp + c * qkq;
-        }
+// The v6 Stiefel kernel solves in the eigenbasis of S, where  p S  is an elementwise shift.
+// Symmetric eigen-decomposition S = Q diag(lam) Q^T of a 32 x 32 matrix: Householder tridiagonalisation followed by the
+// implicit QL iteration (the classical tred2 / tql2 pair), host, deterministic, ~30 us.  Q row-major, eigenvector k in
+// column k.
+static void sym_eig32(const double *S, double *Q, double *lam) {
+  const int n = 32;
+  double V[32][32], d[32], e[32];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) V[i][j] = 0.5 * (S[i * n + j] + S[j * n + i]);
+  // ---- tred2 ----
+  for (int j = 0; j < n; ++j) d[j] = V[n - 1][j];
+  for (int i = n - 1; i > 0; --i) {
+    double scale = 0.0, h = 0.0;
+    for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
+    if (scale == 0.0) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; ++j) { d[j] = V[i - 1][j]; V[i][j] = 0.0; V[j][i] = 0.0; }
+    } else {
+      for (int k = 0; k < i; ++k) { d[k] /= scale; h += d[k] * d[k]; }
+      double f = d[i - 1];
+      double g = std::sqrt(h);
+      if (f > 0) g = -g;
+      e[i] = scale * g;
+      h -= f * g;
+      d[i - 1] = f - g;
+      for (int j = 0; j < i; ++j) e[j] = 0.0;
+      for (int j = 0; j < i; ++j) {
+        f = d[j];
+        V[j][i] = f;
+        g = e[j] + V[j][j] * f;
+        for (int k = j + 1; k <= i - 1; ++k) { g += V[k][j] * d[k]; e[k] += V[k][j] * f; }
+        e[j] = g;
       }
+      f = 0.0;
+      for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
+      const double hh = f / (h + h);
+      for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+      for (int j = 0; j < i; ++j) {
+        f = d[j];
+        g = e[j];
+        for (int k = j; k <= i - 1; ++k) V[k][j] -= (f * e[k] + g * d[k]);
+        d[j] = V[i - 1][j];
+        V[i][j] = 0.0;
+      }
+    }
+    d[i] = h;
   }
-  for (int i = 0; i < P; ++i) lam[i] = A[i][i];
+  for (int i = 0; i < n - 1; ++i) {
+    V[n - 1][i] = V[i][i];
+    V[i][i] = 1.0;
+    const double h = d[i + 1];
+    if (h != 0.0) {
+      for (int k = 0; k <= i; ++k) d[k] = V[k][i + 1] / h;
+      for (int j = 0; j <= i; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= i; ++k) g += V[k][i + 1] * V[k][j];
+        for (int k = 0; k <= i; ++k) V[k][j] -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; ++k) V[k][i + 1] = 0.0;
+  }
+  for (int j = 0; j < n; ++j) { d[j] = V[n - 1][j]; V[n - 1][j] = 0.0; }
+  V[n - 1][n - 1] = 1.0;
+  e[0] = 0.0;
+  // ---- tql2 ----
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  double f = 0.0, tst1 = 0.0;
+  const double eps = 2.220446049250313e-16;
+  for (int l = 0; l < n; ++l) {
+    tst1 = std::fmax(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) {
+      if (std::fabs(e[m]) <= eps * tst1) break;
+      ++m;
+    }
+    if (m > l) {
+      int iter = 0;
+      do {
+        ++iter;
+        double g = d[l];
+        double p = (d[l + 1] - g) / (2.0 * e[l]);
+        double r = std::hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; ++i) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c;
+        const double el1 = e[l + 1];
+        double s = 0.0, s2 = 0.0;
+        for (int i = m - 1; i >= l; --i) {
+          c3 = c2;
+          c2 = c;
+          s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = std::hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          for (int k = 0; k < n; ++k) {
+            h = V[k][i + 1];
+            V[k][i + 1] = s * V[k][i] + c * h;
+            V[k][i] = c * V[k][i] - s * h;
+          }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] = d[l] + f;
+    e[l] = 0.0;
+  }
+  for (int i = 0; i < n; ++i) {
+    lam[i] = d[i];
+    for (int j = 0; j < n; ++j) Q[i * n + j] = V[i][j];
+  }
 }
 
 static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
@@ -741,21 +834,31 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     if (N > ctx->yrot_capacity) {
       cudaFree(ctx->yrot);
       ctx->yrot = nullptr; ctx->yrot_capacity = 0;
+      ctx->rot_valid = false;
       CK(cudaMalloc(&ctx->yrot, sizeof(double) * (N + 64)));
       ctx->yrot_capacity = N;
     }
-    std::vector<double> rot(3 * 1024, 0.0);
-    jacobi_eig32(H->S_host, rot.data(), rot.data() + 2048);
-    for (int i = 0; i < 32; ++i)
-      for (int j = 0; j < 32; ++j) rot[1024 + i * 32 + j] = rot[j * 32 + i];
-    CK(cudaMemcpyAsync(ctx->drot, rot.data(), sizeof(double) * 3 * 1024, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));     // `rot` is pageable host memory
     const unsigned long long nblk_r = (H->n + 127) / 128;
     int grid_r = ctx->sm_count;
     if ((unsigned long long)grid_r > nblk_r) grid_r = (int)nblk_r;
-    CK(launch_stiefel_rowgemm(H->n, nullptr, 0.0, H->Y_dev, ctx->drot, ctx->yrot, grid_r, st));      // Y~ = Y Q
+    // (Q, Lambda, Y~) are kept for repeated solves at the same point: S = sym(Y^T A Y) identifies Y
+    if (!(ctx->rot_valid && ctx->rot_Y == H->Y_dev && ctx->rot_n == H->n &&
+          !memcmp(ctx->rot_S, H->S_host, sizeof(ctx->rot_S)))) {
+      std::vector<double> rot(3 * 1024, 0.0);
+      sym_eig32(H->S_host, rot.data(), rot.data() + 2048);
+      for (int i = 0; i < 32; ++i)
+        for (int j = 0; j < 32; ++j) rot[1024 + i * 32 + j] = rot[j * 32 + i];
+      CK(cudaMemcpyAsync(ctx->drot, rot.data(), sizeof(double) * 3 * 1024, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));     // `rot` is pageable host memory
+      CK(launch_stiefel_rowgemm(H->n, nullptr, 0.0, H->Y_dev, ctx->drot, ctx->yrot, grid_r, st));    // Y~ = Y Q
+      ctx->launches += 1;
+      memcpy(ctx->rot_S, H->S_host, sizeof(ctx->rot_S));
+      ctx->rot_Y = H->Y_dev;
+      ctx->rot_n = H->n;
+      ctx->rot_valid = true;
+    }
     CK(launch_stiefel_rowgemm(H->n, nullptr, 0.0, g_dev, ctx->drot, ctx->p0, grid_r, st));           // g~ = g Q
-    ctx->launches += 2;
+    ctx->launches += 1;
     Y_solve = ctx->yrot;
   }
 

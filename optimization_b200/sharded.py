@@ -12,7 +12,7 @@ def _bits(A_bf16: np.ndarray, device) -> torch.Tensor:
 
 
 class SingleStiefel:
-    kernel_name = "tcg_stiefel_tc_kernel (persistent fused tCG, whole solve; tcgen05 int8 digit planes + fp64 MMA)"
+    kernel_name = "tcg_stiefel_v6_kernel (persistent fused tCG, whole solve; warp-specialised roles, tcgen05 int8 digit planes, TMA-staged operands, solve in the eigenbasis of S)"
 
     def __init__(self, ctx, prob):
         self.ctx, self.prob = ctx, prob
@@ -65,7 +65,7 @@ def row_partition(n: int, world: int, nb: int = 128):
 class ShardedStiefel(SingleStiefel):
     """One Stiefel tCG problem row-sharded over the ranks of a torch.distributed
     job; the reductions travel through NVLink peer memory inside the kernels."""
-    kernel_name = "tcg_stiefel_tc_kernel (persistent fused tCG + in-kernel NVLink peer exchange)"
+    kernel_name = "tcg_stiefel_v6_kernel (persistent fused tCG + in-kernel NVLink peer exchange)"
 
     def __init__(self, ctx, prob, rank, world):
         self.ctx, self.prob, self.rank, self.world = ctx, prob, rank, world

@@ -355,7 +355,7 @@ def test_stiefel_hvp_fused_vs_numpy(ctx, n):
         try:
             hv0 = ctx.hvp(H, V).cpu().numpy()
         finally:
-            ctx.set_option("tcgen05", 2)
+            ctx.set_option("tcgen05", 1)
         assert rel(hv0, want) < 1e-12
         z = ctx.hvp(H, ctx.to_device(np.zeros_like(prob.g))).cpu().numpy()
         assert np.all(z == 0.0)
@@ -461,16 +461,16 @@ def test_stiefel_fp64_mma_path_vs_oracle(ctx, port, n):
     kw = dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.)
     s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
     o_tc = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
-    assert ctx.last_path == "tcgen05_v4"
-    ctx.set_option("tcgen05", 1)            # the warp-specialised generation of the kernel (kept as an option)
+    assert ctx.last_path == "tcgen05"       # default: the warp-specialised v6 kernel (solve in the eigenbasis of S)
+    ctx.set_option("tcgen05", 2)            # the previous generation of the tcgen05 kernel (kept as an option)
     o_v5 = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
-    assert ctx.last_path == "tcgen05"
+    assert ctx.last_path == "tcgen05_v4"
     ctx.set_option("tcgen05", 0)
     try:
         o_mm = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
         assert ctx.last_path == "dmma"
     finally:
-        ctx.set_option("tcgen05", 2)
+        ctx.set_option("tcgen05", 1)
     for o in (o_tc, o_v5, o_mm):
         assert (o.num_iterations, o.exit_reason) == (it_ref, why_ref)
         assert rel(o.s.cpu().numpy(), s_ref) < RTOL
