@@ -448,6 +448,7 @@ def run_ours(args):
         parity = {"num_iterations": int(out.num_iterations), "exit_reason": out.exit_reason}
         if world > 1:
             c1 = Context(local)                          # independent one-GPU context, whole problem
+            c1.set_option("tcgen05", 2)                  # the kernel generation row-sharded runs use (see ob200_stpcg)
             from optimization_b200.sharded import SingleStiefel
             o1 = SingleStiefel(c1, prob).solve_device(**SOLVE)
             s1 = o1.s.cpu().numpy()
@@ -455,6 +456,7 @@ def run_ours(args):
                                                           and o1.num_iterations == out.num_iterations
                                                           and o1.exit_reason == out.exit_reason
                                                           and o1.update_step_M_norm == out.update_step_M_norm),
+                                    "kernel_paths": [ctx.last_path, c1.last_path],
                                     "max_abs_diff": float(np.abs(s1 - s_full).max()),
                                     "num_iterations_one_gpu": int(o1.num_iterations)}
             c1.close()

@@ -823,7 +823,10 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   // v6 kernel: the solve runs in the eigenbasis of S = Q Lambda Q^T -- g~ = g Q, Y~ = Y Q, s = s~ Q^T.  The iteration is
   // the same Steihaug-Toint loop on an orthogonally rotated copy of the problem (Frobenius products, the projection and
   // the trust-region norm are invariant), with  p S  reduced to an elementwise shift.
-  const bool rotate = want_tc && ctx->opt_tcgen05 == 1;
+  // Kernel generation: v6 streams large shards closer to the HBM roofline; row-sharded runs (<= 50 000 rows per GPU at
+  // the BASELINE size) are latency-bound and the lighter v4 pipeline is faster there (measured at N = 2 / 4 / 8).
+  const int tc_gen = (ctx->opt_tcgen05 == 1 && ctx->cm.world > 1) ? 2 : ctx->opt_tcgen05;
+  const bool rotate = want_tc && tc_gen == 1;
   const double *Y_solve = H->Y_dev;
   if (rotate) {
     CK(cudaStreamSynchronize(st));
@@ -883,7 +886,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   a.cm = ctx->cm;
   a.blk_stats = nullptr;
   a.nblk_stats = 0;
-  if (want_tc && ctx->opt_tcgen05 == 1) {   // v6 kernel: block maxima of r (seeded by the init kernel) and p
+  if (want_tc && tc_gen == 1) {   // v6 kernel: block maxima of r (seeded by the init kernel) and p
     const size_t nblk = (H->n + 127) / 128;
     if (nblk > ctx->blk_stats_cap) {
       cudaFree(ctx->blk_stats);
@@ -935,7 +938,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
     const unsigned long long nblk = (H->n + 127) / 128;
     int grid = ctx->sm_count;
     if ((unsigned long long)grid > nblk) grid = (int)nblk;
-    if (use_tc && ctx->opt_tcgen05 == 2)      // previous generation of the tcgen05 kernel, kept for A/B measurements
+    if (use_tc && tc_gen == 2)                // previous generation of the tcgen05 kernel (row-sharded runs, A/B measurements)
       CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
                                ctx->plane_exp, grid, st));
     else if (use_tc)
@@ -943,7 +946,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
                                ctx->planes, ctx->plane_exp, ctx->sm_count, st));
     else
       CK(launch_tcg_stiefel(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, grid, st));
-    ctx->last_path = use_tc ? (ctx->opt_tcgen05 == 2 ? 2 : 1) : 0;
+    ctx->last_path = use_tc ? (tc_gen == 2 ? 2 : 1) : 0;
   }
   CK(cudaEventRecord(ctx->ev1, st));
   ctx->launches += 1;

@@ -335,11 +335,16 @@ __device__ __forceinline__ void v6_run_service(const TcgCommon &a, const Stiefel
   }
 }
 
-// ROLE: 1 = L, 2 = M, 3 = G.  The whole CG loop is instantiated per role so that each warp group's code is compiled
+// role: 1 = L, 2 = M, 3 = G (warp-uniform).  ONE instance of the loop for the three work roles, all on the same register
+// budget: the phase-A role bodies are separate branches, everything else (reductions, scalar stage, phase B) is shared
+// code -- three per-role copies of it evicted each other from the instruction cache (stall_no_instruction).
+// (historical note) The whole CG loop used to be instantiated per role so that each warp group's code was compiled
 // against its own register budget.
-template <int ROLE>
-__device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st, const int *plane_exp,
+// MROLE: the instance for the M role (its own register budget); the other instance serves L and G (runtime `role`).
+template <bool MROLE>
+__device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, const StiefelArgs &st, const int *plane_exp,
                                        unsigned char *base) {
+  const int role = MROLE ? 2 : role_rt;
   unsigned char *Qsm = base + V6_Q;
   const unsigned char *Rsm = base + V6_R;
   unsigned char *POsm = base + V6_PO;
@@ -396,7 +401,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
       const int z0 = per * blockIdx.x;
       for (int i = rt; i < per && z0 + i < ACC_WORDS; i += V6_WORK) nxt[z0 + i] = 0;
     }
-    if constexpr (ROLE == 1) {
+    if (!MROLE && role == 1) {
       // ===== L: p = -r + beta p_old, digit slices -- ONE pass over the staged block =====
       // The digit slices need a scale 2^E with |p| < 2^E over the block BEFORE the first element is cut.  Instead of a
       // maximum pass and a second pass, E comes from a bound that is known when the block arrives:
@@ -512,7 +517,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
       fixacc_flush(fa0, sacc + SC_PP * KUL_STRIDE, fe0);
       fixacc_flush(fa1, sacc + SC_PR * KUL_STRIDE, fe1);
       if (ovf) atomicOr((unsigned long long *)(set + ACC_FLAG_OFF), 1ull);
-    } else if constexpr (ROLE == 2) {
+    } else if (MROLE) {
       // ===== M: p fragments, TMEM read-back, W = Z - p S, stores, partial sums =====
       // warp (qd, g16): TMEM lanes 32 qd + 16 g16 + [0, 16) = block rows 64 g16 + 16 qd + [0, 16), all 32 columns
       const int w = warp - 8, qd = w & 3, g16 = w >> 2;
@@ -715,7 +720,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
       {
         // G (fixed point) -> shared memory (M and G warps) while the four L warps finalize the four exact scalars
         double *Graw = reinterpret_cast<double *>(base + V6_GRAW);
-        if constexpr (ROLE >= 2) {
+        if (role >= 2) {
           for (int e = rt - 128; e < ST_P * ST_P; e += 384) {
             u64 hi, lo;
             if (rvw.world == 1) {
@@ -747,7 +752,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
         exit_reason = -3;
         continue;
       }
-      if constexpr (ROLE == 1) {
+      if (role == 1) {
         if (rw == 0) {
           // lanes 0..2 evaluate the long-latency operations concurrently, lane 0 takes the decisions
           double nG2 = 0.0;
@@ -875,7 +880,7 @@ __device__ __forceinline__ void v6_run(const TcgCommon &a, const StiefelArgs &st
     flush_scalars_w(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1, rt);
     if (!grid_reduce_barrier_w(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
                                KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr)) { exit_reason = -2; continue; }
-    if constexpr (ROLE == 1) {
+    if (role == 1) {
       if (rw == 0) {
         const int o = SC_RV * KUL_STRIDE;
         const double x = kul_finalize_warp([&rvw, o](int jj) { return rvw.load(o + jj); });
@@ -983,15 +988,12 @@ tcg_stiefel_v6_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     v6_run_service(a, st, planes, base);
-  } else if (warp < 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    v6_run<1>(a, st, plane_exp, base);
-  } else if (warp < 16) {
+  } else if (warp >= 8 && warp < 16) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    v6_run<2>(a, st, plane_exp, base);
+    v6_run<true>(2, a, st, plane_exp, base);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    v6_run<3>(a, st, plane_exp, base);
+    v6_run<false>(warp < 8 ? 1 : 3, a, st, plane_exp, base);
   }
   tc_fence_before();
   bar_cta();

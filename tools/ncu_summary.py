@@ -55,7 +55,7 @@ def stalls(rep):
         if len(r) < len(hdr):
             continue
         try:
-            k = int(r[ix["# Samples"]])
+            k = int(r[ix["# Samples"] if "# Samples" in ix else ix["Warp Stall Sampling (All Samples)"]])
         except ValueError:
             continue
         n += k
