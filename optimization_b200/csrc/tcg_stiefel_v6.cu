@@ -135,80 +135,38 @@ __device__ __forceinline__ void recombine_frag8(uint32_t taddr, double (&out)[4]
   }
 }
 
-// Grid-wide (machine-wide) reduction barrier of the 512 work threads; rt = relative thread id.  Same protocol as
-// grid_reduce_barrier (common.cuh), with the CTA-level synchronisation on named barrier 1.
+// Grid-wide reduction barrier of the 512 work threads (rt = relative thread id): the protocol of grid_reduce_barrier
+// (common.cuh) for ONE GPU, with the CTA-level synchronisation on named barrier 1.  Row-sharded runs use the v4 kernel
+// (ob200_stpcg picks the generation), so the machine-wide exchange is not instantiated here: less code in the
+// instruction cache of the persistent loop.
 __device__ __forceinline__ bool grid_reduce_barrier_w(V6Misc &ms, int rt, unsigned *counter, unsigned &gen,
                                                       int *abort_flag, const CommDev &cm, unsigned long long gphase,
                                                       u64 *set, int off, int count, RedView &view,
                                                       unsigned long long *stamps) {
+  (void)gphase; (void)off; (void)count;
   bar_work();
   if (rt == 0) {
     gen += 1;
     const unsigned target = gen * gridDim.x;
-    if (cm.world > 1) __threadfence_system();
-    else __threadfence();
+    __threadfence();
     if (stamps) stamps[0] = globaltimer_ns();
-    const unsigned old = atom_add_acqrel_u32(counter, 1u);
-    int ok = 1;
-    ms.s_last = (old + 1u == target);
-    if (cm.world == 1) {
-      unsigned spins = 0;
-      while (ld_acquire_u32(counter) < target) {
-        if (++spins > (1u << 24)) {
-          if (*((volatile int *)abort_flag) || spins > (1u << 25)) { ok = 0; break; }
-        }
+    atom_add_acqrel_u32(counter, 1u);
+    int ok = cm.world == 1;
+    unsigned spins = 0;
+    while (ok && ld_acquire_u32(counter) < target) {
+      if (++spins > (1u << 24)) {
+        if (*((volatile int *)abort_flag) || spins > (1u << 25)) ok = 0;
       }
-      if (stamps) stamps[1] = globaltimer_ns();
-      if (!ok) atomicExch(abort_flag, 1);
-      __threadfence();
     }
+    if (stamps) stamps[1] = globaltimer_ns();
+    if (!ok) atomicExch(abort_flag, 1);
+    __threadfence();
     ms.s_ok = ok;
   }
   bar_work();
-  view.world = cm.world;
+  view.world = 1;
   view.stride = (size_t)cm.words_per_set;
-  if (cm.world == 1) {
-    view.base0 = set;
-    return ms.s_ok != 0;
-  }
-  const int slot = (int)(gphase % ACC_SLOTS);
-  const size_t slot_off = (size_t)(slot * MAX_RANKS) * cm.words_per_set;
-  if (ms.s_last) {   // CTA-uniform: this CTA completed the local reduction -> publish it to every rank
-    __threadfence();
-    constexpr int PUB_MAX = 6;                       // count <= PUB_MAX * 512
-    u64 wv[PUB_MAX];
-#pragma unroll
-    for (int k = 0; k < PUB_MAX; ++k) {
-      const int i = rt + k * V6_WORK;
-      wv[k] = (i < count) ? __ldcg(set + off + i) : 0ull;
-    }
-    for (int r = 0; r < cm.world; ++r) {
-      u64 *dst = cm.inbox[r] + slot_off + (size_t)cm.rank * cm.words_per_set + off;
-#pragma unroll
-      for (int k = 0; k < PUB_MAX; ++k) {
-        const int i = rt + k * V6_WORK;
-        if (i < count) dst[i] = wv[k];
-      }
-    }
-    bar_work();
-    if (rt < cm.world) st_release_sys_u64(cm.flags[rt] + slot * MAX_RANKS + cm.rank, gphase + 1ull);
-  }
-  if (rt < cm.world) {
-    const unsigned long long *f = cm.flags[cm.rank] + slot * MAX_RANKS + rt;
-    unsigned spins = 0;
-    while (ld_acquire_sys_u64(f) < gphase + 1ull) {
-      if (++spins > (1u << 24)) {
-        if (*((volatile int *)abort_flag) || spins > (1u << 25)) { atomicExch(abort_flag, 1); break; }
-      }
-    }
-  }
-  bar_work();
-  if (rt == 0) {
-    if (stamps) stamps[1] = globaltimer_ns();
-    ms.s_ok = (*((volatile int *)abort_flag) == 0);
-  }
-  bar_work();
-  view.base0 = cm.inbox[cm.rank] + slot_off;
+  view.base0 = set;
   return ms.s_ok != 0;
 }
 
