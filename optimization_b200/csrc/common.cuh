@@ -170,6 +170,9 @@ __device__ __forceinline__ double kul_finalize_warp(Load ld) {
     return __shfl_sync(0xffffffffu, src, j & 31);
   };
   i64 carry = 0;
+  // (not unrolled: this runs once per reduction on one warp; unrolled copies of the shuffle-select chains cost ~1000
+  // instructions per call site, and the persistent kernels are instruction-cache bound between their phases)
+#pragma unroll 1
   for (int j = lo; j <= hi; ++j) carry = (limb(j) + carry) >> 32;
   const bool neg = carry < 0;
   carry = 0;
@@ -179,6 +182,7 @@ __device__ __forceinline__ double kul_finalize_warp(Load ld) {
   uint32_t t0 = 0, t1 = 0, t2 = 0;
   bool tstk = false;
   int top = -1;
+#pragma unroll 1
   for (int j = lo; j <= hi; ++j) {
     const i64 r = limb(j);
     const i64 t = (neg ? -r : r) + carry;

@@ -302,7 +302,7 @@ __device__ __forceinline__ void v6_run_service(const TcgCommon &a, const Stiefel
 template <bool MROLE>
 __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, const StiefelArgs &st, const int *plane_exp,
                                        unsigned char *base) {
-  const int role = MROLE ? 2 : role_rt;
+  const int role0 = MROLE ? 2 : role_rt;
   unsigned char *Qsm = base + V6_Q;
   const unsigned char *Rsm = base + V6_R;
   unsigned char *POsm = base + V6_PO;
@@ -339,6 +339,9 @@ __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, co
   unsigned long long dbg_prev = 0;
 
   for (;;) {
+    // (broadcast from lane 0: the compiler then knows the role is warp-uniform and emits no reconvergence scaffolding
+    // around the shuffles / votes inside role-dependent branches)
+    const int role = MROLE ? 2 : __shfl_sync(0xffffffffu, role0, 0);
     if (exit_reason == -1) {
       if (sh.k >= a.max_iterations) exit_reason = 1;
       else if (sqrt(sh.rv) <= a.target) exit_reason = 0;
