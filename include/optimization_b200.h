@@ -92,6 +92,10 @@ int ob200_debug_phase_times(ob200_context *ctx, int enable, uint64_t *out4_max, 
 int ob200_debug_block_apply(ob200_context *ctx, uint64_t n, const uint16_t *A_bf16_dev, const double *V_dev,
                             double *out_dev, int use_tcgen05);
 
+/* Validation aid (host only, no GPU needed): the eigen-decomposition S = Q diag(lambda) Q^T (32 x 32, row-major, eigenvector
+ * k in column k of Q) that ob200_stpcg uses to run the Stiefel solve in the eigenbasis of S = sym(Y^T A Y). */
+int ob200_debug_sym_eig32(const double *S_host, double *Q_host, double *lambda_host);
+
 /* ---- Hessian operator descriptors -----------------------------------------
  * Replaces the user's `Riemannian::LinearOperator` Hessian functor
  * (reference Riemannian/Concepts.h:49-51, bound to x at TNT.h:400-403 and

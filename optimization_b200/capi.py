@@ -31,7 +31,7 @@ EXPORTS = [
     "ob200_free", "ob200_memcpy_h2d", "ob200_memcpy_d2h", "ob200_malloc_host", "ob200_free_host",
     "ob200_comm_export", "ob200_comm_connect", "ob200_comm_rank", "ob200_comm_world",
     "ob200_stpcg_step_bytes", "ob200_hvp_bytes", "ob200_debug_phase_times",
-    "ob200_debug_block_apply", "ob200_set_option", "ob200_last_path", "ob200_div", "ob200_csr3_model", "ob200_csr3_retract", "ob200_halo_create", "ob200_halo_connect",
+    "ob200_debug_block_apply", "ob200_debug_sym_eig32", "ob200_set_option", "ob200_last_path", "ob200_div", "ob200_csr3_model", "ob200_csr3_retract", "ob200_halo_create", "ob200_halo_connect",
 ]
 
 
@@ -152,6 +152,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.ob200_set_option.argtypes = [vp, C.c_char_p, i]
     lib.ob200_last_path.argtypes = [vp]
     lib.ob200_debug_block_apply.argtypes = [vp, u64, vp, vp, vp, i]
+    lib.ob200_debug_sym_eig32.argtypes = [vp, vp, vp]
     lib.ob200_debug_phase_times.argtypes = [vp, i, C.POINTER(u64), C.POINTER(u64)]
     return lib
 

@@ -450,6 +450,8 @@ int ob200_free_host(ob200_context *ctx, void *p) {
 
 }  // extern "C"
 
+static void sym_eig32(const double *S, double *Q, double *lam);
+
 // ---- internals ----------------------------------------------------------------
 static int ensure_vectors(ob200_context *ctx, size_t N) {
   if (N <= ctx->vec_capacity) return OB200_OK;
@@ -1369,6 +1371,12 @@ int ob200_stiefel_retract(ob200_context *ctx, uint64_t n, uint64_t p, const doub
   CK(launch_stiefel_rowgemm(n, nullptr, 0.0, Z, ctx->dmat + 1024, out, grid, st));   // Q = Z R^{-1}
   ctx->launches += 1;
   CK(cudaStreamSynchronize(st));
+  return OB200_OK;
+}
+
+int ob200_debug_sym_eig32(const double *S, double *Q, double *lam) {
+  if (!S || !Q || !lam) return OB200_INVALID_ARGUMENT;
+  sym_eig32(S, Q, lam);
   return OB200_OK;
 }
 

@@ -56,6 +56,35 @@ def test_byte_model():
     assert lib.ob200_hvp_bytes(C.byref(op)) == 38 * 8 * (1 << 24)
 
 
+def test_sym_eig32_host_decomposition():
+    """The eigen-decomposition S = Q diag(lambda) Q^T behind the rotated Stiefel solve (host code of ob200_stpcg):
+    reconstruction, orthogonality and eigenvalues against numpy, on well- and ill-separated spectra."""
+    import numpy as np
+    lib = capi.load_library()
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        B = rng.standard_normal((32, 32))
+        S = 0.5 * (B + B.T)
+        if trial == 1:
+            S += np.diag(10.0 + np.arange(32))
+        elif trial == 2:
+            S = 1e-3 * S + 5.0 * np.eye(32)                      # clustered spectrum
+        elif trial == 3:
+            S = np.diag(np.linspace(-3.0, 4.0, 32))              # already diagonal
+        elif trial == 4:
+            S = np.zeros((32, 32))                               # zero matrix
+        elif trial == 5:
+            S *= 1e150                                           # large scale
+        S = np.ascontiguousarray(S)
+        Q = np.zeros((32, 32))
+        lam = np.zeros(32)
+        assert lib.ob200_debug_sym_eig32(S.ctypes.data, Q.ctypes.data, lam.ctypes.data) == 0
+        scale = max(np.abs(S).max(), 1e-300)
+        assert np.abs(Q @ np.diag(lam) @ Q.T - S).max() <= 1e-13 * scale * 32
+        assert np.abs(Q.T @ Q - np.eye(32)).max() <= 1e-13
+        assert np.allclose(np.sort(lam), np.linalg.eigvalsh(S), rtol=0, atol=1e-13 * scale * 32)
+
+
 def test_product_never_imports_oracle():
     pk = os.path.join(ROOT, "optimization_b200")
     for dp, _, fs in os.walk(pk):

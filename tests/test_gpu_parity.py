@@ -317,6 +317,62 @@ def test_block_apply_tcgen05_readbacks_match_fp64(ctx, n):
     assert np.array_equal(outs[1], outs[2])          # same integers, same recombination: bit-identical
 
 
+@pytest.mark.parametrize("n", [33, 64, 65, 127, 129, 191, 193, 1000, 4099, 18977])
+def test_stiefel_v6_ragged_sizes_vs_oracle(ctx, port, n):
+    """The default (warp-specialised, rotated-basis) kernel on row counts around the 64-row half / 128-row block / 8-row
+    strip boundaries: partial halves, a single half, last block of 1 .. 127 rows."""
+    for prob, kw in ((P.make_stiefel_critical(n, 32), dict(Delta=1e6, max_iterations=80, kappa_fgr=1e-9, theta=0.)),
+                     (P.make_stiefel(n, 32, y_noise=.2), dict(Delta=3.0, max_iterations=60, kappa_fgr=1e-3, theta=.5))):
+        A, Y, H = stiefel_setup(ctx, prob)
+        s_ref, mn_ref, it_ref, why_ref = port.stpcg_stiefel(prob, prob.Y0, prob.g, **kw)
+        out = ctx.stpcg(ctx.to_device(prob.g), H, **kw)
+        assert ctx.last_path == "tcgen05"
+        assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref)
+        assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+        assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+
+
+def test_stiefel_v6_is_bit_reproducible_and_rotation_cache_follows_the_point(ctx, port):
+    """Repeated solves agree in every bit (exact integer reductions; this is the check that found the cross-proxy race
+    of the stage, tools/v6_stress.py), and the cached rotation (Q, Lambda, Y Q) is dropped when the point changes under
+    the same device address."""
+    import torch
+    n = 20000
+    p1 = P.make_stiefel_critical(n, 32, seed=21)
+    p2 = P.make_stiefel(n, 32, y_noise=.2)
+    kw = dict(Delta=1e6, max_iterations=200, kappa_fgr=1e-9, theta=0.)
+    A = torch.from_numpy(p1.A_bf16.astype(np.int16)).to("cuda:0")
+    Y = ctx.to_device(p1.Y0)
+    H = ctx.stiefel_operator(A, Y)
+    g = ctx.to_device(p1.g)
+    first = ctx.stpcg(g, H, **kw)
+    for _ in range(8):
+        o = ctx.stpcg(g, H, **kw)
+        assert o.num_iterations == first.num_iterations and torch.equal(o.s, first.s)
+    s_ref, _, it_ref, why_ref = port.stpcg_stiefel(p1, p1.Y0, p1.g, **kw)
+    assert (first.num_iterations, first.exit_reason) == (it_ref, why_ref) and rel(first.s.cpu().numpy(), s_ref) < RTOL
+    # same buffers, new point (and new A): the rotated copy of Y must be rebuilt
+    A.copy_(torch.from_numpy(p2.A_bf16.astype(np.int16)))
+    Y.copy_(torch.from_numpy(p2.Y0).to(Y.device))
+    H2 = ctx.stiefel_operator(A, Y)
+    kw2 = dict(Delta=3.0, max_iterations=60, kappa_fgr=1e-3, theta=.5)
+    o2 = ctx.stpcg(ctx.to_device(p2.g), H2, **kw2)
+    s2, _, it2, why2 = port.stpcg_stiefel(p2, p2.Y0, p2.g, **kw2)
+    assert (o2.num_iterations, o2.exit_reason) == (it2, why2) and rel(o2.s.cpu().numpy(), s2) < RTOL
+
+
+def test_stiefel_non_finite_input_is_reported(ctx):
+    """A NaN in g poisons the exact accumulators: the solve must end with an error status, never with a silent answer."""
+    prob = P.make_stiefel_critical(1000, 32)
+    A, Y, H = stiefel_setup(ctx, prob)
+    g = prob.g.copy()
+    g[517, 3] = np.nan
+    with pytest.raises(Exception):
+        out = ctx.stpcg(ctx.to_device(g), H, Delta=1e6, max_iterations=20, kappa_fgr=1e-9, theta=0.)
+        assert not np.all(np.isfinite(out.s.cpu().numpy()))     # (reached only if no status was raised)
+        raise RuntimeError("non-finite solve returned a status of success")
+
+
 def test_planes_cache_follows_the_matrix(ctx, port):
     """The cached tcgen05 digit planes are keyed by pointer, size AND content: an A rewritten in place at the same
     address (what a caching allocator produces when one problem replaces another) must not meet stale planes."""
