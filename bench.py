@@ -448,7 +448,6 @@ def run_ours(args):
         parity = {"num_iterations": int(out.num_iterations), "exit_reason": out.exit_reason}
         if world > 1:
             c1 = Context(local)                          # independent one-GPU context, whole problem
-            c1.set_option("tcgen05", 2)                  # the kernel generation row-sharded runs use (see ob200_stpcg)
             from optimization_b200.sharded import SingleStiefel
             o1 = SingleStiefel(c1, prob).solve_device(**SOLVE)
             s1 = o1.s.cpu().numpy()

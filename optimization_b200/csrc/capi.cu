@@ -825,9 +825,7 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   // v6 kernel: the solve runs in the eigenbasis of S = Q Lambda Q^T -- g~ = g Q, Y~ = Y Q, s = s~ Q^T.  The iteration is
   // the same Steihaug-Toint loop on an orthogonally rotated copy of the problem (Frobenius products, the projection and
   // the trust-region norm are invariant), with  p S  reduced to an elementwise shift.
-  // Kernel generation: v6 streams large shards closer to the HBM roofline; row-sharded runs (<= 50 000 rows per GPU at
-  // the BASELINE size) are latency-bound and the lighter v4 pipeline is faster there (measured at N = 2 / 4 / 8).
-  const int tc_gen = (ctx->opt_tcgen05 == 1 && ctx->cm.world > 1) ? 2 : ctx->opt_tcgen05;
+  const int tc_gen = ctx->opt_tcgen05;
   const bool rotate = want_tc && tc_gen == 1;
   const double *Y_solve = H->Y_dev;
   if (rotate) {

@@ -170,6 +170,83 @@ __device__ __forceinline__ bool grid_reduce_barrier_w(V6Misc &ms, int rt, unsign
   return ms.s_ok != 0;
 }
 
+// The same with the machine-wide exchange of grid_reduce_barrier (common.cuh): row-sharded runs (instantiated only in the
+// MULTI variant of the kernel, so the one-GPU loop stays lean).
+__device__ __forceinline__ bool grid_reduce_barrier_multi(V6Misc &ms, int rt, unsigned *counter, unsigned &gen,
+                                                      int *abort_flag, const CommDev &cm, unsigned long long gphase,
+                                                      u64 *set, int off, int count, RedView &view,
+                                                      unsigned long long *stamps) {
+  bar_work();
+  if (rt == 0) {
+    gen += 1;
+    const unsigned target = gen * gridDim.x;
+    if (cm.world > 1) __threadfence_system();
+    else __threadfence();
+    if (stamps) stamps[0] = globaltimer_ns();
+    const unsigned old = atom_add_acqrel_u32(counter, 1u);
+    int ok = 1;
+    ms.s_last = (old + 1u == target);
+    if (cm.world == 1) {
+      unsigned spins = 0;
+      while (ld_acquire_u32(counter) < target) {
+        if (++spins > (1u << 24)) {
+          if (*((volatile int *)abort_flag) || spins > (1u << 25)) { ok = 0; break; }
+        }
+      }
+      if (stamps) stamps[1] = globaltimer_ns();
+      if (!ok) atomicExch(abort_flag, 1);
+      __threadfence();
+    }
+    ms.s_ok = ok;
+  }
+  bar_work();
+  view.world = cm.world;
+  view.stride = (size_t)cm.words_per_set;
+  if (cm.world == 1) {
+    view.base0 = set;
+    return ms.s_ok != 0;
+  }
+  const int slot = (int)(gphase % ACC_SLOTS);
+  const size_t slot_off = (size_t)(slot * MAX_RANKS) * cm.words_per_set;
+  if (ms.s_last) {   // CTA-uniform: this CTA completed the local reduction -> publish it to every rank
+    __threadfence();
+    constexpr int PUB_MAX = 6;                       // count <= PUB_MAX * 512
+    u64 wv[PUB_MAX];
+#pragma unroll
+    for (int k = 0; k < PUB_MAX; ++k) {
+      const int i = rt + k * V6_WORK;
+      wv[k] = (i < count) ? __ldcg(set + off + i) : 0ull;
+    }
+    for (int r = 0; r < cm.world; ++r) {
+      u64 *dst = cm.inbox[r] + slot_off + (size_t)cm.rank * cm.words_per_set + off;
+#pragma unroll
+      for (int k = 0; k < PUB_MAX; ++k) {
+        const int i = rt + k * V6_WORK;
+        if (i < count) dst[i] = wv[k];
+      }
+    }
+    bar_work();
+    if (rt < cm.world) st_release_sys_u64(cm.flags[rt] + slot * MAX_RANKS + cm.rank, gphase + 1ull);
+  }
+  if (rt < cm.world) {
+    const unsigned long long *f = cm.flags[cm.rank] + slot * MAX_RANKS + rt;
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(f) < gphase + 1ull) {
+      if (++spins > (1u << 24)) {
+        if (*((volatile int *)abort_flag) || spins > (1u << 25)) { atomicExch(abort_flag, 1); break; }
+      }
+    }
+  }
+  bar_work();
+  if (rt == 0) {
+    if (stamps) stamps[1] = globaltimer_ns();
+    ms.s_ok = (*((volatile int *)abort_flag) == 0);
+  }
+  bar_work();
+  view.base0 = cm.inbox[cm.rank] + slot_off;
+  return ms.s_ok != 0;
+}
+
 __device__ __forceinline__ void flush_scalars_w(u64 *sacc, u64 *gacc, int nscal, int rt) {
   for (int i = rt; i < nscal * KUL_STRIDE; i += V6_WORK) {
     const u64 v = sacc[i];
@@ -299,7 +376,7 @@ __device__ __forceinline__ void v6_run_service(const TcgCommon &a, const Stiefel
 // (historical note) The whole CG loop used to be instantiated per role so that each warp group's code was compiled
 // against its own register budget.
 // MROLE: the instance for the M role (its own register budget); the other instance serves L and G (runtime `role`).
-template <bool MROLE>
+template <bool MROLE, bool MULTI>
 __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, const StiefelArgs &st, const int *plane_exp,
                                        unsigned char *base) {
   const int role0 = MROLE ? 2 : role_rt;
@@ -663,8 +740,10 @@ __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, co
     bar_work();
     flush_scalars_w(sacc, set, 4, rt);
     RedView rvw;
-    if (!grid_reduce_barrier_w(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
-                               a.dbg ? ms.s_stamp : nullptr)) { exit_reason = -2; continue; }
+    if (!(MULTI ? grid_reduce_barrier_multi(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS,
+                                            rvw, a.dbg ? ms.s_stamp : nullptr)
+                : grid_reduce_barrier_w(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, ACC_WORDS, rvw,
+                                        a.dbg ? ms.s_stamp : nullptr))) { exit_reason = -2; continue; }
     if (tid == 256) TL6B(43);     // barrier A released
     // first strip of phase B for this warp: start streaming it in before the scalar stage
     int cur = 0;
@@ -839,8 +918,10 @@ __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, co
     if (tid == 256) TL6B(46);     // phase B done, CTA-wide
     if (rt == 0) ms.s_next_strip = s_hi - 1;
     flush_scalars_w(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1, rt);
-    if (!grid_reduce_barrier_w(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
-                               KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr)) { exit_reason = -2; continue; }
+    if (!(MULTI ? grid_reduce_barrier_multi(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set,
+                                            SC_RV * KUL_STRIDE, KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr)
+                : grid_reduce_barrier_w(ms, rt, a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
+                                        KUL_STRIDE, rvw, a.dbg ? ms.s_stamp + 2 : nullptr))) { exit_reason = -2; continue; }
     if (role == 1) {
       if (rw == 0) {
         const int o = SC_RV * KUL_STRIDE;
@@ -887,6 +968,7 @@ __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, co
   }
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(V6_THREADS, 1)
 tcg_stiefel_v6_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, const int *plane_exp) {
   // the dynamic shared-memory window is declared 1024-byte aligned (SWIZZLE_128B operand images); all pointers are
@@ -951,10 +1033,10 @@ tcg_stiefel_v6_kernel(TcgCommon a, StiefelArgs st, const unsigned char *planes, 
     v6_run_service(a, st, planes, base);
   } else if (warp >= 8 && warp < 16) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    v6_run<true>(2, a, st, plane_exp, base);
+    v6_run<true, MULTI>(2, a, st, plane_exp, base);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    v6_run<false>(warp < 8 ? 1 : 3, a, st, plane_exp, base);
+    v6_run<false, MULTI>(warp < 8 ? 1 : 3, a, st, plane_exp, base);
   }
   tc_fence_before();
   bar_cta();
@@ -966,7 +1048,9 @@ cudaError_t launch_tcg_stiefel_v6(const TcgCommon &a, unsigned long long n_rows,
                                   const unsigned char *planes, const int *plane_exp, int sm_count, cudaStream_t stm) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tcg_stiefel_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(tcg_stiefel_v6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_TOTAL);
+    if (e) return e;
+    e = cudaFuncSetAttribute(tcg_stiefel_v6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V6_TOTAL);
     if (e) return e;
     attr = true;
   }
@@ -978,8 +1062,8 @@ cudaError_t launch_tcg_stiefel_v6(const TcgCommon &a, unsigned long long n_rows,
   const unsigned char *pl = planes;
   const int *pe = plane_exp;
   void *args[] = {(void *)&ac, (void *)&sa, (void *)&pl, (void *)&pe};
-  return cudaLaunchCooperativeKernel((const void *)tcg_stiefel_v6_kernel, dim3(grid), dim3(V6_THREADS), args,
-                                     V6_TOTAL, stm);
+  const void *fn = a.cm.world > 1 ? (const void *)tcg_stiefel_v6_kernel<true> : (const void *)tcg_stiefel_v6_kernel<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(V6_THREADS), args, V6_TOTAL, stm);
 }
 
 }  // namespace ob200

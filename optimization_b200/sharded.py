@@ -65,7 +65,7 @@ def row_partition(n: int, world: int, nb: int = 128):
 class ShardedStiefel(SingleStiefel):
     """One Stiefel tCG problem row-sharded over the ranks of a torch.distributed
     job; the reductions travel through NVLink peer memory inside the kernels."""
-    kernel_name = "tcg_stiefel_tc_kernel (v4 generation: persistent fused tCG + in-kernel NVLink peer exchange)"
+    kernel_name = "tcg_stiefel_v6_kernel<MULTI> (persistent fused tCG + in-kernel NVLink peer exchange)"
 
     def __init__(self, ctx, prob, rank, world):
         self.ctx, self.prob, self.rank, self.world = ctx, prob, rank, world

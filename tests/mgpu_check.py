@@ -40,7 +40,6 @@ def main():
                 its = {p[3] for p in parts}
                 assert len(its) == 1
                 c1 = Context(local)                       # independent single-GPU context, whole problem
-                c1.set_option("tcgen05", 2)               # same kernel generation as the row-sharded run
                 single = SingleStiefel(c1, prob)
                 o1 = single.solve_device(**kw)
                 s1 = o1.s.cpu().numpy()
