@@ -180,8 +180,9 @@ __device__ __forceinline__ bool grid_reduce_barrier_multi(V6Misc &ms, int rt, un
   if (rt == 0) {
     gen += 1;
     const unsigned target = gen * gridDim.x;
-    if (cm.world > 1) __threadfence_system();
-    else __threadfence();
+    // (gpu scope: what this phase wrote is consumed on this GPU only; the words that travel are re-stored to the peers by
+    // the publishing CTA below and released at system scope there)
+    __threadfence();
     if (stamps) stamps[0] = globaltimer_ns();
     const unsigned old = atom_add_acqrel_u32(counter, 1u);
     int ok = 1;
@@ -767,7 +768,11 @@ __device__ __forceinline__ void v6_run(const int role_rt, const TcgCommon &a, co
               const ulonglong2 wv = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + ACC_GRAM_OFF + 2 * e));
               hi = wv.x; lo = wv.y;
             } else {
-              hi = rvw.load(ACC_GRAM_OFF + 2 * e); lo = rvw.load(ACC_GRAM_OFF + 2 * e + 1);
+              hi = 0; lo = 0;
+              for (int r = 0; r < rvw.world; ++r) {           // one 16-byte load per source rank
+                const ulonglong2 wv = __ldcg(reinterpret_cast<const ulonglong2 *>(rvw.base0 + (size_t)r * rvw.stride + ACC_GRAM_OFF + 2 * e));
+                hi += wv.x; lo += wv.y;
+              }
             }
             Graw[e] = fix2_to_double((i64)hi, (i64)lo, q);
           }
