@@ -66,67 +66,75 @@ __device__ __forceinline__ void lb_dmma(double &c0, double &c1, double a, double
 constexpr int GR_TR = 32;          // rows per shared-memory tile (8 k-steps of 4 rows)
 constexpr int GR_LDA = 196;        // 192 + 4
 constexpr int GR_LDB = 68;         // 64 + 4
-__global__ void __launch_bounds__(LB_THREADS, 2) blk_gram_kernel(unsigned long long m, const double *A, int lda, int k1,
-                                                              const double *B, int ldb, int k2, double *partial) {
+constexpr int GR_THREADS = 512;    // 16 warps: the (up to 24) row tiles of the block are dealt round-robin, two per warp
+constexpr int GR_STAGE = GR_TR * (GR_LDA + GR_LDB);   // doubles per pipeline stage (66 KB)
+// 16-byte asynchronous copy global -> shared, zero-filled when `ok` is false (src-size 0)
+__device__ __forceinline__ void gr_cp16(double *dst, const double *src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+// Two-stage cp.async pipeline over 32-row tiles: the tile after the one being multiplied streams in meanwhile (the first
+// version loaded a tile, synchronised, multiplied, synchronised: ncu showed the fp64 MMA pipe 33 % active and the warps
+// waiting on the tile loads -- long scoreboard -- most of the time).  One CTA of 16 warps per SM.
+__global__ void __launch_bounds__(GR_THREADS, 1) blk_gram_kernel(unsigned long long m, const double *A, int lda, int k1,
+                                                                 const double *B, int ldb, int k2, double *partial) {
   extern __shared__ double gsm[];
-  double *As = gsm;                          // [GR_TR][GR_LDA]
-  double *Bs = gsm + GR_TR * GR_LDA;         // [GR_TR][GR_LDB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;   // fragment coordinates: (row / col index, k index)
   const int j0 = 64 * blockIdx.y;
   const int kb = min(64, k2 - j0);
   const int it_n = min((k1 + 7) >> 3, 8 * ((int)blockIdx.y + 1));   // row tiles of the block-upper triangle
+  const int ka = min(8 * it_n, LB_KMAX);                              // columns of A this block needs (a multiple of 8)
   const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
-  // rows 16-byte aligned and of even length: vector loads (the bases of LOBPCG: ld = 3 nx or nx even); else scalar
+  // rows 16-byte aligned and of even length: asynchronous 16-byte copies (the bases of LOBPCG: ld = 3 nx or nx even);
+  // otherwise scalar loads, same pipeline structure without the overlap
   const bool vec = !(lda & 1) && !(ldb & 1) && !((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) &&
                    !(k1 & 1) && !(kb & 1);
-  double acc[3][8][2];
+  double acc[2][8][2];
 #pragma unroll
-  for (int u = 0; u < 3; ++u)
+  for (int u = 0; u < 2; ++u)
 #pragma unroll
     for (int v = 0; v < 8; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
-  for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GR_TR) {
+  auto fetch = [&](unsigned long long r0, int stage) {
+    double *As = gsm + (size_t)stage * GR_STAGE, *Bs = As + GR_TR * GR_LDA;
     const int rows = (int)min((unsigned long long)GR_TR, r_hi - r0);
-    __syncthreads();
-    const int ka = min(8 * it_n, LB_KMAX);    // columns of A this block needs (a multiple of 8)
     if (vec) {
-      // 16-byte loads, no index division: lane -> column pair (+32, +64), warp -> rows (+8, +16, +24); all loads of a
-      // thread are independent and issued back to back
-      const int tx = tid & 31, ty = tid >> 5;
-#pragma unroll
-      for (int ra = 0; ra < 4; ++ra) {
-        const int rr = ty + 8 * ra;
-        const bool rok = rr < rows;
-#pragma unroll
-        for (int cb = 0; cb < 3; ++cb) {
-          const int c2 = tx + 32 * cb;                    // double2 index within the row
-          if (2 * c2 < ka) {
-            double2 v = make_double2(0.0, 0.0);
-            if (rok && 2 * c2 < k1) {
-              v = *reinterpret_cast<const double2 *>(A + (r0 + rr) * lda + 2 * c2);
-              if (2 * c2 + 1 >= k1) v.y = 0.0;
-            }
-            *reinterpret_cast<double2 *>(As + rr * GR_LDA + 2 * c2) = v;
-          }
-        }
-        double2 w = make_double2(0.0, 0.0);
-        if (rok && 2 * tx < kb) {
-          w = *reinterpret_cast<const double2 *>(B + (r0 + rr) * ldb + j0 + 2 * tx);
-          if (2 * tx + 1 >= kb) w.y = 0.0;
-        }
-        *reinterpret_cast<double2 *>(Bs + rr * GR_LDB + 2 * tx) = w;
+      const int ka2 = ka >> 1;                              // 16-byte chunks per row of the A tile
+      for (int e = tid; e < GR_TR * ka2; e += GR_THREADS) {
+        const int rr = e / ka2, c2 = e - rr * ka2;
+        const bool ok = rr < rows && 2 * c2 < k1;
+        gr_cp16(As + rr * GR_LDA + 2 * c2, ok ? A + (r0 + rr) * lda + 2 * c2 : A, ok);
+      }
+      for (int e = tid; e < GR_TR * 32; e += GR_THREADS) {
+        const int rr = e >> 5, c2 = e & 31;
+        const bool ok = rr < rows && 2 * c2 < kb;
+        gr_cp16(Bs + rr * GR_LDB + 2 * c2, ok ? B + (r0 + rr) * ldb + j0 + 2 * c2 : B, ok);
       }
     } else {
-      for (int e = tid; e < GR_TR * ka; e += LB_THREADS) {
+      for (int e = tid; e < GR_TR * ka; e += GR_THREADS) {
         const int rr = e / ka, c = e - rr * ka;
         As[rr * GR_LDA + c] = (rr < rows && c < k1) ? A[(r0 + rr) * lda + c] : 0.0;
       }
-      for (int e = tid; e < GR_TR * 64; e += LB_THREADS) {
+      for (int e = tid; e < GR_TR * 64; e += GR_THREADS) {
         const int rr = e >> 6, c = e & 63;
         Bs[rr * GR_LDB + c] = (rr < rows && c < kb) ? B[(r0 + rr) * ldb + j0 + c] : 0.0;
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int stage = 0;
+  if (r_lo < r_hi) fetch(r_lo, 0);
+  for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += GR_TR) {
+    const bool more = r0 + GR_TR < r_hi;
+    if (more) {
+      fetch(r0 + GR_TR, stage ^ 1);                         // (its buffer was released by the barrier that ended the last pass)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
+    const double *As = gsm + (size_t)stage * GR_STAGE, *Bs = As + GR_TR * GR_LDA;
 #pragma unroll 2
     for (int ks = 0; ks < GR_TR / 4; ++ks) {
       const int kr = 4 * ks + fk;
@@ -134,8 +142,8 @@ __global__ void __launch_bounds__(LB_THREADS, 2) blk_gram_kernel(unsigned long l
 #pragma unroll
       for (int v = 0; v < 8; ++v) bf[v] = Bs[kr * GR_LDB + 8 * v + fr];
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int itile = warp + 8 * u;
+      for (int u = 0; u < 2; ++u) {
+        const int itile = warp + 16 * u;
         if (itile < it_n) {                   // warp-uniform
           const double af = As[kr * GR_LDA + 8 * itile + fr];
 #pragma unroll
@@ -143,16 +151,18 @@ __global__ void __launch_bounds__(LB_THREADS, 2) blk_gram_kernel(unsigned long l
         }
       }
     }
+    __syncthreads();
+    stage ^= 1;
   }
   double *out = partial + (size_t)blockIdx.x * k1 * k2;
 #pragma unroll
-  for (int u = 0; u < 3; ++u)
+  for (int u = 0; u < 2; ++u)
 #pragma unroll
     for (int v = 0; v < 8; ++v)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int i = 8 * (warp + 8 * u) + fr, j = 8 * v + 2 * fk + c;
-        if (warp + 8 * u < it_n && i < k1 && j < kb) out[(size_t)i * k2 + j0 + j] = acc[u][v][c];
+        const int i = 8 * (warp + 16 * u) + fr, j = 8 * v + 2 * fk + c;
+        if (warp + 16 * u < it_n && i < k1 && j < kb) out[(size_t)i * k2 + j0 + j] = acc[u][v][c];
       }
 }
 // G[e] = sum_b partial[b][e], fixed order
@@ -461,14 +471,14 @@ cudaError_t launch_lob_plane_exchange(const PlaneXchg &px, double *interior, int
 cudaError_t launch_blk_gram(unsigned long long m, const double *A, int lda, int k1, const double *B, int ldb, int k2,
                             double *partial, int nb, double *G, cudaStream_t st) {
   static bool attr = false;
-  const size_t smem = sizeof(double) * ((size_t)GR_TR * GR_LDA + (size_t)GR_TR * GR_LDB);
+  const size_t smem = sizeof(double) * 2 * (size_t)GR_STAGE;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(blk_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
     attr = true;
   }
   dim3 grid(nb, (k2 + 63) / 64);
-  blk_gram_kernel<<<grid, LB_THREADS, smem, st>>>(m, A, lda, k1, B, ldb, k2, partial);
+  blk_gram_kernel<<<grid, GR_THREADS, smem, st>>>(m, A, lda, k1, B, ldb, k2, partial);
   blk_reduce_kernel<<<(k1 * k2 + 255) / 256, 256, 0, st>>>(partial, nb, k1 * k2, G);
   return cudaGetLastError();
 }
