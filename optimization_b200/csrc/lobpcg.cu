@@ -494,6 +494,87 @@ cudaError_t launch_blk_gemm(unsigned long long m, const double *S, int lds, int 
   blk_gemm_kernel<<<nb, LB_THREADS, smem, st>>>(m, S, lds, k, C, ldc, n2, out, ldo);
   return cudaGetLastError();
 }
+// The same update with a two-stage cp.async pipeline over 32-row tiles of S (rows of S 16-byte aligned: the bases of
+// LOBPCG with an even block size).  The synchronous version above spends more time waiting for a tile than multiplying
+// it.  Warp w: row tile w & 3 (8 rows), column half w >> 2 (four 8-column tiles): eight accumulator chains as before.
+constexpr int UP_TR = 32;
+constexpr int UP_STAGE = UP_TR * GM_LDS;
+__global__ void __launch_bounds__(LB_THREADS, 1) blk_update_pipe_kernel(unsigned long long m, const double *S, int lds, int ns,
+                                                                      int nx, const double *C, int ldc, double *Xo, int ldx,
+                                                                      double *Po, int ldp) {
+  extern __shared__ double sm[];
+  double *Cs = sm;                              // [LB_KMAX][GM_LDC]
+  double *Sb = sm + (size_t)LB_KMAX * GM_LDC;   // two stages of [UP_TR][GM_LDS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int rt = warp & 3, ch = warp >> 2;
+  const int k4 = (ns + 3) & ~3, k2c = k4 >> 1;  // 16-byte chunks per row
+  const bool vec_out = !(ldp & 1) && !(ldx & 1) && !((reinterpret_cast<uintptr_t>(Po) | reinterpret_cast<uintptr_t>(Xo)) & 15);
+  for (int e = tid; e < k4 * 64; e += LB_THREADS) {
+    const int kk = e >> 6, c = e & 63;
+    Cs[kk * GM_LDC + c] = (kk < ns && c < nx) ? C[(size_t)kk * ldc + c] : 0.0;
+  }
+  const unsigned long long r_lo = m * blockIdx.x / gridDim.x, r_hi = m * (blockIdx.x + 1ull) / gridDim.x;
+  auto fetch = [&](unsigned long long r0, int stage) {
+    double *Ss = Sb + (size_t)stage * UP_STAGE;
+    const int rows = (int)min((unsigned long long)UP_TR, r_hi - r0);
+    for (int e = tid; e < UP_TR * k2c; e += LB_THREADS) {
+      const int rr = e / k2c, c2 = e - rr * k2c;
+      // bytes of this chunk that hold columns < ns (0, 8 or 16): the rest is zero-filled by the copy
+      const int nbytes = rr < rows ? max(0, min(16, 8 * (ns - 2 * c2))) : 0;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(Ss + rr * GM_LDS + 2 * c2);
+      const double *src = nbytes ? S + (r0 + rr) * lds + 2 * c2 : S;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int stage = 0;
+  if (r_lo < r_hi) fetch(r_lo, 0);
+  for (unsigned long long r0 = r_lo; r0 < r_hi; r0 += UP_TR) {
+    const int rows = (int)min((unsigned long long)UP_TR, r_hi - r0);
+    if (r0 + UP_TR < r_hi) {
+      fetch(r0 + UP_TR, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                              // (also orders the first pass after the staging of C)
+    const double *Ss = Sb + (size_t)stage * UP_STAGE;
+    double ax[4][2], ap[4][2];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ax[v][0] = ax[v][1] = ap[v][0] = ap[v][1] = 0.0;
+    for (int k0 = 0; k0 < k4; k0 += 4) {
+      const double af = Ss[(8 * rt + fr) * GM_LDS + k0 + fk];
+      const bool lowp = k0 < nx, highp = k0 + 3 >= nx;      // k-step touches the X part / the (W, P) part (warp-uniform)
+      const bool mine_low = k0 + fk < nx;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const double c = Cs[(k0 + fk) * GM_LDC + 32 * ch + 8 * v + fr];
+        if (lowp) lb_dmma(ax[v][0], ax[v][1], af, (highp && !mine_low) ? 0.0 : c);
+        if (highp) lb_dmma(ap[v][0], ap[v][1], af, (lowp && mine_low) ? 0.0 : c);
+      }
+    }
+    const int rr = 8 * rt + fr;
+    if (rr < rows)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int col = 32 * ch + 8 * v + 2 * fk;
+        if (col + 1 < nx && vec_out) {
+          *reinterpret_cast<double2 *>(Po + (r0 + rr) * ldp + col) = make_double2(ap[v][0], ap[v][1]);
+          *reinterpret_cast<double2 *>(Xo + (r0 + rr) * ldx + col) = make_double2(ax[v][0] + ap[v][0], ax[v][1] + ap[v][1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (col + c < nx) {
+              Po[(r0 + rr) * ldp + col + c] = ap[v][c];
+              Xo[(r0 + rr) * ldx + col + c] = ax[v][c] + ap[v][c];
+            }
+        }
+      }
+    __syncthreads();
+    stage ^= 1;
+  }
+}
 cudaError_t launch_blk_update(unsigned long long m, const double *S, int lds, int ns, int nx, const double *C, int ldc, double *Xo,
                               int ldx, double *Po, int ldp, int nb, cudaStream_t st) {
   static bool attr = false;
@@ -502,6 +583,18 @@ cudaError_t launch_blk_update(unsigned long long m, const double *S, int lds, in
     cudaError_t e = cudaFuncSetAttribute(blk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e) return e;
     attr = true;
+  }
+  const bool pipe = !(lds & 1) && !(reinterpret_cast<uintptr_t>(S) & 15);
+  if (pipe) {
+    static bool attr2 = false;
+    const size_t smem2 = sizeof(double) * ((size_t)LB_KMAX * GM_LDC + 2 * (size_t)UP_STAGE);
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(blk_update_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      if (e) return e;
+      attr2 = true;
+    }
+    blk_update_pipe_kernel<<<nb, LB_THREADS, smem2, st>>>(m, S, lds, ns, nx, C, ldc, Xo, ldx, Po, ldp);
+    return cudaGetLastError();
   }
   blk_update_kernel<<<nb, LB_THREADS, smem, st>>>(m, S, lds, ns, nx, C, ldc, Xo, ldx, Po, ldp);
   return cudaGetLastError();
