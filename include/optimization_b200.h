@@ -113,6 +113,15 @@ int ob200_debug_sym_eig32(const double *S_host, double *Q_host, double *lambda_h
                                         (ob200_csr3_model fills it); n == 3 N, 3 <= p == r <= 8 */
 #define OB200_OP_STENCIL7 5         /* H V = 7-point Dirichlet Laplacian on a gx x gy x gz grid (x fastest) applied to each
                                         of the p columns of V; n == gx gy gz (BASELINE config C4's operator as a Hessian) */
+#define OB200_OP_HOST_CALLBACK 6    /* any other Hessian: `apply` is called once per CG iteration (reference
+                                        IterativeSolvers.h:294 with an opaque functor).  UNFUSED fallback: ob200_stpcg then
+                                        runs the Steihaug-Toint loop on the host over the device level-1 kernels (exact
+                                        reductions), statement for statement IterativeSolvers.h:211-424 */
+
+/* out = H v (or v = P r for a preconditioner callback) on n*p doubles in DEVICE memory.  The library synchronises the
+ * context's stream before the call; work the callback launches must be complete, or ordered on the context's stream,
+ * when it returns.  Return 0 on success (anything else aborts the solve with OB200_ABORTED). */
+typedef int (*ob200_apply_fn)(void *user, const double *in_dev, double *out_dev);
 
 typedef struct {
   int kind;
@@ -150,15 +159,21 @@ typedef struct {
   const uint32_t *halo_send_idx_dev;   /* own pose indices to push, grouped by destination rank */
   uint64_t halo_send_ptr[9];           /* entries [ptr[q], ptr[q+1]) of halo_send_idx_dev go to rank q */
   uint64_t halo_dst_off[8];            /* first halo slot (in poses) of my rows inside rank q's halo buffer */
+  /* OB200_OP_HOST_CALLBACK */
+  ob200_apply_fn apply;
+  void *apply_user;
 } ob200_operator;
 
 /* Replaces the optional preconditioner functor (reference
  * IterativeSolvers.h:83-85, adapter TNT.h:413-426). */
 #define OB200_PRECON_NONE 0
 #define OB200_PRECON_JACOBI 1 /* v = minv .* r */
+#define OB200_PRECON_HOST_CALLBACK 2 /* v = apply(user, r): any other preconditioner (selects the unfused loop) */
 typedef struct {
   int kind;
   const double *minv_dev; /* n*p */
+  ob200_apply_fn apply;   /* OB200_PRECON_HOST_CALLBACK */
+  void *apply_user;
 } ob200_precon;
 
 typedef struct {

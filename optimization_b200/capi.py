@@ -19,8 +19,8 @@ LIB_PATH = os.environ.get("OB200_LIB") or os.path.join(_HERE, "liboptimization_b
 OK, INVALID_ARGUMENT, CUDA_ERROR, UNSUPPORTED, NUMERIC_RANGE, ABORTED = range(6)
 EXIT_RESIDUAL, EXIT_MAX_ITERATIONS, EXIT_KERNEL, EXIT_BOUNDARY = range(4)
 EXIT_NAMES = {0: "residual", 1: "max_iterations", 2: "kernel", 3: "boundary"}
-OP_DIAG, OP_STIEFEL_BLOCKDIAG, OP_SPHERE_LOWRANK, OP_BLOCK_CSR3, OP_STENCIL7 = 1, 2, 3, 4, 5
-PRECON_NONE, PRECON_JACOBI = 0, 1
+OP_DIAG, OP_STIEFEL_BLOCKDIAG, OP_SPHERE_LOWRANK, OP_BLOCK_CSR3, OP_STENCIL7, OP_HOST_CALLBACK = 1, 2, 3, 4, 5, 6
+PRECON_NONE, PRECON_JACOBI, PRECON_HOST_CALLBACK = 0, 1, 2
 
 # every symbol include/optimization_b200.h declares (checked by the CPU test-suite)
 EXPORTS = [
@@ -44,7 +44,8 @@ class Operator(C.Structure):
                 ("csr_rowptr_dev", C.c_void_p), ("csr_colidx_dev", C.c_void_p), ("csr_blocks_dev", C.c_void_p),
                 ("csr_lambda_dev", C.c_void_p), ("csr_nnz", C.c_uint64), ("gx", C.c_uint32), ("gy", C.c_uint32),
                 ("gz", C.c_uint32), ("csr_n_halo", C.c_uint64), ("halo_send_idx_dev", C.c_void_p),
-                ("halo_send_ptr", C.c_uint64 * 9), ("halo_dst_off", C.c_uint64 * 8)]
+                ("halo_send_ptr", C.c_uint64 * 9), ("halo_dst_off", C.c_uint64 * 8),
+                ("apply", C.c_void_p), ("apply_user", C.c_void_p)]
 
 
 class BlockOperator(C.Structure):
@@ -56,7 +57,7 @@ BLK_DIAG, BLK_STENCIL7, BLK_SCALAR = 1, 2, 3
 
 
 class Precon(C.Structure):
-    _fields_ = [("kind", C.c_int), ("minv_dev", C.c_void_p)]
+    _fields_ = [("kind", C.c_int), ("minv_dev", C.c_void_p), ("apply", C.c_void_p), ("apply_user", C.c_void_p)]
 
 
 class StpcgParams(C.Structure):

@@ -784,12 +784,132 @@ static void sym_eig32(const double *S, double *Q, double *lam) {
   }
 }
 
+// ---- unfused Steihaug-Toint loop for callback operators / preconditioners --------------------------------------------
+// Reference IterativeSolvers.h:211-424 statement for statement (no `At`, no user function: how TNT calls it), with the
+// vectors on the device: H and P are host callbacks (or the pointwise Jacobi scaling), every inner product is the exact
+// device reduction (dots_sync), every update a level-1 kernel.  Three launches + one synchronisation per inner product.
+static int stpcg_generic(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
+                         const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
+  const uint64_t N = H->n * H->p;
+  int rc = ensure_vectors(ctx, N);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const uint64_t launches0 = ctx->launches;
+  double *r = ctx->r, *p = ctx->p0, *Hp = ctx->Hp, *vbuf = ctx->p1;
+  const bool has_P = P && P->kind != OB200_PRECON_NONE;
+  auto apply_cb = [&](ob200_apply_fn fn, void *user, const double *in, double *out) -> int {
+    CK(cudaStreamSynchronize(st));
+    if (fn(user, in, out)) return fail(ctx, OB200_ABORTED, "operator / preconditioner callback reported a failure");
+    return OB200_OK;
+  };
+  auto precondition = [&](const double *rin, double *vout) -> int {               // v = P(r), l.383-386
+    if (P->kind == OB200_PRECON_JACOBI) {
+      CK(launch_hadamard(N, P->minv_dev, rin, vout, ctx->sm_count, st));
+      ctx->launches += 1;
+      return OB200_OK;
+    }
+    return apply_cb(P->apply, P->apply_user, rin, vout);
+  };
+  auto axpby = [&](double a, const double *x, double b, const double *y, double *out) -> int {
+    CK(launch_axpby(N, a, x, b, y, out, ctx->sm_count, st));
+    ctx->launches += 1;
+    return OB200_OK;
+  };
+  CK(cudaMemsetAsync(s_dev, 0, sizeof(double) * N, st));                          // s_0 = 0 * g           (l.211)
+  CK(cudaMemcpyAsync(r, g_dev, sizeof(double) * N, cudaMemcpyDeviceToDevice, st)); // r_0 = g              (l.214)
+  const double *v = r;
+  if (has_P) {
+    if ((rc = precondition(r, vbuf))) return rc;
+    v = vbuf;
+  }
+  if ((rc = axpby(-1.0, v, 0.0, nullptr, p))) return rc;                          // p_0 = -v_0            (l.256)
+  double rv = 0.0;
+  {
+    const double *aa[1] = {r}, *bb[1] = {v};
+    if ((rc = dots_sync(ctx, N, 1, aa, bb, &rv))) return rc;                      // <r_0, v_0>            (l.259)
+  }
+  const double r0_norm = std::sqrt(rv);                                           // l.275
+  const double target = r0_norm * std::min(prm->kappa_fgr, std::pow(r0_norm, prm->theta));   // l.278-279
+  const double Delta_2 = prm->Delta * prm->Delta;                                 // l.271
+  double sk_M_2 = 0.0, sk_M_pk = 0.0, pk_M_2 = rv;                                // l.262-266
+  uint64_t it = 0;
+  int exit_reason = OB200_EXIT_MAX_ITERATIONS;
+  double mnorm = 0.0;
+  bool on_boundary = false;
+  for (; it < prm->max_iterations; ++it) {                                        // l.285
+    if (std::sqrt(rv) <= target) { exit_reason = OB200_EXIT_RESIDUAL; break; }    // l.290
+    if ((rc = apply_cb(H->apply, H->apply_user, p, Hp))) return rc;               // l.294
+    double d3[3];
+    {
+      const double *aa[3] = {p, Hp, p}, *bb[3] = {Hp, Hp, p};
+      if ((rc = dots_sync(ctx, N, 3, aa, bb, d3))) return rc;                     // kappa, |Hp|^2, |p|^2 (l.300-306)
+    }
+    const double kappa = d3[0];
+    if (std::sqrt(d3[1]) / std::sqrt(d3[2]) < prm->epsilon) {                     // l.305-307: p in ker(H)
+      double pr = 0.0;
+      const double *aa[1] = {p}, *bb[1] = {r};
+      if ((rc = dots_sync(ctx, N, 1, aa, bb, &pr))) return rc;                    // l.320
+      double sgn = 1.0;
+      if (pr < 0) { sgn = -1.0; sk_M_pk = -sk_M_pk; }                             // l.324-325
+      const double sigma = (-sk_M_pk + std::sqrt(sk_M_pk * sk_M_pk + pk_M_2 * (Delta_2 - sk_M_2))) / pk_M_2;   // l.330-332
+      if ((rc = axpby(1.0, s_dev, sgn * sigma, p, s_dev))) return rc;             // l.336
+      exit_reason = OB200_EXIT_KERNEL;
+      on_boundary = true;
+      break;
+    }
+    const double alpha = rv / kappa;                                              // l.341
+    const double skp1 = sk_M_2 + 2 * alpha * sk_M_pk + alpha * alpha * pk_M_2;    // l.344-345
+    if (kappa <= 0 || skp1 > Delta_2) {                                           // l.347
+      const double sigma = (-sk_M_pk + std::sqrt(sk_M_pk * sk_M_pk + pk_M_2 * (Delta_2 - sk_M_2))) / pk_M_2;   // l.355-357
+      if ((rc = axpby(1.0, s_dev, sigma, p, s_dev))) return rc;                   // l.360
+      exit_reason = OB200_EXIT_BOUNDARY;
+      on_boundary = true;
+      break;
+    }
+    if ((rc = axpby(1.0, s_dev, alpha, p, s_dev))) return rc;                     // l.374
+    if ((rc = axpby(1.0, r, alpha, Hp, r))) return rc;                            // l.377
+    if (has_P && (rc = precondition(r, vbuf))) return rc;                         // l.383-386
+    double rv_new = 0.0;
+    {
+      const double *aa[1] = {r}, *bb[1] = {v};
+      if ((rc = dots_sync(ctx, N, 1, aa, bb, &rv_new))) return rc;                // l.408
+    }
+    const double beta = rv_new / (alpha * kappa);                                 // l.412
+    sk_M_2 = skp1;                                                                // l.415
+    sk_M_pk = beta * (sk_M_pk + alpha * pk_M_2);                                  // l.416
+    pk_M_2 = rv_new + beta * beta * pk_M_2;                                       // l.417
+    if ((rc = axpby(-1.0, v, beta, p, p))) return rc;                             // l.420
+    rv = rv_new;
+  }
+  mnorm = on_boundary ? prm->Delta : std::sqrt(sk_M_2);                           // l.334 / 359 / 424
+  CK(cudaStreamSynchronize(st));
+  res->update_step_M_norm = mnorm;
+  res->num_iterations = it;
+  res->exit_reason = exit_reason;
+  res->r0_norm = r0_norm;
+  res->final_rv = rv;
+  res->kernel_launches = ctx->launches - launches0;
+  res->solve_kernel_ms = 0.f;
+  ctx->last_path = 3;
+  return OB200_OK;
+}
+
 static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
                         const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
   int rc = check_params(ctx, prm);
   if (rc) return rc;
   if (!H || !g_dev || !s_dev || !res) return fail(ctx, OB200_INVALID_ARGUMENT, "null argument");
   if (H->n == 0 || H->p == 0) return fail(ctx, OB200_INVALID_ARGUMENT, "empty operator");
+  if (H->kind == OB200_OP_HOST_CALLBACK || (P && P->kind == OB200_PRECON_HOST_CALLBACK)) {
+    if (H->kind != OB200_OP_HOST_CALLBACK)
+      return fail(ctx, OB200_UNSUPPORTED, "a callback preconditioner needs a callback operator (the unfused loop calls both)");
+    if (!H->apply || (P && P->kind == OB200_PRECON_HOST_CALLBACK && !P->apply))
+      return fail(ctx, OB200_INVALID_ARGUMENT, "callback operator / preconditioner without a function");
+    if (P && P->kind == OB200_PRECON_JACOBI && !P->minv_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "Jacobi preconditioner without minv");
+    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "callback operators are single-GPU");
+    CK(cudaSetDevice(ctx->device));
+    return stpcg_generic(ctx, H, P, g_dev, prm, s_dev, res);
+  }
   const uint64_t N = H->n * H->p;
   const double *minv = nullptr;
   if (P && P->kind == OB200_PRECON_JACOBI) {

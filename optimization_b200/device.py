@@ -122,7 +122,7 @@ class Context:
 
     @property
     def last_path(self):
-        return {1: "tcgen05", 2: "tcgen05_v4", 0: "dmma"}.get(self.lib.ob200_last_path(self.h), "?")
+        return {1: "tcgen05", 2: "tcgen05_v4", 0: "dmma", 3: "generic"}.get(self.lib.ob200_last_path(self.h), "?")
 
     def synchronize(self):
         self._check(self.lib.ob200_synchronize(self.h))
@@ -135,6 +135,52 @@ class Context:
         op.p = 1
         op.diag_dev = d.data_ptr()
         return OperatorHandle(self, op, [d])
+
+    def callback_operator(self, n: int, p: int, fn) -> "OperatorHandle":
+        """OB200_OP_HOST_CALLBACK: `fn(v, out)` receives torch views (n x p, float64, this device) of the library's
+        device buffers and must fill `out` with H v (unfused fallback: ob200_stpcg runs the reference loop on the host
+        over the device level-1 kernels)."""
+        cb, keep = self._callback(n, p, fn)
+        op = capi.Operator()
+        op.kind = capi.OP_HOST_CALLBACK
+        op.n, op.p = n, p
+        op.apply = C.cast(cb, C.c_void_p).value
+        op.apply_user = None
+        return OperatorHandle(self, op, [cb, keep])
+
+    def callback_precon(self, n: int, p: int, fn):
+        """OB200_PRECON_HOST_CALLBACK: v = fn(r, out) (to be used with a callback operator)."""
+        cb, keep = self._callback(n, p, fn)
+        pc = capi.Precon()
+        pc.kind = capi.PRECON_HOST_CALLBACK
+        pc.minv_dev = None
+        pc.apply = C.cast(cb, C.c_void_p).value
+        pc.apply_user = None
+        pc._keep = (cb, keep)
+        return pc
+
+    def _callback(self, n, p, fn):
+        dev = self.device
+
+        class _View:          # a device pointer as a CUDA array (zero-copy torch view)
+            def __init__(self, ptr, ro):
+                self.__cuda_array_interface__ = {"shape": (n, p), "typestr": "<f8", "data": (ptr, ro), "version": 2}
+
+        def trampoline(user, in_ptr, out_ptr):
+            try:
+                with torch.cuda.device(dev):
+                    v = torch.as_tensor(_View(in_ptr, False), device=f"cuda:{dev}")   # (torch has no read-only views)
+                    out = torch.as_tensor(_View(out_ptr, False), device=f"cuda:{dev}")
+                    fn(v, out)
+                    torch.cuda.synchronize(dev)      # contract: complete (or stream-ordered) on return
+                return 0
+            except Exception:   # never let a Python exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)(trampoline)
+        return cb, trampoline
 
     def stiefel_operator(self, A_bf16: torch.Tensor, Y: torch.Tensor) -> "OperatorHandle":
         """Hess f(Y)[V] = P_Y(A V - V sym(Y^T A Y)); computes S on the device."""
@@ -298,7 +344,7 @@ class Context:
         prm = capi.StpcgParams(float(Delta), int(max_iterations), float(kappa_fgr), float(theta),
                                float(epsilon))
         res = capi.StpcgResult()
-        pc = self.jacobi(minv)
+        pc = minv if isinstance(minv, capi.Precon) else self.jacobi(minv)
         if host:
             if s_out is None:
                 s_out = np.empty_like(g) if isinstance(g, np.ndarray) else torch.empty_like(g)

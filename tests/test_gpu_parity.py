@@ -92,6 +92,49 @@ def test_diag_vs_oracle_ragged(ctx, port, n, precon):
         assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
 
 
+@pytest.mark.parametrize("precon", ["none", "jacobi", "callback"])
+def test_host_callback_operator_runs_the_reference_loop(ctx, port, precon):
+    """OB200_OP_HOST_CALLBACK / OB200_PRECON_HOST_CALLBACK (the unfused fallback for arbitrary Hessian /
+    preconditioner functors): ob200_stpcg runs IterativeSolvers.h:211-424 on the host over device vectors, the functors
+    being host callbacks.  Same iteration counts / exits / steps as the oracle and as the fused diagonal kernel, on a
+    positive definite, an indefinite and a singular operator."""
+    import torch
+    n = 4099
+    dp = P.make_diag(n, seed=5)
+    g = ctx.to_device(dp.g)
+    minv_np = dp.minv if precon != "none" else None
+    minv = ctx.to_device(dp.minv)
+    for h_np, kws in ((dp.h, (dict(Delta=1e6, max_iterations=40, kappa_fgr=1e-10, theta=0.),
+                              dict(Delta=1e-3, max_iterations=40, kappa_fgr=.1, theta=.5),
+                              dict(Delta=1e6, max_iterations=3, kappa_fgr=1e-10, theta=0.))),
+                      (np.where(np.arange(n) % 7 == 0, -dp.h, dp.h), (dict(Delta=50., max_iterations=100, kappa_fgr=1e-8, theta=0.),)),
+                      (np.zeros(n), (dict(Delta=50., max_iterations=100, kappa_fgr=1e-8, theta=0.),))):
+        h = ctx.to_device(h_np)
+        calls = {"H": 0, "P": 0}
+
+        def apply_H(v, out, h=h):
+            calls["H"] += 1
+            torch.mul(h.view_as(v), v, out=out)
+
+        def apply_P(r, out):
+            calls["P"] += 1
+            torch.mul(minv.view_as(r), r, out=out)
+
+        Hcb = ctx.callback_operator(n, 1, apply_H)
+        pc = {"none": None, "jacobi": minv, "callback": ctx.callback_precon(n, 1, apply_P)}[precon]
+        for kw in kws:
+            s_ref, mn_ref, it_ref, why_ref = port.stpcg_diag(dp.g, h_np, minv_np, **kw)
+            out = ctx.stpcg(g, Hcb, minv=pc, **kw)
+            assert ctx.last_path == "generic"
+            assert (out.num_iterations, out.exit_reason) == (it_ref, why_ref), kw
+            assert rel(out.s.cpu().numpy().ravel(), s_ref) < RTOL
+            assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+            fused = ctx.stpcg(g, ctx.diag_operator(h), minv=(minv if precon != "none" else None), **kw)
+            assert (fused.num_iterations, fused.exit_reason) == (out.num_iterations, out.exit_reason)
+            assert rel(out.s.cpu().numpy().ravel(), fused.s.cpu().numpy().ravel()) < RTOL
+        assert calls["H"] > 0 and (calls["P"] > 0) == (precon == "callback")
+
+
 def test_diag_indefinite_and_kernel(ctx, port):
     n = 5000
     dp = P.make_diag(n, seed=3)
