@@ -75,6 +75,20 @@ __device__ __forceinline__ double pose_sum(double v) {
   return v;
 }
 
+// Nine consecutive doubles at an 8-byte aligned address (a 3x3 block of the CSR array, Lambda_i) as five 16-byte loads
+// from the enclosing 16-byte granules: phase A2 is bound by L1 wavefronts (every load instruction of a warp touches
+// one line per pose, eight lines), so five instructions instead of nine is 4/9 fewer wavefronts for these operands.
+// The granules lie inside the same pages as the nine doubles, whatever their parity.
+__device__ __forceinline__ void load9(const double *p, double (&b)[9]) {
+  const unsigned long long addr = (unsigned long long)p;
+  const double2 *q = reinterpret_cast<const double2 *>(addr & ~15ull);
+  const bool odd = (addr & 8ull) != 0;
+  const double2 d0 = __ldg(q), d1 = __ldg(q + 1), d2 = __ldg(q + 2), d3 = __ldg(q + 3), d4 = __ldg(q + 4);
+  b[0] = odd ? d0.y : d0.x; b[1] = odd ? d1.x : d0.y; b[2] = odd ? d1.y : d1.x; b[3] = odd ? d2.x : d1.y;
+  b[4] = odd ? d2.y : d2.x; b[5] = odd ? d3.x : d2.y; b[6] = odd ? d3.y : d3.x; b[7] = odd ? d4.x : d3.y;
+  b[8] = odd ? d4.y : d4.x;
+}
+
 // One pose, one column per lane (c < r active): w = (2 Q V - Lambda V)(pose, :, c), then the tangent projection.
 // V is read with L2 loads (other CTAs wrote it in the previous phase).  Returns hp[3]; vi[3] = V(pose, :, c).
 template <int LPP>
@@ -88,24 +102,39 @@ __device__ __forceinline__ void csr3_pose_apply(const SparseArgs &sp, unsigned l
   double w0 = 0.0, w1 = 0.0, w2 = 0.0;
   if (active) {
     const unsigned long long e0 = __ldg(sp.rowptr + pose), e1 = __ldg(sp.rowptr + pose + 1);
-    for (unsigned long long e = e0; e < e1; ++e) {
-      const double *B = sp.blocks + 9 * e;
-      const unsigned long long jcol = __ldg(sp.colidx + e);
-      const double *Vj = (jcol < sp.units ? V + (size_t)3 * jcol * r : sp.halo + (size_t)3 * (jcol - sp.units) * r) + c;
-      const double v0 = __ldcg(Vj), v1 = __ldcg(Vj + r), v2 = __ldcg(Vj + 2 * r);
-      const double b0 = __ldg(B), b1 = __ldg(B + 1), b2 = __ldg(B + 2), b3 = __ldg(B + 3), b4 = __ldg(B + 4),
-                   b5 = __ldg(B + 5), b6 = __ldg(B + 6), b7 = __ldg(B + 7), b8 = __ldg(B + 8);
-      z0 = fma(b0, v0, z0); z0 = fma(b1, v1, z0); z0 = fma(b2, v2, z0);
-      z1 = fma(b3, v0, z1); z1 = fma(b4, v1, z1); z1 = fma(b5, v2, z1);
-      z2 = fma(b6, v0, z2); z2 = fma(b7, v1, z2); z2 = fma(b8, v2, z2);
+    // Edges in chunks of four: the four column indices first, then the twelve gathered values of V (the index -> gather
+    // dependency is the latency chain of this phase: one chain per chunk instead of one per edge), then the blocks and the
+    // FMAs in edge order (same arithmetic, same order as an edge-by-edge loop).
+    for (unsigned long long e = e0; e < e1; e += 4) {
+      unsigned long long jc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) jc[q] = (e + q < e1) ? (unsigned long long)__ldg(sp.colidx + e + q) : pose;
+      double vv[4][3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double *Vj = (jc[q] < sp.units ? V + (size_t)3 * jc[q] * r : sp.halo + (size_t)3 * (jc[q] - sp.units) * r) + c;
+        vv[q][0] = __ldcg(Vj); vv[q][1] = __ldcg(Vj + r); vv[q][2] = __ldcg(Vj + 2 * r);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (e + q < e1) {
+          double b[9];
+          load9(sp.blocks + 9 * (e + q), b);
+          const double v0 = vv[q][0], v1 = vv[q][1], v2 = vv[q][2];
+          z0 = fma(b[0], v0, z0); z0 = fma(b[1], v1, z0); z0 = fma(b[2], v2, z0);
+          z1 = fma(b[3], v0, z1); z1 = fma(b[4], v1, z1); z1 = fma(b[5], v2, z1);
+          z2 = fma(b[6], v0, z2); z2 = fma(b[7], v1, z2); z2 = fma(b[8], v2, z2);
+        }
+      }
     }
     const double *Vi = V + (size_t)3 * pose * r + c;
     vi[0] = __ldcg(Vi); vi[1] = __ldcg(Vi + r); vi[2] = __ldcg(Vi + 2 * r);
-    const double *L = sp.lambda + 9 * pose;
+    double L[9];
+    load9(sp.lambda + 9 * pose, L);
     w0 = __dmul_rn(2.0, z0); w1 = __dmul_rn(2.0, z1); w2 = __dmul_rn(2.0, z2);
-    w0 = fma(-__ldg(L + 0), vi[0], w0); w0 = fma(-__ldg(L + 1), vi[1], w0); w0 = fma(-__ldg(L + 2), vi[2], w0);
-    w1 = fma(-__ldg(L + 3), vi[0], w1); w1 = fma(-__ldg(L + 4), vi[1], w1); w1 = fma(-__ldg(L + 5), vi[2], w1);
-    w2 = fma(-__ldg(L + 6), vi[0], w2); w2 = fma(-__ldg(L + 7), vi[1], w2); w2 = fma(-__ldg(L + 8), vi[2], w2);
+    w0 = fma(-L[0], vi[0], w0); w0 = fma(-L[1], vi[1], w0); w0 = fma(-L[2], vi[2], w0);
+    w1 = fma(-L[3], vi[0], w1); w1 = fma(-L[4], vi[1], w1); w1 = fma(-L[5], vi[2], w1);
+    w2 = fma(-L[6], vi[0], w2); w2 = fma(-L[7], vi[1], w2); w2 = fma(-L[8], vi[2], w2);
     const double *Xi = sp.X + (size_t)3 * pose * r + c;
     x0 = __ldg(Xi); x1 = __ldg(Xi + r); x2 = __ldg(Xi + 2 * r);
   }
@@ -144,15 +173,33 @@ __device__ __forceinline__ double stencil_elem(const SparseArgs &sp, unsigned lo
   return h;
 }
 
-// out = H(V) over the units this CTA owns ([w0, w1) warp-iterations); optional partial sums <V,HV>, <HV,HV>
+#ifndef OB200_C5_DYN
+#define OB200_C5_DYN 1
+#endif
+// out = H(V) over the units this CTA owns ([it0, it1) warp-iterations, round-robin over the warps), then -- fused kernel
+// only -- over warp-iterations [dyn0, dyn1) handed out one at a time through `ticket` (levels the tail: the duration of
+// a warp-iteration varies from SM to SM); optional partial sums <V,HV>, <HV,HV>
 template <int LPP>
 __device__ __forceinline__ void sparse_apply_range(const SparseArgs &sp, unsigned long long N, const double *V, double *out,
                                                    unsigned long long it0, unsigned long long it1, int warp, int lane,
-                                                   u64 *sacc /* nullable */) {
+                                                   u64 *sacc /* nullable */, unsigned *ticket = nullptr,
+                                                   unsigned long long dyn0 = 0, unsigned long long dyn1 = 0) {
   if (sp.kind == 4) {
     constexpr int PPW = 32 / LPP;                           // poses per warp iteration
+    constexpr unsigned long long NONE = ~0ull;
     const int pl = lane / LPP, c = lane % LPP;
-    for (unsigned long long it = it0 + warp; it < it1; it += TCG_WARPS) {
+    // next warp-iteration of this warp: the static round-robin first, then tickets
+    auto successor = [&](unsigned long long it) -> unsigned long long {
+      if (it < it1 && it + TCG_WARPS < it1) return it + TCG_WARPS;
+      if (!OB200_C5_DYN || ticket == nullptr) return NONE;
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(ticket, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      return dyn0 + t < dyn1 ? dyn0 + t : NONE;
+    };
+    unsigned long long it = it0 + warp < it1 ? it0 + warp : successor(NONE - TCG_WARPS);
+    while (it != NONE) {
+      const unsigned long long nxt = successor(it);         // (ticket latency hidden behind this iteration)
       const unsigned long long pose = it * PPW + pl;
       const bool active = pose < sp.units && c < sp.r;
       double hp[3], vi[3];
@@ -169,6 +216,7 @@ __device__ __forceinline__ void sparse_apply_range(const SparseArgs &sp, unsigne
         if (lane == 0) kul_add_atomic(sacc + SC_PHP * KUL_STRIDE, php);
         if (lane == 1) kul_add_atomic(sacc + SC_HPHP * KUL_STRIDE, hphp);
       }
+      it = nxt;
     }
   } else {
     for (unsigned long long it = it0 + warp; it < it1; it += TCG_WARPS) {
@@ -197,8 +245,14 @@ __device__ __forceinline__ unsigned long long sparse_iterations(const SparseArgs
   return (N + 255ull) / 256ull;
 }
 
+// Two CTAs per SM (64 registers per thread): phase A2 is a chain of dependent gathers (row pointer -> column index ->
+// row of p), so its rate is set by the number of warps in flight, not by the width of one warp's loads; the streaming
+// phases use runs of SP_RUN elements per warp to stay inside that register budget.
+constexpr int SP_CTAS_PER_SM = 2;
+constexpr int SP_CH = 2;                                   // double2 per lane and array in the streaming phases
+constexpr unsigned long long SP_RUN = 64ull * SP_CH;      // elements per warp iteration there
 template <int LPP>
-__global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a, SparseArgs sp) {
+__global__ void __launch_bounds__(TCG_THREADS, SP_CTAS_PER_SM) tcg_sparse_kernel(TcgCommon a, SparseArgs sp) {
   __shared__ CgShared sh;
   __shared__ u64 sacc[ACC_NSCAL * KUL_STRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,10 +270,14 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
   __syncthreads();
 
   const unsigned long long N = a.N;
-  const unsigned long long runs = (N + 255ull) / 256ull;
+  const unsigned long long runs = (N + SP_RUN - 1ull) / SP_RUN;
   const unsigned long long u0 = runs * blockIdx.x / gridDim.x, u1 = runs * (blockIdx.x + 1ull) / gridDim.x;
   const unsigned long long its = sparse_iterations(sp, N, LPP);
-  const unsigned long long i0 = its * blockIdx.x / gridDim.x, i1 = its * (blockIdx.x + 1ull) / gridDim.x;
+  // phase A2 of the block-CSR operator: 7/8 of the warp-iterations are owned statically, the rest is handed out by
+  // ticket (two counters behind the barrier word, used alternately; CTA 0 clears the idle one in phase A1)
+  const unsigned long long its_static = (OB200_C5_DYN && sp.kind == 4) ? its - its / 8 : its;
+  const unsigned long long i0 = its_static * blockIdx.x / gridDim.x, i1 = its_static * (blockIdx.x + 1ull) / gridDim.x;
+  unsigned *const tickets = a.barrier + 4;
   unsigned gen = 0, phase = 0;
   int exit_reason = -1;
 
@@ -241,15 +299,16 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
     // ------------------------------ phase A1 ------------------------------
     u64 *set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
     recycle(phase);
+    if (blockIdx.x == 0 && threadIdx.x == 0) tickets[(k + 1ull) & 1ull] = 0u;   // idle until phase A2 of iteration k + 1
     for (unsigned long long u = u0 + warp; u < u1; u += TCG_WARPS) {
-      const unsigned long long e0 = u * 256ull;
-      double2 r[4], po[4], m[4], pn[4];
-      sp_load<4>(a.r, N, e0, lane, r);
-      if (k) sp_load<4>(p_old, N, e0, lane, po);
-      if (a.minv) sp_load<4>(a.minv, N, e0, lane, m);
+      const unsigned long long e0 = u * SP_RUN;
+      double2 r[SP_CH], po[SP_CH], m[SP_CH], pn[SP_CH];
+      sp_load<SP_CH>(a.r, N, e0, lane, r);
+      if (k) sp_load<SP_CH>(p_old, N, e0, lane, po);
+      if (a.minv) sp_load<SP_CH>(a.minv, N, e0, lane, m);
       double pp = 0.0, pr = 0.0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < SP_CH; ++i) {
         const double vx = a.minv ? m[i].x * r[i].x : r[i].x;
         const double vy = a.minv ? m[i].y * r[i].y : r[i].y;
         pn[i].x = k ? fma(beta, po[i].x, -vx) : -vx;                        // l.256 / l.420
@@ -257,7 +316,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
         pp = fma(pn[i].x, pn[i].x, pp); pp = fma(pn[i].y, pn[i].y, pp);
         pr = fma(pn[i].x, r[i].x, pr);  pr = fma(pn[i].y, r[i].y, pr);
       }
-      sp_store<4>(p_new, N, e0, lane, pn);
+      sp_store<SP_CH>(p_new, N, e0, lane, pn);
       pp = warp_sum(pp); pr = warp_sum(pr);
       if (lane == 0) kul_add_atomic(sacc + SC_PP * KUL_STRIDE, pp);
       if (lane == 1) kul_add_atomic(sacc + SC_PR * KUL_STRIDE, pr);
@@ -282,15 +341,24 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
     __syncthreads();
     // <p,p>, <p,r> ride in the set of phase A2 (same reduction); this barrier only orders p
     RedView rvw;
+#ifdef OB200_TIMELINE_BUILD
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && sh.k == 3) a.dbg[4096 + 0] = globaltimer_ns();
+#endif
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, 0, rvw)) { exit_reason = -2; break; }
     ++phase;
 
+#ifdef OB200_TIMELINE_BUILD
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && sh.k == 3) a.dbg[4096 + 1] = globaltimer_ns();
+#endif
     // ------------------------------ phase A2 ------------------------------
     set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
     recycle(phase);
-    sparse_apply_range<LPP>(sp, N, p_new, a.Hp, i0, i1, warp, lane, sacc);
+    sparse_apply_range<LPP>(sp, N, p_new, a.Hp, i0, i1, warp, lane, sacc, tickets + (k & 1ull), its_static, its);
     __syncthreads();
     flush_scalars(sacc, set, 4);
+#ifdef OB200_TIMELINE_BUILD
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && sh.k == 3) a.dbg[4096 + 2] = globaltimer_ns();
+#endif
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, 0, 4 * KUL_STRIDE, rvw)) {
       exit_reason = -2;
       break;
@@ -305,45 +373,51 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
     if (sh.action != ACT_CONTINUE) {
       // boundary / kernel exit: s += sigma * p   (l.336 / l.360)
       for (unsigned long long u = u0 + warp; u < u1; u += TCG_WARPS) {
-        const unsigned long long e0 = u * 256ull;
-        double2 s[4], p[4];
-        sp_load<4>(a.s, N, e0, lane, s);
-        sp_load<4>(p_new, N, e0, lane, p);
+        const unsigned long long e0 = u * SP_RUN;
+        double2 s[SP_CH], p[SP_CH];
+        sp_load<SP_CH>(a.s, N, e0, lane, s);
+        sp_load<SP_CH>(p_new, N, e0, lane, p);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { s[i].x = fma(step, p[i].x, s[i].x); s[i].y = fma(step, p[i].y, s[i].y); }
-        sp_store<4>(a.s, N, e0, lane, s);
+        for (int i = 0; i < SP_CH; ++i) { s[i].x = fma(step, p[i].x, s[i].x); s[i].y = fma(step, p[i].y, s[i].y); }
+        sp_store<SP_CH>(a.s, N, e0, lane, s);
       }
       exit_reason = sh.action - 1;
       break;
     }
 
+#ifdef OB200_TIMELINE_BUILD
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && sh.k == 3) a.dbg[4096 + 3] = globaltimer_ns();
+#endif
     // ------------------------------ phase B ------------------------------
     set = a.acc + (phase % ACC_SETS) * ACC_WORDS;
     recycle(phase);
     for (unsigned long long u = u0 + warp; u < u1; u += TCG_WARPS) {
-      const unsigned long long e0 = u * 256ull;
-      double2 s[4], p[4], r[4], hp[4], m[4];
-      sp_load<4>(a.s, N, e0, lane, s);
-      sp_load<4>(p_new, N, e0, lane, p);
-      sp_load<4>(a.r, N, e0, lane, r);
-      sp_load<4>(a.Hp, N, e0, lane, hp);
-      if (a.minv) sp_load<4>(a.minv, N, e0, lane, m);
+      const unsigned long long e0 = u * SP_RUN;
+      double2 s[SP_CH], p[SP_CH], r[SP_CH], hp[SP_CH], m[SP_CH];
+      sp_load<SP_CH>(a.s, N, e0, lane, s);
+      sp_load<SP_CH>(p_new, N, e0, lane, p);
+      sp_load<SP_CH>(a.r, N, e0, lane, r);
+      sp_load<SP_CH>(a.Hp, N, e0, lane, hp);
+      if (a.minv) sp_load<SP_CH>(a.minv, N, e0, lane, m);
       double rv = 0.0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < SP_CH; ++i) {
         s[i].x = fma(step, p[i].x, s[i].x);  s[i].y = fma(step, p[i].y, s[i].y);     // l.374
         r[i].x = fma(step, hp[i].x, r[i].x); r[i].y = fma(step, hp[i].y, r[i].y);    // l.377
         const double vx = a.minv ? m[i].x * r[i].x : r[i].x;                          // l.383/386
         const double vy = a.minv ? m[i].y * r[i].y : r[i].y;
         rv = fma(r[i].x, vx, rv); rv = fma(r[i].y, vy, rv);                           // l.408
       }
-      sp_store<4>(a.s, N, e0, lane, s);
-      sp_store<4>(a.r, N, e0, lane, r);
+      sp_store<SP_CH>(a.s, N, e0, lane, s);
+      sp_store<SP_CH>(a.r, N, e0, lane, r);
       rv = warp_sum(rv);
       if (lane == 0) kul_add_atomic(sacc + SC_RV * KUL_STRIDE, rv);
     }
     __syncthreads();
     flush_scalars(sacc + SC_RV * KUL_STRIDE, set + SC_RV * KUL_STRIDE, 1);
+#ifdef OB200_TIMELINE_BUILD
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && sh.k == 3) a.dbg[4096 + 4] = globaltimer_ns();
+#endif
     if (!grid_reduce_barrier(a.barrier, gen, a.abort_flag, a.cm, a.cm.epoch + phase, set, SC_RV * KUL_STRIDE,
                              KUL_STRIDE, rvw)) {
       exit_reason = -2;
@@ -375,7 +449,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) tcg_sparse_kernel(TcgCommon a,
 
 // ---- stand-alone pieces ---------------------------------------------------------------------------------------
 template <int LPP>
-__global__ void __launch_bounds__(TCG_THREADS) sparse_apply_kernel(unsigned long long N, SparseArgs sp, const double *V,
+__global__ void __launch_bounds__(TCG_THREADS, SP_CTAS_PER_SM) sparse_apply_kernel(unsigned long long N, SparseArgs sp, const double *V,
                                                                    double *out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long its = sparse_iterations(sp, N, LPP);
@@ -466,9 +540,9 @@ __global__ void csr3_retract_kernel(unsigned long long N, int r, const double *X
 }
 
 // ---- host launchers -------------------------------------------------------------------------------------------
-static int sparse_grid(unsigned long long work_items, int sm_count) {
+static int sparse_grid(unsigned long long work_items, int ctas) {
   unsigned long long g = (work_items + TCG_WARPS - 1) / TCG_WARPS;
-  if (g > (unsigned long long)sm_count) g = sm_count;
+  if (g > (unsigned long long)ctas) g = ctas;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -476,9 +550,14 @@ cudaError_t launch_tcg_sparse(const TcgCommon &a, const SparseArgs &sp, int sm_c
   TcgCommon ac = a;
   SparseArgs sa = sp;
   void *args[] = {(void *)&ac, (void *)&sa};
-  const unsigned long long runs = (a.N + 255ull) / 256ull;
-  const int grid = sparse_grid(runs, sm_count);
+  const unsigned long long runs = (a.N + SP_RUN - 1ull) / SP_RUN;
   const void *fn = (sp.kind == 4 && sp.r > 4) ? (const void *)tcg_sparse_kernel<8> : (const void *)tcg_sparse_kernel<4>;
+  int per_sm = 0;   // co-resident CTAs per SM (cooperative launch: the grid must fit at once)
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TCG_THREADS, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  if (per_sm > SP_CTAS_PER_SM) per_sm = SP_CTAS_PER_SM;
+  const int grid = sparse_grid(runs, per_sm * sm_count);
   return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(TCG_THREADS), args, 0, st);
 }
 cudaError_t launch_sparse_apply(unsigned long long N, const SparseArgs &sp, const double *V, double *out, int sm_count,
