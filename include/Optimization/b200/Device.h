@@ -219,13 +219,29 @@ struct ProjectedJacobiPreconditioner {
   }
 };
 
-// One fused tCG solve through the C ABI (ob200_stpcg): the whole STPCG loop in one persistent kernel.
+// The same preconditioner bound to the point (what TNT's inner views hand to STPCG): callable, and recognised by the STPCG
+// dispatch hook, which passes it to ob200_stpcg as OB200_PRECON_STIEFEL_PROJECTED_JACOBI (the C ABI runs the loop with
+// the one-launch device HVP and no temporaries).
+struct BoundProjectedJacobi {
+  ob200_context *ctx = nullptr;
+  std::shared_ptr<const DeviceMatrix> minv;
+  const DeviceMatrix *Y = nullptr;   // the outer iterate; outlives the inner solve (TNT.h:400-426)
+  template <typename... Args>
+  std::pair<DeviceMatrix, std::nullptr_t> operator()(const DeviceMatrix &r, Args &...a) const {
+    return {ProjectedJacobiPreconditioner{ctx, minv}(*Y, r, a...), nullptr};
+  }
+};
+
+// One tCG solve through the C ABI (ob200_stpcg): the whole STPCG loop in one persistent kernel (projected: the unfused
+// device loop of the C ABI).
 inline DeviceMatrix fused_stpcg(const OperatorState &st, const DeviceMatrix *minv, const DeviceMatrix &g,
                                 double &update_step_M_norm, size_t &num_iterations, double Delta,
-                                size_t max_iterations, double kappa_fgr, double theta, double epsilon) {
+                                size_t max_iterations, double kappa_fgr, double theta, double epsilon,
+                                bool projected = false) {
   DeviceMatrix s = g.like();
   ob200_stpcg_params prm{Delta, max_iterations, kappa_fgr, theta, epsilon};
-  ob200_precon pc{minv ? OB200_PRECON_JACOBI : OB200_PRECON_NONE, minv ? minv->data() : nullptr};
+  ob200_precon pc{minv ? (projected ? OB200_PRECON_STIEFEL_PROJECTED_JACOBI : OB200_PRECON_JACOBI) : OB200_PRECON_NONE,
+                  minv ? minv->data() : nullptr};
   ob200_stpcg_result res{};
   check(st.ctx, ob200_stpcg(st.ctx, &st.op, &pc, g.data(), &prm, s.data(), &res));
   update_step_M_norm = res.update_step_M_norm;
@@ -427,6 +443,8 @@ struct InnerViews<b200::DeviceMatrix, b200::DeviceMatrix, double, Args...> {
     if constexpr (std::is_same<Multiplier, std::nullptr_t>::value) {
       if (const b200::JacobiPreconditioner *jp = precon->template target<b200::JacobiPreconditioner>())
         return LinearAlgebra::STPCGPreconditioner<M, Multiplier, Args...>(b200::BoundJacobi{jp->minv});
+      if (const b200::ProjectedJacobiPreconditioner *pj = precon->template target<b200::ProjectedJacobiPreconditioner>())
+        return LinearAlgebra::STPCGPreconditioner<M, Multiplier, Args...>(b200::BoundProjectedJacobi{pj->ctx, pj->minv, &x});
     }
     return LinearAlgebra::STPCGPreconditioner<M, Multiplier, Args...>(
         [&x, &precon](const M &v, Args &...a) -> std::pair<M, Multiplier> { return {(*precon)(x, v, a...), Multiplier()}; });
@@ -497,13 +515,22 @@ struct FusedSTPCG<b200::DeviceMatrix, std::nullptr_t, double, Args...> {
     const b200::BoundHessian *bh = H.template target<b200::BoundHessian>();
     if (!bh || !ip.template target<b200::FrobeniusProduct>()) return false;
     const b200::DeviceMatrix *minv = nullptr;
+    bool projected = false;
     if (P) {
-      const b200::BoundJacobi *bj = P->template target<b200::BoundJacobi>();
-      if (!bj) return false;
-      minv = bj->minv.get();
+      if (const b200::BoundJacobi *bj = P->template target<b200::BoundJacobi>()) {
+        minv = bj->minv.get();
+      } else if (const b200::BoundProjectedJacobi *pj = P->template target<b200::BoundProjectedJacobi>()) {
+        // the C ABI projects at the Stiefel descriptor's own copy of the point (TNT builds the Hessian and the
+        // preconditioner at the same outer iterate); other operators: the generic loop calls the functor
+        if (bh->st->op.kind != OB200_OP_STIEFEL_BLOCKDIAG) return false;
+        minv = pj->minv.get();
+        projected = true;
+      } else {
+        return false;
+      }
     }
     out = b200::fused_stpcg(*bh->st, minv, g, update_step_M_norm, num_iterations, Delta, max_iterations, kappa_fgr,
-                            theta, epsilon);
+                            theta, epsilon, projected);
     return true;
   }
 };

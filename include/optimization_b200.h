@@ -169,6 +169,11 @@ typedef struct {
 #define OB200_PRECON_NONE 0
 #define OB200_PRECON_JACOBI 1 /* v = minv .* r */
 #define OB200_PRECON_HOST_CALLBACK 2 /* v = apply(user, r): any other preconditioner (selects the unfused loop) */
+#define OB200_PRECON_STIEFEL_PROJECTED_JACOBI 3 /* v = P_Y(minv .* r), P_Y(Z) = Z - Y sym(Y^T Z), Y = the operator's Y_dev:
+                                                  * the tangent-space preserving form of the Jacobi scaling for
+                                                  * OB200_OP_STIEFEL_BLOCKDIAG (what TNT's adapter, TNT.h:413-426, hands
+                                                  * to STPCG for precon(Y, V) = P_Y(minv o V)); runs the unfused loop
+                                                  * with the one-launch device HVP */
 typedef struct {
   int kind;
   const double *minv_dev; /* n*p */

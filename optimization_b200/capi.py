@@ -20,7 +20,7 @@ OK, INVALID_ARGUMENT, CUDA_ERROR, UNSUPPORTED, NUMERIC_RANGE, ABORTED = range(6)
 EXIT_RESIDUAL, EXIT_MAX_ITERATIONS, EXIT_KERNEL, EXIT_BOUNDARY = range(4)
 EXIT_NAMES = {0: "residual", 1: "max_iterations", 2: "kernel", 3: "boundary"}
 OP_DIAG, OP_STIEFEL_BLOCKDIAG, OP_SPHERE_LOWRANK, OP_BLOCK_CSR3, OP_STENCIL7, OP_HOST_CALLBACK = 1, 2, 3, 4, 5, 6
-PRECON_NONE, PRECON_JACOBI, PRECON_HOST_CALLBACK = 0, 1, 2
+PRECON_NONE, PRECON_JACOBI, PRECON_HOST_CALLBACK, PRECON_STIEFEL_PROJECTED_JACOBI = 0, 1, 2, 3
 
 # every symbol include/optimization_b200.h declares (checked by the CPU test-suite)
 EXPORTS = [

@@ -128,6 +128,8 @@ struct ob200_context {
   // workspace
   size_t vec_capacity = 0;        // doubles per work vector
   double *r = nullptr, *p0 = nullptr, *p1 = nullptr, *Hp = nullptr, *gs = nullptr; // gs: staging for g/s (host entry)
+  double *gen_vec = nullptr;      // the unfused loop's own r | p | Hp | v | scratch (stpcg_generic)
+  size_t gen_capacity = 0;
   size_t gs_capacity = 0;
   u64 *acc = nullptr;             // ACC_SETS * ACC_WORDS
   unsigned *barrier = nullptr;    // [0] counter, [1] abort flag (int)
@@ -248,6 +250,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->r); cudaFree(ctx->p0); cudaFree(ctx->p1); cudaFree(ctx->Hp); cudaFree(ctx->gs);
+  cudaFree(ctx->gen_vec);
   cudaFree(ctx->acc); cudaFree(ctx->barrier); cudaFree(ctx->dres); cudaFree(ctx->dscal);
   cudaFree(ctx->drot); cudaFree(ctx->yrot);
   cudaFree(ctx->dmat); cudaFree(ctx->dbits); cudaFree(ctx->dsum); cudaFreeHost(ctx->hsum);
@@ -784,10 +787,14 @@ static void sym_eig32(const double *S, double *Q, double *lam) {
   }
 }
 
-// ---- unfused Steihaug-Toint loop for callback operators / preconditioners --------------------------------------------
+// ---- unfused Steihaug-Toint loop ----------------------------------------------------------------------------------------
 // Reference IterativeSolvers.h:211-424 statement for statement (no `At`, no user function: how TNT calls it), with the
-// vectors on the device: H and P are host callbacks (or the pointwise Jacobi scaling), every inner product is the exact
-// device reduction (dots_sync), every update a level-1 kernel.  Three launches + one synchronisation per inner product.
+// vectors on the device: every inner product is the exact device reduction (dots_sync), every update a level-1 kernel.
+// H is a host callback or any built-in operator (its stand-alone HVP, ob200_hvp); P is the pointwise Jacobi scaling, the
+// projected Jacobi scaling of the Stiefel model, or a host callback.  Serves the operator x preconditioner pairs the fused
+// kernels do not implement.
+extern "C" int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, double *out);
+extern "C" int ob200_stiefel_project(ob200_context *ctx, uint64_t n, uint64_t p, const double *Y, const double *Z, double *out);
 static int stpcg_generic(ob200_context *ctx, const ob200_operator *H, const ob200_precon *P, const double *g_dev,
                          const ob200_stpcg_params *prm, double *s_dev, ob200_stpcg_result *res) {
   const uint64_t N = H->n * H->p;
@@ -795,17 +802,32 @@ static int stpcg_generic(ob200_context *ctx, const ob200_operator *H, const ob20
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
   const uint64_t launches0 = ctx->launches;
-  double *r = ctx->r, *p = ctx->p0, *Hp = ctx->Hp, *vbuf = ctx->p1;
+  // (the built-in HVPs use the context's tCG vectors as their workspace: the loop keeps its own set)
+  const uint64_t Npad = (N + 31ull) & ~31ull;   // 256-byte aligned vectors (the level-1 kernels use 16-byte accesses)
+  if (ctx->gen_capacity < Npad) {
+    cudaFree(ctx->gen_vec);
+    ctx->gen_vec = nullptr;
+    ctx->gen_capacity = 0;
+    CK(cudaMalloc(&ctx->gen_vec, sizeof(double) * 5 * Npad));
+    ctx->gen_capacity = Npad;
+  }
+  double *r = ctx->gen_vec, *p = r + Npad, *Hp = p + Npad, *vbuf = Hp + Npad, *scratch = vbuf + Npad;
   const bool has_P = P && P->kind != OB200_PRECON_NONE;
   auto apply_cb = [&](ob200_apply_fn fn, void *user, const double *in, double *out) -> int {
     CK(cudaStreamSynchronize(st));
     if (fn(user, in, out)) return fail(ctx, OB200_ABORTED, "operator / preconditioner callback reported a failure");
     return OB200_OK;
   };
+  auto apply_H = [&](const double *in, double *out) -> int {                      // Hp = H(p), l.294
+    if (H->kind == OB200_OP_HOST_CALLBACK) return apply_cb(H->apply, H->apply_user, in, out);
+    return ob200_hvp(ctx, H, in, out);
+  };
   auto precondition = [&](const double *rin, double *vout) -> int {               // v = P(r), l.383-386
-    if (P->kind == OB200_PRECON_JACOBI) {
-      CK(launch_hadamard(N, P->minv_dev, rin, vout, ctx->sm_count, st));
+    if (P->kind == OB200_PRECON_JACOBI || P->kind == OB200_PRECON_STIEFEL_PROJECTED_JACOBI) {
+      const bool proj = P->kind == OB200_PRECON_STIEFEL_PROJECTED_JACOBI;
+      CK(launch_hadamard(N, P->minv_dev, rin, proj ? scratch : vout, ctx->sm_count, st));
       ctx->launches += 1;
+      if (proj) return ob200_stiefel_project(ctx, H->n, H->p, H->Y_dev, scratch, vout);
       return OB200_OK;
     }
     return apply_cb(P->apply, P->apply_user, rin, vout);
@@ -838,7 +860,7 @@ static int stpcg_generic(ob200_context *ctx, const ob200_operator *H, const ob20
   bool on_boundary = false;
   for (; it < prm->max_iterations; ++it) {                                        // l.285
     if (std::sqrt(rv) <= target) { exit_reason = OB200_EXIT_RESIDUAL; break; }    // l.290
-    if ((rc = apply_cb(H->apply, H->apply_user, p, Hp))) return rc;               // l.294
+    if ((rc = apply_H(p, Hp))) return rc;                                         // l.294
     double d3[3];
     {
       const double *aa[3] = {p, Hp, p}, *bb[3] = {Hp, Hp, p};
@@ -900,13 +922,17 @@ static int stpcg_device(ob200_context *ctx, const ob200_operator *H, const ob200
   if (rc) return rc;
   if (!H || !g_dev || !s_dev || !res) return fail(ctx, OB200_INVALID_ARGUMENT, "null argument");
   if (H->n == 0 || H->p == 0) return fail(ctx, OB200_INVALID_ARGUMENT, "empty operator");
-  if (H->kind == OB200_OP_HOST_CALLBACK || (P && P->kind == OB200_PRECON_HOST_CALLBACK)) {
-    if (H->kind != OB200_OP_HOST_CALLBACK)
-      return fail(ctx, OB200_UNSUPPORTED, "a callback preconditioner needs a callback operator (the unfused loop calls both)");
-    if (!H->apply || (P && P->kind == OB200_PRECON_HOST_CALLBACK && !P->apply))
-      return fail(ctx, OB200_INVALID_ARGUMENT, "callback operator / preconditioner without a function");
-    if (P && P->kind == OB200_PRECON_JACOBI && !P->minv_dev) return fail(ctx, OB200_INVALID_ARGUMENT, "Jacobi preconditioner without minv");
-    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "callback operators are single-GPU");
+  const int pkind = P ? P->kind : OB200_PRECON_NONE;
+  if (H->kind == OB200_OP_HOST_CALLBACK || pkind == OB200_PRECON_HOST_CALLBACK || pkind == OB200_PRECON_STIEFEL_PROJECTED_JACOBI) {
+    if (H->kind == OB200_OP_HOST_CALLBACK && !H->apply) return fail(ctx, OB200_INVALID_ARGUMENT, "callback operator without a function");
+    if (pkind == OB200_PRECON_HOST_CALLBACK && !P->apply) return fail(ctx, OB200_INVALID_ARGUMENT, "callback preconditioner without a function");
+    if ((pkind == OB200_PRECON_JACOBI || pkind == OB200_PRECON_STIEFEL_PROJECTED_JACOBI) && !P->minv_dev)
+      return fail(ctx, OB200_INVALID_ARGUMENT, "Jacobi preconditioner without minv");
+    if (pkind == OB200_PRECON_STIEFEL_PROJECTED_JACOBI && (H->kind != OB200_OP_STIEFEL_BLOCKDIAG || !H->Y_dev))
+      return fail(ctx, OB200_INVALID_ARGUMENT, "the projected Jacobi preconditioner belongs to the Stiefel operator");
+    if (pkind == OB200_PRECON_JACOBI && H->kind == OB200_OP_STIEFEL_BLOCKDIAG)
+      return fail(ctx, OB200_UNSUPPORTED, "elementwise Jacobi does not preserve the Stiefel tangent space");
+    if (ctx->cm.world > 1) return fail(ctx, OB200_UNSUPPORTED, "the unfused loop is single-GPU");
     CK(cudaSetDevice(ctx->device));
     return stpcg_generic(ctx, H, P, g_dev, prm, s_dev, res);
   }

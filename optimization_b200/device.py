@@ -334,6 +334,15 @@ class Context:
             pc.minv_dev = minv.data_ptr()
         return pc
 
+    def projected_jacobi(self, minv: torch.Tensor):
+        """OB200_PRECON_STIEFEL_PROJECTED_JACOBI: v = P_Y(minv o r) for the Stiefel operator (Y is the operator's point):
+        the tangent-space preserving form of the Jacobi scaling; selects the unfused loop with the one-launch HVP."""
+        pc = capi.Precon()
+        pc.kind = capi.PRECON_STIEFEL_PROJECTED_JACOBI
+        pc.minv_dev = minv.data_ptr()
+        pc._keep = minv
+        return pc
+
     # -- the hot path --------------------------------------------------------------
     def stpcg(self, g, H: "OperatorHandle", Delta, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
               minv=None, epsilon=1e-8, s_out=None, host=False) -> StpcgOutput:

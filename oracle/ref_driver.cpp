@@ -489,11 +489,13 @@ void ref_stiefel_retract(void *hh, const double *Y, const double *V, double *out
 
 // Stand-alone tCG on the Stiefel Hessian at Y:
 // reference STPCG with H = Hess f(Y), Frobenius inner product, optional Jacobi.
-int ref_stiefel_stpcg(void *hh, const double *Y, const double *g,
-                      const double *minv /* nullable, n*p */, double Delta,
-                      uint64_t max_iterations, double kappa_fgr, double theta,
-                      double epsilon, double *s_out, double *update_step_M_norm,
-                      uint64_t *num_iterations) {
+// projected != 0: P(x) = P_Y(minv o x), P_Y(Z) = Z - Y sym(Y^T Z) (what TNT's adapter hands to STPCG for the
+// tangent-space preserving preconditioner of ref_stiefel_tnt_precon).
+int ref_stiefel_stpcg_precon(void *hh, const double *Y, const double *g,
+                             const double *minv /* nullable, n*p */, int projected, double Delta,
+                             uint64_t max_iterations, double kappa_fgr, double theta,
+                             double epsilon, double *s_out, double *update_step_M_norm,
+                             uint64_t *num_iterations) {
   auto *h = static_cast<RefStiefel *>(hh);
   using V = HostMat;
   using M = std::nullptr_t;
@@ -516,6 +518,15 @@ int ref_stiefel_stpcg(void *hh, const double *Y, const double *g,
       oracle::parallel_ranges(N, [&](int, size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) o[i] = minv[i] * xd[i];
       });
+      if (projected) {
+        const size_t n = h->op.n, p = h->op.p;
+        std::vector<double> Gm(p * p);
+        gram(Ym.data(), out.data(), n, p, Gm.data());
+        symmetrize(Gm.data(), p);
+        V proj(N);
+        sub_right_mul(out.data(), Ym.data(), Gm.data(), n, p, proj.data());
+        out = std::move(proj);
+      }
       return std::make_pair(std::move(out), M());
     };
   try {
@@ -531,6 +542,15 @@ int ref_stiefel_stpcg(void *hh, const double *Y, const double *g,
     return 1;
   }
   return 0;
+}
+
+int ref_stiefel_stpcg(void *hh, const double *Y, const double *g,
+                      const double *minv /* nullable, n*p */, double Delta,
+                      uint64_t max_iterations, double kappa_fgr, double theta,
+                      double epsilon, double *s_out, double *update_step_M_norm,
+                      uint64_t *num_iterations) {
+  return ref_stiefel_stpcg_precon(hh, Y, g, minv, 0, Delta, max_iterations, kappa_fgr, theta, epsilon, s_out,
+                                  update_step_M_norm, num_iterations);
 }
 
 // End-to-end reference TNT on the Stiefel trace-min problem.

@@ -101,6 +101,8 @@ class RefOracle:
         L.ref_stiefel_retract.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.ref_stiefel_stpcg.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_uint64,
                                         C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
+        L.ref_stiefel_stpcg_precon.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, C.c_double, C.c_uint64,
+                                               C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
         L.ref_stpcg_diag.argtypes = [C.c_uint64, _dp, _dp, _dp, C.c_double, C.c_uint64,
                                      C.c_double, C.c_double, C.c_double, _dp, _dp, _u64p]
         L.ref_sphere_stpcg.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp,
@@ -347,13 +349,14 @@ class RefStiefel:
         return out
 
     def stpcg(self, Y, g, minv=None, Delta=1.0, max_iterations=1000, kappa_fgr=0.1, theta=0.5,
-              epsilon=1e-8):
+              epsilon=1e-8, projected=False):
+        """projected: the preconditioner is P_Y(minv o r) (tangent-space preserving) instead of minv o r."""
         s = np.zeros_like(g)
         mn = C.c_double(0)
         it = C.c_uint64(0)
-        rc = self.ora.lib.ref_stiefel_stpcg(self.h, _d(Y), _d(g), _d(minv), Delta, max_iterations,
-                                            kappa_fgr, theta, epsilon, _d(s), C.byref(mn),
-                                            C.byref(it))
+        rc = self.ora.lib.ref_stiefel_stpcg_precon(self.h, _d(Y), _d(g), _d(minv), int(bool(projected)), Delta,
+                                                   max_iterations, kappa_fgr, theta, epsilon, _d(s), C.byref(mn),
+                                                   C.byref(it))
         if rc:
             raise ValueError("std::invalid_argument from reference STPCG")
         return s, float(mn.value), int(it.value)

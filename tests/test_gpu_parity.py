@@ -310,6 +310,55 @@ def test_stiefel_full_size_vs_reference(ctx, build_oracle, which):
             assert out.exit_reason == "residual" and 20 < it_ref < 200
 
 
+@pytest.mark.parametrize("n", [512, 4099, 20000])
+def test_stiefel_projected_jacobi_vs_reference(ctx, build_oracle, n):
+    """OB200_PRECON_STIEFEL_PROJECTED_JACOBI (v = P_Y(minv o r), the preconditioner TNT's adapter TNT.h:413-426 hands
+    to STPCG for a tangent-space preserving precon): the C ABI's unfused loop with the one-launch device HVP against
+    the reference's own STPCG header with the same preconditioner functor -- counts exact, iterate within 1e-10 -- and
+    against the same loop driven through host callbacks."""
+    import torch
+    R, _ = _host_oracle()
+    if R is None:
+        pytest.skip("oracle/_ref (the compiled reference headers) did not travel with this snapshot")
+    minv_np = P.stiefel_row_scaling(n, 32)
+    for prob, kws in ((P.make_stiefel_critical(n, 32), (dict(Delta=1e6, max_iterations=60, kappa_fgr=1e-9, theta=0.),
+                                                         dict(Delta=1e6, max_iterations=3, kappa_fgr=1e-9, theta=0.))),
+                      (P.make_stiefel(n, 32, y_noise=.2), (dict(Delta=3.0, max_iterations=60, kappa_fgr=1e-3, theta=.5),))):
+        A, Y, H = stiefel_setup(ctx, prob)
+        minv = ctx.to_device(minv_np)
+        g = ctx.to_device(prob.g)
+        rs = R.stiefel(prob)
+
+        def apply_H(v, out, H=H):
+            out.copy_(ctx.hvp(H, v.contiguous()))
+
+        def apply_P(r, out, Y=Y):
+            z = minv * r
+            G = Y.t() @ z
+            out.copy_(z - Y @ (0.5 * (G + G.t())))
+
+        for kw in kws:
+            s_ref, mn_ref, it_ref = rs.stpcg(prob.Y0, prob.g, minv=minv_np, projected=True, **kw)
+            out = ctx.stpcg(g, H, minv=ctx.projected_jacobi(minv), **kw)
+            assert ctx.last_path == "generic"
+            assert out.num_iterations == it_ref, kw
+            assert rel(out.s.cpu().numpy(), s_ref) < RTOL
+            assert abs(out.update_step_M_norm - mn_ref) <= RTOL * abs(mn_ref)
+            # the step stays in the tangent space at Y: sym(Y^T s) = 0
+            YtS = (Y.t() @ out.s).cpu().numpy()
+            assert np.abs(YtS + YtS.T).max() <= 1e-12 * max(1.0, float(out.s.abs().max()))
+            cb = ctx.stpcg(g, ctx.callback_operator(n, 32, apply_H), minv=ctx.callback_precon(n, 32, apply_P), **kw)
+            # (the callbacks round differently -- torch matmul instead of the exact reductions -- so a count may move by
+            # one at a residual threshold)
+            assert abs(cb.num_iterations - out.num_iterations) <= 1
+            if cb.num_iterations == out.num_iterations:
+                assert rel(cb.s.cpu().numpy(), out.s.cpu().numpy()) < 1e-8
+    # wrong pairing is refused, not mis-computed
+    Hd = ctx.diag_operator(ctx.to_device(np.ones(n * 32)))
+    with pytest.raises(Exception):
+        ctx.stpcg(g, Hd, minv=ctx.projected_jacobi(minv), Delta=1.0)
+
+
 def test_sphere_full_size_vs_reference(ctx, build_oracle):
     """BASELINE size (config C2, n = 2^24, k = 16): same inputs on both sides (generated on the device, copied to the
     host), CG iterations capped so the CPU side finishes in seconds; counts / exits exact, iterate within 1e-10."""
