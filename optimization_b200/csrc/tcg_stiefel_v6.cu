@@ -136,9 +136,9 @@ __device__ __forceinline__ void recombine_frag8(uint32_t taddr, double (&out)[4]
 }
 
 // Grid-wide reduction barrier of the 512 work threads (rt = relative thread id): the protocol of grid_reduce_barrier
-// (common.cuh) for ONE GPU, with the CTA-level synchronisation on named barrier 1.  Row-sharded runs use the v4 kernel
-// (ob200_stpcg picks the generation), so the machine-wide exchange is not instantiated here: less code in the
-// instruction cache of the persistent loop.
+// (common.cuh) for ONE GPU, with the CTA-level synchronisation on named barrier 1.  Row-sharded runs instantiate the
+// kernel with MULTI = true and use grid_reduce_barrier_multi below; the one-GPU instantiation carries no exchange code:
+// less to hold in the instruction cache of the persistent loop (3 800 instructions, 3 us per iteration).
 __device__ __forceinline__ bool grid_reduce_barrier_w(V6Misc &ms, int rt, unsigned *counter, unsigned &gen,
                                                       int *abort_flag, const CommDev &cm, unsigned long long gphase,
                                                       u64 *set, int off, int count, RedView &view,
