@@ -120,3 +120,20 @@ def test_ctypes_mirror_matches_the_header_layout(tmp_path):
         assert int(parts[1]) == C.sizeof(cls), parts[0]
         offs = [getattr(cls, f).offset for f, _ in cls._fields_]
         assert [int(x) for x in parts[2:]] == offs, parts[0]
+
+
+def test_python_constants_equal_the_header_defines():
+    """Every OB200_OP_* / OB200_PRECON_* / OB200_EXIT_* / status value of include/optimization_b200.h has the same value
+    in the ctypes mirror (a drift would select the wrong kernel or mis-report an exit silently)."""
+    import re
+    text = open(os.path.join(ROOT, "include", "optimization_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"^#define\s+OB200_([A-Z0-9_]+)\s+(-?\d+)\b", text, re.M)}
+    assert defs["PRECON_STIEFEL_PROJECTED_JACOBI"] == 3 and defs["OP_HOST_CALLBACK"] == 6
+    checked = 0
+    for name, value in defs.items():
+        if hasattr(capi, name):
+            assert getattr(capi, name) == value, name
+            checked += 1
+    assert checked >= 12, checked
+    for name in ("PRECON_NONE", "PRECON_JACOBI", "PRECON_HOST_CALLBACK", "PRECON_STIEFEL_PROJECTED_JACOBI", "OP_HOST_CALLBACK"):
+        assert getattr(capi, name) == defs[name]
