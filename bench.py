@@ -443,8 +443,9 @@ def run_ours(args):
         t_hvp = ev0.elapsed_time(ev1) / 10
         hb = solver.H.hvp_bytes()
         hvp = {"value": hb / t_hvp / 1e6, "unit": "GB/s", "algorithmic_bytes": hb, "ms": t_hvp,
-               "what": "ob200_hvp (stand-alone Hess f(Y)[V]): exact <V,V> + ONE persistent launch of the fused kernel in "
-                       "HVP mode (contraction + Gram | projection), no host round trip before the final status read; "
+               "what": "ob200_hvp (stand-alone Hess f(Y)[V]): one prologue launch (exact <V,V>, content checksum of A, clears) + ONE "
+                       "persistent launch of the fused kernel in HVP mode (contraction + Gram | projection), no host round trip "
+                       "before the final status read; "
                        "inside the fused tCG step the HVP never runs stand-alone"}
     if sampler:   # a short default run may end between two 50 ms samples: stay under the same load until three are in
         t0 = time.time()

@@ -106,6 +106,10 @@ cudaError_t launch_rr_scale_transpose(int ns, const double *Z, const double *D, 
 cudaError_t launch_dots(unsigned long long N, int count, const double *const *a, const double *const *b,
                         u64 *set, int sm_count, cudaStream_t st);
 cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st);
+cudaError_t launch_hvp_prologue(unsigned long long N, const double *V, const unsigned short *A, unsigned long long nvec,
+                                u64 *vv_acc, unsigned long long *sum, u64 *vv_acc_next, unsigned long long *sum_next,
+                                u64 *zero_words, unsigned long long n_zero, unsigned *barrier_words,
+                                unsigned *done_counter, double *vv_out, int sm_count, cudaStream_t st);
 cudaError_t launch_axpby(unsigned long long N, double alpha, const double *x, double beta, const double *y,
                          double *out, int sm_count, cudaStream_t st);
 cudaError_t launch_hadamard(unsigned long long N, const double *d, const double *x, double *out,
@@ -165,6 +169,8 @@ struct ob200_context {
   size_t blk_stats_cap = 0;
   unsigned long long planes_sum = 0;       // checksum of the A the planes were built from
   unsigned long long *dsum = nullptr;      // device / pinned-host word for the per-solve checksum of A
+  u64 *hvp_ws = nullptr;                   // stand-alone HVP prologue: 2 x (KUL_STRIDE accumulator words + checksum word) + counter
+  int hvp_par = 0;                         // which copy the next call accumulates into
   unsigned long long *hsum = nullptr;
   int opt_tcgen05 = 1;            // 1: tcgen05 kernel v6 (warp-specialised register budgets, eigenbasis of S), 2: tcgen05 kernel v4, 0: fp64 MMA kernel
   int last_path = 0;              // 1 = tcgen05 kernel, 0 = fp64 tensor-core kernel
@@ -231,6 +237,8 @@ int ob200_create(int device, void *stream, ob200_context **out) {
   CK(cudaMalloc(&ctx->drot, sizeof(double) * 3 * 32 * 32));
   CK(cudaMalloc(&ctx->dbits, 64));
   CK(cudaMalloc(&ctx->dsum, 8));
+  CK(cudaMalloc(&ctx->hvp_ws, sizeof(u64) * (2 * (KUL_STRIDE + 1) + 1)));
+  CK(cudaMemset(ctx->hvp_ws, 0, sizeof(u64) * (2 * (KUL_STRIDE + 1) + 1)));
   CK(cudaMallocHost(&ctx->hsum, 8));
   CK(cudaMallocHost(&ctx->hres, sizeof(TcgDeviceResult)));
   CK(cudaMallocHost(&ctx->hscal, sizeof(double) * 8));
@@ -253,7 +261,7 @@ int ob200_destroy(ob200_context *ctx) {
   cudaFree(ctx->gen_vec);
   cudaFree(ctx->acc); cudaFree(ctx->barrier); cudaFree(ctx->dres); cudaFree(ctx->dscal);
   cudaFree(ctx->drot); cudaFree(ctx->yrot);
-  cudaFree(ctx->dmat); cudaFree(ctx->dbits); cudaFree(ctx->dsum); cudaFreeHost(ctx->hsum);
+  cudaFree(ctx->dmat); cudaFree(ctx->dbits); cudaFree(ctx->dsum); cudaFree(ctx->hvp_ws); cudaFreeHost(ctx->hsum);
   cudaFreeHost(ctx->hres); cudaFreeHost(ctx->hscal); cudaFreeHost(ctx->hacc); cudaFreeHost(ctx->hmat);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int r = 0; r < MAX_RANKS; ++r)
@@ -1311,13 +1319,21 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
   const unsigned long long nblk = (H->n + 127) / 128;
   int grid = ctx->sm_count;
   if ((unsigned long long)grid > nblk) grid = (int)nblk;
-  // <V,V> stays on the device: it bounds the exact fixed-point Gram of the projection
-  const double *aa[1] = {v}, *bb[1] = {v};
-  CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SCAL_WORDS, st));
-  CK(launch_dots(N, 1, aa, bb, ctx->acc, ctx->sm_count, st));
-  if ((rc = exchange(ctx, ctx->acc, 0, KUL_STRIDE))) return rc;
-  CK(launch_finalize_many(ctx->acc, 1, ctx->dscal, st));
-  ctx->launches += 2;
+  // <V,V> stays on the device: it bounds the exact fixed-point Gram of the projection.  One GPU + cached digit planes:
+  // <V,V>, the content checksum of A and every clearing the persistent kernel needs come from ONE prologue launch
+  // (hvp_prologue_kernel); otherwise the separate kernels (and the cross-rank fold of <V,V>).
+  if (ctx->opt_tcgen05 && !(ctx->planes_key == H->A_bf16_dev && ctx->planes_n == H->n)) {
+    if ((rc = ensure_planes(ctx, H->A_bf16_dev, H->n))) return rc;
+  }
+  const bool fused_prologue = ctx->opt_tcgen05 && ctx->planes_ok && ctx->cm.world == 1;
+  if (!fused_prologue) {
+    const double *aa[1] = {v}, *bb[1] = {v};
+    CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SCAL_WORDS, st));
+    CK(launch_dots(N, 1, aa, bb, ctx->acc, ctx->sm_count, st));
+    if ((rc = exchange(ctx, ctx->acc, 0, KUL_STRIDE))) return rc;
+    CK(launch_finalize_many(ctx->acc, 1, ctx->dscal, st));
+    ctx->launches += 2;
+  }
   if (!(ctx->S_cache_valid && !memcmp(ctx->S_cache, H->S_host, sizeof(ctx->S_cache)))) {
     memcpy(ctx->S_cache, H->S_host, sizeof(ctx->S_cache));
     CK(cudaMemcpyAsync(ctx->dmat, ctx->S_cache, sizeof(double) * 1024, cudaMemcpyHostToDevice, st));
@@ -1326,14 +1342,25 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
   if (ctx->opt_tcgen05) {
     // One persistent launch (the two fused phases of a CG step: contraction + Gram | projection), no host round trip:
     // the digit planes are validated ON THE DEVICE against the content checksum of A (stale: rebuild and relaunch).
-    if (!(ctx->planes_key == H->A_bf16_dev && ctx->planes_n == H->n)) {
-      if ((rc = ensure_planes(ctx, H->A_bf16_dev, H->n))) return rc;
-    }
     for (int attempt = 0; attempt < 2 && ctx->planes_ok; ++attempt) {
-      CK(cudaMemsetAsync(ctx->dsum, 0, 8, st));
-      CK(launch_stiefel_checksum(H->A_bf16_dev, nblk, ctx->dsum, ctx->sm_count, st));
-      CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SETS * ACC_WORDS, st));
-      CK(cudaMemsetAsync(ctx->barrier, 0, 64, st));
+      unsigned long long *sum_dev = ctx->dsum;
+      if (fused_prologue) {
+        const int par = ctx->hvp_par;
+        ctx->hvp_par ^= 1;
+        u64 *cur = ctx->hvp_ws + (size_t)par * (KUL_STRIDE + 1), *nxt = ctx->hvp_ws + (size_t)(par ^ 1) * (KUL_STRIDE + 1);
+        sum_dev = reinterpret_cast<unsigned long long *>(cur + KUL_STRIDE);
+        CK(launch_hvp_prologue(N, v, H->A_bf16_dev, nblk * (128ull * 128ull * 2ull / 16ull), cur, sum_dev, nxt,
+                               reinterpret_cast<unsigned long long *>(nxt + KUL_STRIDE), ctx->acc,
+                               (unsigned long long)ACC_SETS * ACC_WORDS, ctx->barrier,
+                               reinterpret_cast<unsigned *>(ctx->hvp_ws + 2 * (KUL_STRIDE + 1)), ctx->dscal, ctx->sm_count, st));
+        ctx->launches += 1;
+      } else {
+        CK(cudaMemsetAsync(ctx->dsum, 0, 8, st));
+        CK(launch_stiefel_checksum(H->A_bf16_dev, nblk, ctx->dsum, ctx->sm_count, st));
+        CK(cudaMemsetAsync(ctx->acc, 0, sizeof(u64) * ACC_SETS * ACC_WORDS, st));
+        CK(cudaMemsetAsync(ctx->barrier, 0, 64, st));
+        ctx->launches += 1;
+      }
       TcgCommon a;
       memset(&a, 0, sizeof(a));
       a.N = N;
@@ -1349,8 +1376,8 @@ int ob200_hvp(ob200_context *ctx, const ob200_operator *H, const double *v, doub
       a.result = ctx->dres;
       a.cm = ctx->cm;
       CK(launch_tcg_stiefel_tc(a, H->n, H->A_bf16_dev, H->Y_dev, ctx->dmat, H->op_norm_bound, ctx->planes,
-                               ctx->plane_exp, grid, st, 1, ctx->dsum, ctx->planes_sum));
-      ctx->launches += 2;
+                               ctx->plane_exp, grid, st, 1, sum_dev, ctx->planes_sum));
+      ctx->launches += 1;
       CK(cudaMemcpyAsync(ctx->hres, ctx->dres, sizeof(TcgDeviceResult), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (ctx->hres->status == 6) {                 // A changed under the cached planes: rebuild, once

@@ -460,6 +460,16 @@ __device__ __forceinline__ bool grid_reduce_barrier(unsigned *counter, unsigned 
   return s_ok != 0;
 }
 
+// One 16-byte vector of the content checksum of A (position-dependent 64-bit mix; the sum over the vectors is the
+// checksum: order independent, so any grid computes the same value).
+__device__ __forceinline__ unsigned long long a_checksum_term(const uint4 v, unsigned long long i) {
+  const unsigned long long lo = ((unsigned long long)v.y << 32) | v.x, hi = ((unsigned long long)v.w << 32) | v.z;
+  unsigned long long z = (lo ^ (i * 0x9E3779B97F4A7C15ull)) * 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 29;
+  z += (hi ^ ((i + 0x632BE59BD9B4E019ull) * 0x94D049BB133111EBull)) * 0xD6E8FEB86659FD93ull;
+  return z ^ (z >> 31);
+}
+
 // ---------------------------------------------------------------------------
 // fp64 tensor-core MMA (DMMA): D(8x8) += A(8x4) * B(4x8)
 //   a : A[row = lane/4][k = lane%4]

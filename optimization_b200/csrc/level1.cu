@@ -63,6 +63,68 @@ __global__ void __launch_bounds__(TCG_THREADS) dots_kernel(unsigned long long N,
   flush_scalars(sacc, set, d.count);
 }
 
+// Prologue of the stand-alone Stiefel HVP in ONE launch (it used to be seven stream operations): the exact <V,V> (bound of
+// the fixed-point projection Gram), the content checksum of A that validates the cached digit planes, and the clearing
+// of what the persistent kernel expects to be zero.  `vv_acc` / `sum` alternate between two copies from call to call:
+// this launch accumulates into one copy (zero on entry) and clears the other for the next call.  The last CTA to finish
+// rounds <V,V> once (same exact accumulator and finalisation as dots_kernel + finalize_many_kernel).
+__global__ void __launch_bounds__(TCG_THREADS)
+hvp_prologue_kernel(unsigned long long N, const double *V, const uint4 *A16, unsigned long long nvec, u64 *vv_acc,
+                    unsigned long long *sum, u64 *vv_acc_next, unsigned long long *sum_next, u64 *zero_words,
+                    unsigned long long n_zero, unsigned *barrier_words, unsigned *done_counter, double *vv_out) {
+  __shared__ u64 sacc[KUL_STRIDE];
+  __shared__ int s_last;
+  for (int i = threadIdx.x; i < KUL_STRIDE; i += blockDim.x) sacc[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long gthreads = (unsigned long long)gridDim.x * blockDim.x;
+  // (a) content checksum of A (stiefel_checksum_kernel's hash; the loads go first: they are the long pole)
+  unsigned long long acc = 0;
+  for (unsigned long long i = gtid; i < nvec; i += gthreads) acc += a_checksum_term(__ldg(A16 + i), i);
+  // (b) <V,V>, unit of determinism = 256-element run
+  const unsigned long long units = (N + 255ull) / 256ull;
+  for (unsigned long long u = (unsigned long long)blockIdx.x * TCG_WARPS + warp; u < units;
+       u += (unsigned long long)gridDim.x * TCG_WARPS) {
+    double2 x[4];
+    l1_load_run(V, N, u * 256ull, lane, x);
+    double part = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part = fma(x[i].x, x[i].x, part);
+      part = fma(x[i].y, x[i].y, part);
+    }
+    part = warp_sum(part);
+    if (lane == 0) kul_add_atomic(sacc, part);
+  }
+  // (c) what the persistent kernel and the next call expect to be zero
+  for (unsigned long long i = gtid; i < n_zero; i += gthreads) zero_words[i] = 0;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 16) barrier_words[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < KUL_STRIDE; i += blockDim.x) vv_acc_next[i] = 0;
+    if (threadIdx.x == 0) *sum_next = 0ull;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && acc) atomicAdd(sum, acc);
+  __syncthreads();
+  flush_scalars(sacc, vv_acc, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(done_counter, 1u) + 1u == gridDim.x);
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    const double v = kul_finalize_warp([vv_acc](int j) { return __ldcg(vv_acc + j); });
+    if (lane == 0) {
+      *vv_out = v;
+      *done_counter = 0u;
+    }
+  }
+}
+
 __global__ void finalize_many_kernel(const u64 *set, int count, double *out) {
   const int warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && warp < count) {
@@ -153,6 +215,15 @@ cudaError_t launch_dots(unsigned long long N, int count, const double *const *a,
     d.b[i] = i < count ? b[i] : nullptr;
   }
   dots_kernel<<<l1_grid(N, sm_count), TCG_THREADS, 0, st>>>(N, d, set);
+  return cudaGetLastError();
+}
+cudaError_t launch_hvp_prologue(unsigned long long N, const double *V, const unsigned short *A, unsigned long long nvec,
+                                u64 *vv_acc, unsigned long long *sum, u64 *vv_acc_next, unsigned long long *sum_next,
+                                u64 *zero_words, unsigned long long n_zero, unsigned *barrier_words,
+                                unsigned *done_counter, double *vv_out, int sm_count, cudaStream_t st) {
+  hvp_prologue_kernel<<<2 * sm_count, TCG_THREADS, 0, st>>>(N, V, reinterpret_cast<const uint4 *>(A), nvec, vv_acc, sum,
+                                                            vv_acc_next, sum_next, zero_words, n_zero, barrier_words,
+                                                            done_counter, vv_out);
   return cudaGetLastError();
 }
 cudaError_t launch_finalize_many(const u64 *set, int count, double *out, cudaStream_t st) {

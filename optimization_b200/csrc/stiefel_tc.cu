@@ -93,12 +93,7 @@ __global__ void __launch_bounds__(256) stiefel_checksum_kernel(const uint4 *A16,
   unsigned long long acc = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(A16 + i);
-    const unsigned long long lo = ((unsigned long long)v.y << 32) | v.x, hi = ((unsigned long long)v.w << 32) | v.z;
-    unsigned long long z = (lo ^ (i * 0x9E3779B97F4A7C15ull)) * 0xBF58476D1CE4E5B9ull;
-    z ^= z >> 29;
-    z += (hi ^ ((i + 0x632BE59BD9B4E019ull) * 0x94D049BB133111EBull)) * 0xD6E8FEB86659FD93ull;
-    acc += z ^ (z >> 31);
+    acc += a_checksum_term(__ldg(A16 + i), i);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
