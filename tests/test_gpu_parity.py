@@ -352,7 +352,7 @@ def test_stiefel_projected_jacobi_vs_reference(ctx, build_oracle, n):
             # one at a residual threshold)
             assert abs(cb.num_iterations - out.num_iterations) <= 1
             if cb.num_iterations == out.num_iterations:
-                assert rel(cb.s.cpu().numpy(), out.s.cpu().numpy()) < 1e-8
+                assert rel(cb.s.cpu().numpy(), out.s.cpu().numpy()) < 1e-6
     # wrong pairing is refused, not mis-computed
     Hd = ctx.diag_operator(ctx.to_device(np.ones(n * 32)))
     with pytest.raises(Exception):
